@@ -1,0 +1,850 @@
+// C ABI of libgonova_hift.so (include/gonova_hift.h): weight re-packing, the per-(B,T) launch plan
+// and the decode schedule.  Nothing here allocates, synchronises or aborts inside the decode calls;
+// every failure becomes a non-zero status plus gnv_last_error() text.
+//
+// Decode schedule for one [B,80,T] batch (HiFTGenerator.decode), E = bf16 | tf32 | fp32:
+//   mel NCT -> melE [B,T,Cld]                               pack kernel
+//   s -> spec [B,F,18] fp32                                 STFT kernel
+//   conv_pre            melE -> X0 = lrelu(.)               conv GEMM, activation fused
+//   per stage i (C = 256/128/64, L = 8T/40T/120T+1):
+//     source_downs[i]   spec -> F1 (raw), E0 = snake        strided conv (CUDA cores, K = 18k)
+//     source_resblock   6 conv GEMMs, residual stream F1 updated in place
+//     ups[i]            X_i -> F2 = convT + bias + F1,  E0/E1/E2 = snake_j(F2)   (polyphase GEMM)
+//     resblocks 3i+j    6 conv GEMMs each on (E_j, E3, F1); the last one accumulates F3 += x/3 and,
+//                       for j = 2, emits X_{i+1} = lrelu(F3) straight from the epilogue
+//   conv_post           X_3 -> P [B,F,18] fp32
+//   iSTFT head          P -> wav                            exp/sin/iDFT/overlap-add/clamp kernel
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/gonova_hift.h"
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "kernels.h"
+
+using namespace gnv;
+
+namespace {
+
+thread_local std::string tl_error;
+
+constexpr int kSPF = 480;
+constexpr int kMelC = 80;
+
+struct HostT {
+  const float* data = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+using WeightMap = std::map<std::string, HostT>;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline float host_round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u = (u + 0x1000u) & ~0x1FFFu;   // cvt.rna.tf32.f32: round to nearest, ties away from zero
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
+struct ConvLayer {
+  int C_in = 0, C_out = 0, k = 1, stride = 1, pad = 0, dil = 1;
+  bool transposed = false;
+  bool strided_simt = false;   // source_downs: fp32 operands, strided rows, CUDA cores only
+  int C_in_ld = 0;             // channel stride of the A operand (and of each tap in the packed W)
+  int n_taps = 0;
+  int N_valid = 0, N_total = 0, block_n = 0;
+  int w_elem = 4;              // bytes per packed weight element
+  void* w = nullptr;           // device [N_total, n_taps * C_in_ld]
+  float* bias = nullptr;       // device [C_out]
+};
+
+struct ResBlockW {
+  ConvLayer c1[3], c2[3];
+  float* a1[3] = {nullptr, nullptr, nullptr};
+  float* a2[3] = {nullptr, nullptr, nullptr};
+};
+
+enum SimtVariant { SV_FFF = 0, SV_BBB = 1, SV_FFB = 2 };
+
+struct ConvOp {
+  bool tc = false;
+  ConvTcLaunch tcl;
+  ConvGeom g;
+  EpiParams ep;
+  const void* A = nullptr;
+  const void* W = nullptr;
+  int variant = SV_FFF;
+};
+
+// Offsets (bytes) into the caller's workspace for one (B, T).
+struct WsLayout {
+  size_t melE = 0, spec = 0, X0 = 0, P = 0, H0 = 0, H1 = 0, f0 = 0;
+  size_t F1[3], F2[3], F3[3], E[3][4];
+  size_t total = 0;
+};
+
+struct Plan {
+  std::vector<ConvOp> decode_ops;
+  std::vector<ConvOp> f0_ops;
+  WsLayout lay;
+};
+
+using PlanKey = std::tuple<int, int, const void*>;
+
+}  // namespace
+
+struct gnv_decoder {
+  int device = 0, dtype = GNV_DTYPE_TF32;
+  unsigned flags = 0;
+  int eb = 4;            // bytes per activation element E
+  bool use_tc = true;
+  int snake_kind = ACT_SNAKE;
+  std::string err;
+  std::vector<void*> allocs;
+  ConvLayer conv_pre, ups[3], sdown[3], conv_post, f0c[5];
+  ResBlockW rb[9], srb[3];
+  float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr;
+  std::map<PlanKey, Plan> plans;
+  std::mutex mu;
+};
+
+namespace {
+
+int fail(gnv_handle h, const std::string& msg) {
+  tl_error = msg;
+  if (h) h->err = msg;
+  return 1;
+}
+int fail_cuda(gnv_handle h, const char* what, cudaError_t e) {
+  return fail(h, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+const int kStageC[3] = {256, 128, 64};
+const int kUpRate[3] = {8, 5, 3};
+const int kUpK[3] = {16, 11, 7};
+const int kRbK[3] = {3, 7, 11};
+const int kSrbK[3] = {7, 7, 11};
+const int kDil[3] = {1, 3, 5};
+const int kSdK[3] = {30, 6, 1};
+const int kSdS[3] = {15, 3, 1};
+const int kSdP[3] = {7, 1, 0};
+
+inline int stage_len(int i, int T) { return i == 0 ? 8 * T : (i == 1 ? 40 * T : 120 * T + 1); }
+
+int choose_block_n(int N) {
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 32;
+}
+
+// ---- weights ------------------------------------------------------------------------------------
+struct Uploader {
+  gnv_handle h;
+  bool ok = true;
+  std::string msg;
+  void* put(const void* host, size_t bytes) {
+    if (!ok) return nullptr;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, align_up(bytes, 256));
+    if (e != cudaSuccess) { ok = false; msg = std::string("cudaMalloc: ") + cudaGetErrorString(e); return nullptr; }
+    h->allocs.push_back(d);
+    e = cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { ok = false; msg = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return nullptr; }
+    return d;
+  }
+};
+
+const HostT* find(const WeightMap& wm, const std::string& name, std::string* err) {
+  auto it = wm.find(name);
+  if (it == wm.end()) { *err = "missing weight '" + name + "'"; return nullptr; }
+  return &it->second;
+}
+
+// Packs one Conv1d [Cout,Cin,k] / ConvTranspose1d [Cin,Cout,k] into the GEMM B operand
+// W[n, tap*C_in_ld + ci] (K-major rows) in the element type of the chosen arithmetic.
+bool pack_layer(gnv_handle h, Uploader& up, const WeightMap& wm, const std::string& prefix, ConvLayer& L,
+                int C_in, int C_out, int k, int stride, int pad, int dil, bool transposed, bool strided_simt,
+                std::string* err) {
+  const HostT* w = find(wm, prefix + ".weight", err);
+  const HostT* b = find(wm, prefix + ".bias", err);
+  if (!w || !b) return false;
+  const int64_t want = (int64_t)C_in * C_out * k;
+  const bool shape_ok = w->shape.size() == 3 && w->numel() == want &&
+                        w->shape[0] == (transposed ? C_in : C_out) && w->shape[1] == (transposed ? C_out : C_in) &&
+                        w->shape[2] == k && b->numel() == C_out;
+  if (!shape_ok) { *err = "bad shape for '" + prefix + "'"; return false; }
+  L.C_in = C_in; L.C_out = C_out; L.k = k; L.stride = stride; L.pad = pad; L.dil = dil;
+  L.transposed = transposed; L.strided_simt = strided_simt;
+  const int eb = strided_simt ? 4 : h->eb;
+  const int kbe = 128 / eb;
+  L.C_in_ld = strided_simt ? C_in : (int)align_up(C_in, kbe);
+  L.w_elem = eb;
+  if (transposed) {
+    L.n_taps = (k + stride - 1) / stride;
+    L.N_valid = stride * C_out;
+  } else {
+    L.n_taps = k;
+    L.N_valid = C_out;
+  }
+  L.block_n = choose_block_n(L.N_valid);
+  L.N_total = (int)align_up(L.N_valid, L.block_n);
+  const size_t K = (size_t)L.n_taps * L.C_in_ld;
+  std::vector<float> P((size_t)L.N_total * K, 0.f);
+  if (transposed) {
+    for (int r = 0; r < stride; ++r)
+      for (int j = 0; j < L.n_taps; ++j) {
+        const int kk = r + stride * j;
+        if (kk >= k) continue;
+        for (int co = 0; co < C_out; ++co)
+          for (int ci = 0; ci < C_in; ++ci)
+            P[((size_t)r * C_out + co) * K + (size_t)j * L.C_in_ld + ci] = w->data[((size_t)ci * C_out + co) * k + kk];
+      }
+  } else {
+    for (int co = 0; co < C_out; ++co)
+      for (int ci = 0; ci < C_in; ++ci)
+        for (int kk = 0; kk < k; ++kk)
+          P[(size_t)co * K + (size_t)kk * L.C_in_ld + ci] = w->data[((size_t)co * C_in + ci) * k + kk];
+  }
+  if (eb == 2) {
+    std::vector<__nv_bfloat16> Q(P.size());
+    for (size_t i = 0; i < P.size(); ++i) Q[i] = __float2bfloat16_rn(P[i]);
+    L.w = up.put(Q.data(), Q.size() * 2);
+  } else {
+    if (!strided_simt && h->dtype == GNV_DTYPE_TF32)
+      for (auto& v : P) v = host_round_tf32(v);
+    L.w = up.put(P.data(), P.size() * 4);
+  }
+  L.bias = (float*)up.put(b->data, (size_t)C_out * 4);
+  return up.ok;
+}
+
+bool put_vec(Uploader& up, const WeightMap& wm, const std::string& name, int64_t n, float** out, std::string* err) {
+  const HostT* t = find(wm, name, err);
+  if (!t) return false;
+  if (t->numel() != n) { *err = "bad shape for '" + name + "'"; return false; }
+  *out = (float*)up.put(t->data, (size_t)n * 4);
+  return up.ok;
+}
+
+bool pack_resblock(gnv_handle h, Uploader& up, const WeightMap& wm, const std::string& prefix, ResBlockW& R, int C,
+                   int k, std::string* err) {
+  for (int d = 0; d < 3; ++d) {
+    const std::string sd = std::to_string(d);
+    if (!pack_layer(h, up, wm, prefix + ".convs1." + sd, R.c1[d], C, C, k, 1, (k * kDil[d] - kDil[d]) / 2, kDil[d],
+                    false, false, err))
+      return false;
+    if (!pack_layer(h, up, wm, prefix + ".convs2." + sd, R.c2[d], C, C, k, 1, (k - 1) / 2, 1, false, false, err))
+      return false;
+    if (!put_vec(up, wm, prefix + ".activations1." + sd + ".alpha", C, &R.a1[d], err)) return false;
+    if (!put_vec(up, wm, prefix + ".activations2." + sd + ".alpha", C, &R.a2[d], err)) return false;
+  }
+  return true;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+WsLayout make_layout(const gnv_decoder* h, int B, int T) {
+  WsLayout w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  const size_t eb = h->eb;
+  const int F = 120 * T + 1;
+  w.melE = take((size_t)B * T * h->conv_pre.C_in_ld * eb);
+  w.spec = take((size_t)B * F * 18 * 4);
+  w.X0 = take((size_t)B * T * 512 * eb);
+  w.P = take((size_t)B * F * 18 * 4);
+  w.H0 = take((size_t)B * T * 512 * eb);
+  w.H1 = take((size_t)B * T * 512 * eb);
+  w.f0 = take((size_t)B * T * 4);
+  for (int i = 0; i < 3; ++i) {
+    const size_t n = (size_t)B * stage_len(i, T) * kStageC[i];
+    w.F1[i] = take(n * 4);
+    w.F2[i] = take(n * 4);
+    w.F3[i] = take(n * 4);
+    for (int j = 0; j < 4; ++j) w.E[i][j] = take(n * eb);
+  }
+  w.total = off;
+  return w;
+}
+
+// ---- op construction ----------------------------------------------------------------------------
+struct ActSpec {
+  int kind = ACT_NONE;
+  const float* alpha = nullptr;
+  float slope = 0.f;
+  void* out = nullptr;
+};
+
+struct EpiSpec {
+  const float* res = nullptr;
+  float* raw = nullptr;
+  float raw_scale = 1.f;
+  int raw_accum = 0;
+  std::vector<ActSpec> acts;
+  int len_mul = 1, len_add = 0;
+  bool reflect_front = false;   // ReflectionPad1d((1,0)) after the last upsampling
+};
+
+// Builds the GEMM geometry + fused epilogue of one layer on input [B, L_in, C_in_ld].
+std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int B, int L_in, const EpiSpec& es,
+                    ConvOp* op) {
+  ConvGeom& g = op->g;
+  EpiParams& ep = op->ep;
+  memset(&g, 0, sizeof(g));
+  memset(&ep, 0, sizeof(ep));
+  g.B = B; g.L_in = L_in; g.C_in = L.C_in; g.C_in_ld = L.C_in_ld; g.C_in_w = L.C_in_ld;
+  g.N_total = L.N_total; g.n_taps = L.n_taps;
+  ep.C_out = L.C_out; ep.N_valid = L.N_valid;
+  if (L.transposed) {
+    g.off0 = 0; g.tap_step = -1; g.in_stride = 1;
+    ep.up = L.stride; ep.pad_out = L.pad;
+    ep.L_store = L_in * L.stride;
+    g.M_rows = (ep.L_store - 1 + L.pad) / L.stride + 1;
+    ep.shift = es.reflect_front ? 1 : 0;
+    ep.dup_row = es.reflect_front ? 1 : -1;
+    ep.L_out = ep.L_store + ep.shift;
+  } else {
+    const int L_out = (L_in + 2 * L.pad - L.dil * (L.k - 1) - 1) / L.stride + 1;
+    g.off0 = -L.pad; g.tap_step = L.dil; g.in_stride = L.stride;
+    g.M_rows = L_out;
+    ep.up = 1; ep.pad_out = 0; ep.shift = 0; ep.dup_row = -1;
+    ep.L_store = L_out; ep.L_out = L_out;
+  }
+  ep.lengths = nullptr; ep.len_mul = es.len_mul; ep.len_add = es.len_add;
+  ep.bias = L.bias; ep.res = es.res; ep.raw = es.raw; ep.raw_scale = es.raw_scale; ep.raw_accum = es.raw_accum;
+  if ((int)es.acts.size() > kMaxAct) return "too many fused activations";
+  ep.n_act = (int)es.acts.size();
+  for (int i = 0; i < ep.n_act; ++i) {
+    ep.act_out[i] = es.acts[i].out;
+    ep.act_alpha[i] = es.acts[i].alpha;
+    ep.act_kind[i] = es.acts[i].kind;
+    ep.act_slope[i] = es.acts[i].slope;
+  }
+  ep.round_tf32 = h->dtype == GNV_DTYPE_TF32 ? 1 : 0;
+  op->A = A; op->W = L.w;
+  if (L.strided_simt) {
+    op->tc = false;
+    op->variant = h->eb == 2 ? SV_FFB : SV_FFF;
+    return "";
+  }
+  if (h->use_tc) {
+    op->tc = true;
+    const char* e = make_conv_tc_launch(&op->tcl, h->eb, A, L.w, L.N_total, g, ep, L.block_n);
+    return e;
+  }
+  op->tc = false;
+  op->variant = h->eb == 2 ? SV_BBB : SV_FFF;
+  return "";
+}
+
+cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
+  if (op.tc) {
+    if (!lengths) return launch_conv_tc(op.tcl, st);
+    ConvTcLaunch L = op.tcl;
+    L.p.ep.lengths = lengths;
+    return launch_conv_tc(L, st);
+  }
+  EpiParams ep = op.ep;
+  ep.lengths = lengths;
+  switch (op.variant) {
+    case SV_BBB: return launch_conv_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(op.A, op.W, op.g, ep, st);
+    case SV_FFB: return launch_conv_simt<float, float, __nv_bfloat16>(op.A, op.W, op.g, ep, st);
+    default:     return launch_conv_simt<float, float, float>(op.A, op.W, op.g, ep, st);
+  }
+}
+
+std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
+  plan->lay = make_layout(h, B, T);
+  const WsLayout& w = plan->lay;
+  char* base = (char*)ws;
+  auto P = [&](size_t off) { return (void*)(base + off); };
+  auto Fp = [&](size_t off) { return (float*)(base + off); };
+  std::string e;
+  auto add = [&](std::vector<ConvOp>& ops, const ConvLayer& L, const void* A, int L_in, const EpiSpec& es) {
+    if (!e.empty()) return;
+    ConvOp op;
+    e = make_op(h, L, A, B, L_in, es, &op);
+    if (e.empty()) ops.push_back(op);
+  };
+  const int snake = h->snake_kind;
+  const int F = 120 * T + 1;
+
+  // ---- f0 predictor: 5 x (conv k3 + ELU) ----
+  {
+    const void* in = P(w.melE);
+    size_t outs[2] = {w.H0, w.H1};
+    for (int i = 0; i < 5; ++i) {
+      EpiSpec es;
+      es.acts.push_back({ACT_ELU, nullptr, 0.f, P(outs[i & 1])});
+      add(plan->f0_ops, h->f0c[i], in, T, es);
+      in = P(outs[i & 1]);
+    }
+  }
+  // ---- decode ----
+  auto& ops = plan->decode_ops;
+  {
+    EpiSpec es;
+    es.acts.push_back({ACT_LRELU, nullptr, 0.1f, P(w.X0)});
+    add(ops, h->conv_pre, P(w.melE), T, es);
+  }
+  const void* X = P(w.X0);
+  int Lx = T;
+  for (int i = 0; i < 3; ++i) {
+    const int Ls = stage_len(i, T);
+    const int lm = i == 0 ? 8 : (i == 1 ? 40 : 120), la = i == 2 ? 1 : 0;
+    float *F1 = Fp(w.F1[i]), *F2 = Fp(w.F2[i]), *F3 = Fp(w.F3[i]);
+    void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
+    auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
+                        int j) {
+      for (int d = 0; d < 3; ++d) {
+        {
+          EpiSpec es; es.len_mul = lm; es.len_add = la;
+          es.acts.push_back({snake, R.a2[d], 0.f, E[3]});
+          add(ops, R.c1[d], EA, Ls, es);
+        }
+        EpiSpec es; es.len_mul = lm; es.len_add = la;
+        es.res = d == 0 ? res_first : raw_stream;
+        if (d < 2) {
+          es.raw = raw_stream;
+          es.acts.push_back({snake, R.a1[d + 1], 0.f, EA});
+        } else if (!final_to_sum) {
+          es.raw = raw_stream;
+        } else {
+          es.raw = F3; es.raw_scale = 1.f / 3.f; es.raw_accum = j > 0 ? 1 : 0;
+          if (j == 2) es.acts.push_back({ACT_LRELU, nullptr, i == 2 ? 0.01f : 0.1f, E[0]});
+        }
+        add(ops, R.c2[d], E[3], Ls, es);
+      }
+    };
+    // source branch
+    {
+      EpiSpec es; es.len_mul = lm; es.len_add = la;
+      es.raw = F1;
+      es.acts.push_back({snake, h->srb[i].a1[0], 0.f, E[0]});
+      add(ops, h->sdown[i], P(w.spec), F, es);
+    }
+    resblock(h->srb[i], E[0], F1, F1, false, 0);
+    // upsampling + fuse
+    {
+      EpiSpec es; es.len_mul = lm; es.len_add = la;
+      es.res = F1; es.raw = F2; es.reflect_front = (i == 2);
+      for (int j = 0; j < 3; ++j) es.acts.push_back({snake, h->rb[3 * i + j].a1[0], 0.f, E[j]});
+      add(ops, h->ups[i], X, Lx, es);
+    }
+    for (int j = 0; j < 3; ++j) resblock(h->rb[3 * i + j], E[j], F2, F1, true, j);
+    X = E[0];
+    Lx = Ls;
+  }
+  {
+    EpiSpec es; es.len_mul = 120; es.len_add = 1;
+    es.raw = Fp(w.P);
+    add(ops, h->conv_post, X, Lx, es);
+  }
+  return e;
+}
+
+int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, Plan** out) {
+  if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
+  if (!ws) return fail(h, "workspace is NULL");
+  if (((uintptr_t)ws & 1023) != 0) return fail(h, "workspace must be 1024-byte aligned");
+  std::lock_guard<std::mutex> lk(h->mu);
+  PlanKey key(B, T, ws);
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    Plan p;
+    std::string e = build_plan(h, B, T, ws, &p);
+    if (!e.empty()) return fail(h, e);
+    if (h->plans.size() > 64) h->plans.clear();
+    it = h->plans.emplace(key, std::move(p)).first;
+  }
+  if (ws_bytes < it->second.lay.total) return fail(h, "workspace too small for (B, T)");
+  *out = &it->second;
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+#define GNV_CK(h, what, expr)                                  \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return fail_cuda(h, what, _e);      \
+  } while (0)
+
+int run_f0(gnv_handle h, Plan* plan, const float* mel, const int* lengths, int B, int T, float* f0, char* ws,
+           bool pack_mel, cudaStream_t st) {
+  const WsLayout& w = plan->lay;
+  if (pack_mel)
+    GNV_CK(h, "pack mel", launch_nct_to_nlc(mel, B, kMelC, T, lengths, ws + w.melE, h->conv_pre.C_in_ld, h->eb,
+                                            h->dtype == GNV_DTYPE_TF32, st));
+  for (const ConvOp& op : plan->f0_ops) GNV_CK(h, "f0 conv", run_op(op, lengths, st));
+  const void* hl = ws + (plan->f0_ops.size() % 2 ? w.H0 : w.H1);
+  GNV_CK(h, "f0 head", launch_f0_head(hl, h->eb, B * T, 512, h->f0_w, h->f0_b, f0, st));
+  return 0;
+}
+
+int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const int* lengths, int B, int T,
+               float* wav, char* ws, bool pack_mel, cudaStream_t st) {
+  const WsLayout& w = plan->lay;
+  if (pack_mel)
+    GNV_CK(h, "pack mel", launch_nct_to_nlc(mel, B, kMelC, T, lengths, ws + w.melE, h->conv_pre.C_in_ld, h->eb,
+                                            h->dtype == GNV_DTYPE_TF32, st));
+  GNV_CK(h, "stft", launch_stft(s, B, T * kSPF, lengths, (float*)(ws + w.spec), st));
+  for (const ConvOp& op : plan->decode_ops) GNV_CK(h, "conv", run_op(op, lengths, st));
+  GNV_CK(h, "istft", launch_istft((const float*)(ws + w.P), B, 120 * T + 1, lengths, 0.99f, wav, st));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int gnv_abi_version(void) { return GNV_ABI_VERSION; }
+
+const char* gnv_last_error(gnv_handle h) { return h ? h->err.c_str() : tl_error.c_str(); }
+
+void gnv_destroy(gnv_handle h) {
+  if (!h) return;
+  {
+    DeviceGuard dg(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+  }
+  delete h;
+}
+
+int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, unsigned flags, gnv_handle* out) {
+  if (!out) return fail(nullptr, "out handle is NULL");
+  *out = nullptr;
+  if (!weights || n_weights <= 0) return fail(nullptr, "no weights given");
+  if (dtype != GNV_DTYPE_TF32 && dtype != GNV_DTYPE_BF16 && dtype != GNV_DTYPE_FP32)
+    return fail(nullptr, "unknown dtype");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess) return fail_cuda(nullptr, "cudaGetDeviceCount", ce);
+  if (device < 0 || device >= ndev) return fail(nullptr, "no such CUDA device");
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, device);
+  if (ce != cudaSuccess) return fail_cuda(nullptr, "cudaGetDeviceProperties", ce);
+  if (prop.major != 10) return fail(nullptr, "libgonova_hift is built for sm_100a (B200) only; found sm_" +
+                                                 std::to_string(prop.major) + std::to_string(prop.minor));
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(nullptr, "cudaSetDevice failed");
+
+  WeightMap wm;
+  for (int i = 0; i < n_weights; ++i) {
+    const GnvWeight& g = weights[i];
+    if (!g.name || !g.data || g.ndim < 1 || g.ndim > 4) return fail(nullptr, "malformed GnvWeight entry");
+    HostT t;
+    t.data = g.data;
+    for (int d = 0; d < g.ndim; ++d) t.shape.push_back(g.shape[d]);
+    wm[g.name] = t;
+  }
+
+  gnv_decoder* h = new gnv_decoder();
+  h->device = device; h->dtype = dtype; h->flags = flags;
+  h->eb = dtype == GNV_DTYPE_BF16 ? 2 : 4;
+  h->use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV);
+  h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
+  Uploader up{h};
+  std::string err;
+  bool ok = true;
+  ok = ok && pack_layer(h, up, wm, "conv_pre", h->conv_pre, 80, 512, 7, 1, 3, 1, false, false, &err);
+  for (int i = 0; ok && i < 3; ++i) {
+    const std::string si = std::to_string(i);
+    const int cin = 512 >> i, cout = 256 >> i;
+    ok = ok && pack_layer(h, up, wm, "ups." + si, h->ups[i], cin, cout, kUpK[i], kUpRate[i],
+                          (kUpK[i] - kUpRate[i]) / 2, 1, true, false, &err);
+    ok = ok && pack_layer(h, up, wm, "source_downs." + si, h->sdown[i], 18, cout, kSdK[i], kSdS[i], kSdP[i], 1, false,
+                          true, &err);
+    ok = ok && pack_resblock(h, up, wm, "source_resblocks." + si, h->srb[i], cout, kSrbK[i], &err);
+    for (int j = 0; ok && j < 3; ++j)
+      ok = ok && pack_resblock(h, up, wm, "resblocks." + std::to_string(3 * i + j), h->rb[3 * i + j], cout, kRbK[j],
+                               &err);
+  }
+  ok = ok && pack_layer(h, up, wm, "conv_post", h->conv_post, 64, 18, 7, 1, 3, 1, false, false, &err);
+  for (int i = 0; ok && i < 5; ++i)
+    ok = ok && pack_layer(h, up, wm, "f0_predictor.condnet." + std::to_string(2 * i), h->f0c[i], i == 0 ? 80 : 512, 512,
+                          3, 1, 1, 1, false, false, &err);
+  ok = ok && put_vec(up, wm, "f0_predictor.classifier.weight", 512, &h->f0_w, &err);
+  ok = ok && put_vec(up, wm, "f0_predictor.classifier.bias", 1, &h->f0_b, &err);
+  ok = ok && put_vec(up, wm, "m_source.l_linear.weight", 9, &h->lin_w, &err);
+  ok = ok && put_vec(up, wm, "m_source.l_linear.bias", 1, &h->lin_b, &err);
+  if (!ok || !up.ok) {
+    std::string m = !err.empty() ? err : up.msg;
+    gnv_destroy(h);
+    return fail(nullptr, "gnv_create: " + m);
+  }
+  if (h->use_tc) {
+    ce = conv_tc_init();
+    if (ce != cudaSuccess) {
+      gnv_destroy(h);
+      return fail_cuda(nullptr, "conv_tc_init", ce);
+    }
+    if (!get_encode_tiled()) {
+      gnv_destroy(h);
+      return fail(nullptr, "driver does not export cuTensorMapEncodeTiled");
+    }
+  }
+  *out = h;
+  return 0;
+}
+
+int gnv_workspace_bytes(gnv_handle h, int B, int T, size_t* out_bytes) {
+  if (!h || !out_bytes) return fail(h, "NULL argument");
+  if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
+  *out_bytes = make_layout(h, B, T).total;
+  return 0;
+}
+
+int gnv_f0(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T, float* f0, void* workspace,
+           size_t workspace_bytes, void* stream) {
+  if (!h || !mel || !f0) return fail(h, "NULL argument");
+  DeviceGuard dg(h->device);
+  Plan* plan = nullptr;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  return run_f0(h, plan, mel, lengths, B, T, f0, (char*)workspace, true, (cudaStream_t)stream);
+}
+
+int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
+               float* s, void* stream) {
+  if (!h || !f0 || !s) return fail(h, "NULL argument");
+  if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
+  DeviceGuard dg(h->device);
+  GNV_CK(h, "source", launch_source(f0, B, T, seed, phase_vec, noise, h->lin_w, h->lin_b, s, (cudaStream_t)stream));
+  return 0;
+}
+
+int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* lengths, int B, int T, float* wav,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !mel || !s || !wav) return fail(h, "NULL argument");
+  DeviceGuard dg(h->device);
+  Plan* plan = nullptr;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  return run_decode(h, plan, mel, s, lengths, B, T, wav, (char*)workspace, true, (cudaStream_t)stream);
+}
+
+int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int cache_len, const int32_t* lengths,
+                  int B, int T, uint64_t seed, float* wav, float* s_out, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  if (!h || !mel || !wav || !s_out) return fail(h, "NULL argument");
+  if (cache_len < 0 || (cache_len > 0 && !cache_source)) return fail(h, "bad cache_source");
+  DeviceGuard dg(h->device);
+  Plan* plan = nullptr;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* f0 = (float*)(ws + plan->lay.f0);
+  if (int rc = run_f0(h, plan, mel, lengths, B, T, f0, ws, true, st)) return rc;
+  GNV_CK(h, "source", launch_source(f0, B, T, seed, nullptr, nullptr, h->lin_w, h->lin_b, s_out, st));
+  const size_t L = (size_t)T * kSPF;
+  if (cache_len > 0) {
+    const size_t n = (size_t)cache_len < L ? (size_t)cache_len : L;
+    GNV_CK(h, "cache_source copy", cudaMemcpy2DAsync(s_out, L * 4, cache_source, (size_t)cache_len * 4, n * 4, B,
+                                                     cudaMemcpyDeviceToDevice, st));
+  }
+  return run_decode(h, plan, mel, s_out, lengths, B, T, wav, ws, false, st);
+}
+
+int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, const float* fade_w, int rows, int n,
+                 int fade, float limit, int16_t* out_i16, float* out_f32, int64_t out_stride, void* stream) {
+  if (!cur || (!out_i16 && !out_f32)) return fail(nullptr, "NULL argument");
+  if (rows < 0 || n < 0 || fade < 0) return fail(nullptr, "negative size");
+  if (fade > n) fade = n;
+  cudaError_t e = launch_pcm_tail(cur, cur_stride, prev_tail, fade_w, rows, n, fade, limit, out_i16, out_f32,
+                                  out_stride, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "pcm_tail", e);
+  return 0;
+}
+
+// ---- unit-test hooks ----------------------------------------------------------------------------
+namespace {
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  void* get(size_t bytes, cudaError_t* e) {
+    void* d = nullptr;
+    *e = cudaMalloc(&d, align_up(bytes ? bytes : 1, 1024));
+    if (*e == cudaSuccess) p.push_back(d);
+    return d;
+  }
+};
+}  // namespace
+
+int gnv_stft(const float* s, int B, int L, float* spec_nct, void* stream) {
+  if (!s || !spec_nct || B <= 0 || L < 16 || L % 4) return fail(nullptr, "gnv_stft: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int F = L / 4 + 1;
+  Scratch sc;
+  cudaError_t e;
+  float* nlc = (float*)sc.get((size_t)B * F * 18 * 4, &e);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+  GNV_CK(nullptr, "stft", launch_stft(s, B, L, nullptr, nlc, st));
+  GNV_CK(nullptr, "unpack", launch_nlc_to_nct(nlc, B, F, 18, 18, 4, spec_nct, st));
+  GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gnv_istft(const float* x_nct, int B, int F, float limit, float* wav, void* stream) {
+  if (!x_nct || !wav || B <= 0 || F < 2) return fail(nullptr, "gnv_istft: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch sc;
+  cudaError_t e;
+  float* nlc = (float*)sc.get((size_t)B * F * 18 * 4, &e);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+  GNV_CK(nullptr, "pack", launch_nct_to_nlc(x_nct, B, 18, F, nullptr, nlc, 18, 4, 0, st));
+  GNV_CK(nullptr, "istft", launch_istft(nlc, B, F, nullptr, limit, wav, st));
+  GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const float* x, int B, int Cin, int Lin,
+               const float* w_host, const float* bias_host, int Cout, int k, int stride, int pad, int dil, int act,
+               const float* alpha_host, float slope, const float* res_nct, float* y_nct, int Lout, void* stream) {
+  if (!x || !w_host || !y_nct) return fail(nullptr, "gnv_conv1d: NULL argument");
+  if (dtype != GNV_DTYPE_TF32 && dtype != GNV_DTYPE_BF16 && dtype != GNV_DTYPE_FP32)
+    return fail(nullptr, "unknown dtype");
+  DeviceGuard dg(device);
+  if (!dg.ok) return fail(nullptr, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  gnv_decoder tmp;
+  tmp.device = device; tmp.dtype = dtype; tmp.flags = flags;
+  tmp.eb = dtype == GNV_DTYPE_BF16 ? 2 : 4;
+  const bool strided = !transposed && stride != 1;
+  tmp.use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV) && !strided;
+  struct Cleanup {
+    gnv_decoder* d;
+    ~Cleanup() { for (void* p : d->allocs) cudaFree(p); }
+  } cleanup{&tmp};
+  if (tmp.use_tc) {
+    cudaError_t ce = conv_tc_init();
+    if (ce != cudaSuccess) return fail_cuda(nullptr, "conv_tc_init", ce);
+  }
+  std::vector<float> zero_bias((size_t)Cout, 0.f);
+  WeightMap wm;
+  HostT tw, tb;
+  tw.data = w_host;
+  tw.shape = transposed ? std::vector<int64_t>{Cin, Cout, k} : std::vector<int64_t>{Cout, Cin, k};
+  tb.data = bias_host ? bias_host : zero_bias.data();
+  tb.shape = {Cout};
+  wm["l.weight"] = tw;
+  wm["l.bias"] = tb;
+  Uploader up{&tmp};
+  ConvLayer L;
+  std::string err;
+  if (!pack_layer(&tmp, up, wm, "l", L, Cin, Cout, k, stride, pad, dil, transposed != 0, strided, &err))
+    return fail(nullptr, "gnv_conv1d: " + (err.empty() ? up.msg : err));
+  const int expect = transposed ? Lin * stride : (Lin + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  if (transposed && (k - stride) != 2 * pad) return fail(nullptr, "gnv_conv1d: convT needs pad == (k - stride) / 2");
+  if (expect != Lout) return fail(nullptr, "gnv_conv1d: Lout does not match the layer geometry");
+  float* alpha_d = nullptr;
+  if (alpha_host) alpha_d = (float*)up.put(alpha_host, (size_t)Cout * 4);
+  if (!up.ok) return fail(nullptr, up.msg);
+  Scratch sc;
+  cudaError_t e;
+  const int a_eb = strided ? 4 : tmp.eb;
+  void* A = sc.get((size_t)B * Lin * L.C_in_ld * a_eb, &e);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+  float* raw = (float*)sc.get((size_t)B * Lout * Cout * 4, &e);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+  void* actb = sc.get((size_t)B * Lout * Cout * tmp.eb, &e);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+  float* res = nullptr;
+  if (res_nct) {
+    res = (float*)sc.get((size_t)B * Lout * Cout * 4, &e);
+    if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
+    GNV_CK(nullptr, "pack res", launch_nct_to_nlc(res_nct, B, Cout, Lout, nullptr, res, Cout, 4, 0, st));
+  }
+  GNV_CK(nullptr, "pack x", launch_nct_to_nlc(x, B, Cin, Lin, nullptr, A, L.C_in_ld, a_eb,
+                                              (!strided && dtype == GNV_DTYPE_TF32) ? 1 : 0, st));
+  EpiSpec es;
+  es.res = res;
+  es.raw = raw;
+  if (act != GNV_ACT_NONE) es.acts.push_back({act, alpha_d, slope, actb});
+  ConvOp op;
+  std::string me = make_op(&tmp, L, A, B, Lin, es, &op);
+  if (!me.empty()) return fail(nullptr, "gnv_conv1d: " + me);
+  GNV_CK(nullptr, "conv", run_op(op, nullptr, st));
+  if (act != GNV_ACT_NONE)
+    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(actb, B, Lout, Cout, Cout, tmp.eb, y_nct, st));
+  else
+    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(raw, B, Lout, Cout, Cout, 4, y_nct, st));
+  GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace, float* out_nct,
+                  size_t out_capacity_elems, int64_t* out_shape3, void* stream) {
+  if (!h || !name || !workspace || !out_nct || !out_shape3) return fail(h, "NULL argument");
+  DeviceGuard dg(h->device);
+  const WsLayout w = make_layout(h, B, T);
+  char* ws = (char*)workspace;
+  const std::string n(name);
+  const float* src = nullptr;
+  int L = 0, C = 0;
+  const int F = 120 * T + 1;
+  if (n == "s_stft") { src = (const float*)(ws + w.spec); L = F; C = 18; }
+  else if (n == "conv_post") { src = (const float*)(ws + w.P); L = F; C = 18; }
+  else if (n.size() == 5 && n.compare(0, 4, "fuse") == 0 && n[4] >= '0' && n[4] <= '2') {
+    const int i = n[4] - '0';
+    src = (const float*)(ws + w.F2[i]); L = stage_len(i, T); C = kStageC[i];
+  } else if (n.size() == 6 && n.compare(0, 5, "stage") == 0 && n[5] >= '0' && n[5] <= '2') {
+    const int i = n[5] - '0';
+    src = (const float*)(ws + w.F3[i]); L = stage_len(i, T); C = kStageC[i];
+  } else {
+    return fail(h, "unknown tap '" + n + "'");
+  }
+  if ((size_t)B * L * C > out_capacity_elems) return fail(h, "tap output buffer too small");
+  out_shape3[0] = B; out_shape3[1] = C; out_shape3[2] = L;
+  GNV_CK(h, "tap", launch_nlc_to_nct(src, B, L, C, C, 4, out_nct, (cudaStream_t)stream));
+  return 0;
+}
+
+int gnv_decode_launches(gnv_handle h, int B, int T, int* out) {
+  if (!h || !out) return fail(h, "NULL argument");
+  (void)B; (void)T;
+  // pack mel + STFT + conv_pre + 3 x (source_down + 6 + ups + 18) + conv_post + iSTFT
+  *out = 2 + 1 + 3 * (1 + 6 + 1 + 18) + 1 + 1;
+  return 0;
+}
+
+int gnv_inference_launches(gnv_handle h, int B, int T, int* out) {
+  if (!h || !out) return fail(h, "NULL argument");
+  int d = 0;
+  gnv_decode_launches(h, B, T, &d);
+  *out = d + 5 /*f0 convs*/ + 1 /*f0 head*/ + 1 /*source*/;   // the mel pack is shared
+  return 0;
+}
+
+}  // extern "C"

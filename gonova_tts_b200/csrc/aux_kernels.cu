@@ -1,0 +1,444 @@
+// Bandwidth-bound kernels of the decoder: layout packers, f0 head, NSF source, STFT, iSTFT +
+// overlap-add, and the streaming PCM tail.  All are HBM-bound byte movers: coalesced, vectorised,
+// staged through shared memory where a thread's natural access would be strided.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gnv {
+
+// ------------------------------------------------------------------------------------------------
+// layout packers
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void nct_to_nlc_kernel(const float* __restrict__ in, int C, int L, const int* __restrict__ lengths,
+                                  E* __restrict__ out, int C_ld, int round) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int Lb = lengths ? min(L, lengths[b]) : L;       // rows past the utterance's end become zeros
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    tile[i][tx] = (c < C && l < Lb) ? in[((size_t)b * C + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    if (l < L && c < C_ld) {
+      float v = tile[tx][i];
+      if constexpr (sizeof(E) == 4) { if (round) v = round_tf32(v); }
+      ElemIO<E>::store(out + ((size_t)b * L + l) * C_ld + c, v);
+    }
+  }
+}
+
+template <typename E>
+__global__ void nlc_to_nct_kernel(const E* __restrict__ in, int L, int C, int C_ld, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i, c = c0 + tx;
+    tile[i][tx] = (l < L && c < C) ? ElemIO<E>::load(in + ((size_t)b * L + l) * C_ld + c) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, l = l0 + tx;
+    if (c < C && l < L) out[((size_t)b * C + c) * L + l] = tile[tx][i];
+  }
+}
+
+cudaError_t launch_nct_to_nlc(const float* in, int B, int C, int L, const int* lengths, void* out, int C_ld,
+                              int elem_bytes, int round, cudaStream_t st) {
+  dim3 grid((L + 31) / 32, (C_ld + 31) / 32, B), block(32, 8);
+  if (elem_bytes == 2)
+    nct_to_nlc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, C, L, lengths, (__nv_bfloat16*)out, C_ld, 0);
+  else
+    nct_to_nlc_kernel<float><<<grid, block, 0, st>>>(in, C, L, lengths, (float*)out, C_ld, round);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nlc_to_nct(const void* in, int B, int L, int C, int C_ld, int elem_bytes, float* out,
+                              cudaStream_t st) {
+  dim3 grid((L + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (elem_bytes == 2)
+    nlc_to_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, L, C, C_ld, out);
+  else
+    nlc_to_nct_kernel<float><<<grid, block, 0, st>>>((const float*)in, L, C, C_ld, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// f0 head: |Linear(512 -> 1)|, one warp per (b, t) row
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void f0_head_kernel(const E* __restrict__ h, int rows, int C, const float* __restrict__ w,
+                               const float* __restrict__ bias, float* __restrict__ f0) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const E* p = h + (size_t)row * C;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(ElemIO<E>::load(p + c), w[c], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) f0[row] = fabsf(acc + bias[0]);
+}
+
+cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int C, const float* w, const float* bias,
+                           float* f0, cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
+  if (elem_bytes == 2)
+    f0_head_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)h, rows, C, w, bias, f0);
+  else
+    f0_head_kernel<float><<<grid, block, 0, st>>>((const float*)h, rows, C, w, bias, f0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// NSF harmonic source (SineGen + SourceModuleHnNSF).  f0 is piecewise constant over a mel frame
+// (nearest x480 upsampling), so the running phase cumsum(f0*h/24000) at sample j of frame t is
+//   h * ( sum_{t'<t} f0[t']/50  +  (j+1) * f0[t]/24000 )
+// The frame prefix is reduced in fp64 by every block for its own frames (T <= a few thousand), so
+// the phase never loses precision however long the utterance is; the [9, 480T] harmonic bank
+// lives in registers only.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(uint32_t x) {      // (0, 1]
+  return (__uint2float_rn(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+constexpr int kSrcFramesPerBlock = 4;
+constexpr int kSPF = 480;
+
+__global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f0, int T, uint64_t seed,
+                                                      const float* __restrict__ phase_vec,
+                                                      const float* __restrict__ noise,
+                                                      const float* __restrict__ lin_w,
+                                                      const float* __restrict__ lin_b, float* __restrict__ s) {
+  __shared__ double red[8];
+  __shared__ double base_s[kSrcFramesPerBlock];
+  __shared__ float f0_s[kSrcFramesPerBlock];
+  __shared__ float phi_s[9], lw_s[9];
+  const int b = blockIdx.y, t0 = blockIdx.x * kSrcFramesPerBlock;
+  const float* f0b = f0 + (size_t)b * T;
+  double part = 0.0;
+  for (int t = threadIdx.x; t < t0; t += blockDim.x) part += (double)f0b[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  if (threadIdx.x < 9) {
+    float ph;
+    if (phase_vec) {
+      ph = phase_vec[b * 9 + threadIdx.x];
+    } else if (threadIdx.x == 0) {
+      ph = 0.f;                                          // the fundamental keeps phase 0
+    } else {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)b, 0xFFFFFFFFu, threadIdx.x, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      ph = (2.f * u01(r[0]) - 1.f) * 3.14159265358979f;
+    }
+    phi_s[threadIdx.x] = ph;
+    lw_s[threadIdx.x] = lin_w[threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < 8; ++i) acc += red[i];
+    acc /= 50.0;                                         // 480 / 24000 per frame
+    for (int i = 0; i < kSrcFramesPerBlock; ++i) {
+      const float f = (t0 + i < T) ? f0b[t0 + i] : 0.f;
+      base_s[i] = acc - floor(acc);
+      f0_s[i] = f;
+      acc += (double)f / 50.0;
+    }
+  }
+  __syncthreads();
+  const float lb = lin_b[0];
+  const size_t L = (size_t)T * kSPF;
+  for (int i = threadIdx.x; i < kSrcFramesPerBlock * kSPF; i += blockDim.x) {
+    const int fi = i / kSPF, j = i - fi * kSPF;
+    const int t = t0 + fi;
+    if (t >= T) break;
+    const size_t n = (size_t)t * kSPF + j;
+    const float f = f0_s[fi];
+    const double base = base_s[fi] + (double)(j + 1) * ((double)f / 24000.0);
+    const float uv = f > 10.f ? 1.f : 0.f;
+    const float namp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
+    float nz[12];
+    if (!noise) {
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)n, (uint32_t)(n >> 32) ^ ((uint32_t)b << 8), (uint32_t)g, 0u, (uint32_t)seed,
+                      (uint32_t)(seed >> 32), r);
+        const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
+        float s0, c0, s1, c1;
+        __sincosf(6.2831853f * u01(r[1]), &s0, &c0);
+        __sincosf(6.2831853f * u01(r[3]), &s1, &c1);
+        nz[4 * g + 0] = r0 * c0; nz[4 * g + 1] = r0 * s0; nz[4 * g + 2] = r1 * c1; nz[4 * g + 3] = r1 * s1;
+      }
+    }
+    float acc = lb;
+#pragma unroll
+    for (int h = 0; h < 9; ++h) {
+      const double hp = (double)(h + 1) * base;
+      const float frac = (float)(hp - floor(hp));
+      const float sw = 0.1f * sinf(6.283185307179586f * frac + phi_s[h]);
+      const float nv = noise ? noise[((size_t)b * 9 + h) * L + n] : nz[h];
+      acc = fmaf(lw_s[h], sw * uv + namp * nv, acc);
+    }
+    s[(size_t)b * L + n] = tanhf(acc);
+  }
+}
+
+cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
+                          const float* lin_w, const float* lin_b, float* s, cudaStream_t st) {
+  dim3 grid((T + kSrcFramesPerBlock - 1) / kSrcFramesPerBlock, B);
+  source_kernel<<<grid, 256, 0, st>>>(f0, T, seed, phase_vec, noise, lin_w, lin_b, s);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// STFT (n_fft 16, hop 4, periodic Hann, center=True with reflect padding) -> [B, F, 18]
+// (9 real parts then 9 imaginary parts per frame, the channel order of torch.cat([real, imag], 1)).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStftFrames = 256;
+
+__global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restrict__ s, int L,
+                                                           const int* __restrict__ lengths,
+                                                           float* __restrict__ spec) {
+  __shared__ float x_s[kStftFrames * 4 + 12];
+  __shared__ float cw[9][16], sw[9][16];
+  __shared__ float out_s[kStftFrames * 18];
+  const int b = blockIdx.y, fb = blockIdx.x * kStftFrames;
+  const int F = L / 4 + 1;
+  const int Lb = lengths ? min(L, lengths[b] * kSPF) : L;     // this utterance's samples
+  const int Fb = Lb / 4 + 1;
+  const float* sb = s + (size_t)b * L;
+  for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
+    const int k = i / 16, n = i % 16;
+    const float win = 0.5f - 0.5f * cospif((float)n / 8.f);
+    const float ang = (float)((k * n) % 16) / 8.f;            // exact argument reduction
+    cw[k][n] = win * cospif(ang);
+    sw[k][n] = -win * sinpif(ang);
+  }
+  for (int i = threadIdx.x; i < kStftFrames * 4 + 12; i += blockDim.x) {
+    int idx = fb * 4 - 8 + i;
+    if (idx < 0) idx = -idx;
+    if (idx >= Lb) idx = 2 * (Lb - 1) - idx;
+    x_s[i] = (idx >= 0 && idx < Lb) ? sb[idx] : 0.f;
+  }
+  __syncthreads();
+  const int f = fb + threadIdx.x;
+  float x[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) x[n] = x_s[threadIdx.x * 4 + n];
+  const bool live = f < Fb;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      re = fmaf(x[n], cw[k][n], re);
+      im = fmaf(x[n], sw[k][n], im);
+    }
+    out_s[threadIdx.x * 18 + k] = live ? re : 0.f;
+    out_s[threadIdx.x * 18 + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
+  }
+  __syncthreads();
+  const int nf = min(kStftFrames, F - fb);
+  float* ob = spec + ((size_t)b * F + fb) * 18;
+  for (int i = threadIdx.x; i < nf * 18; i += blockDim.x) ob[i] = out_s[i];
+}
+
+cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, float* spec_nlc, cudaStream_t st) {
+  const int F = L / 4 + 1;
+  dim3 grid((F + kStftFrames - 1) / kStftFrames, B);
+  stft_kernel<<<grid, kStftFrames, 0, st>>>(s, L, lengths, spec_nlc);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// iSTFT head: mag = min(exp(x[:9]), 100), ph = sin(x[9:]), X = mag*exp(i*ph); inverse 16-point real
+// DFT per frame, synthesis window, 4-frame overlap-add, division by the window envelope, trim of the
+// 8-sample centre padding, clamp(+-limit).  A block owns 253 frames' worth of output (1012 samples)
+// and recomputes the 3 halo frames it overlaps with, so there is no inter-block exchange.
+// ------------------------------------------------------------------------------------------------
+constexpr int kIstftThreads = 256;
+constexpr int kIstftNew = kIstftThreads - 3;
+
+__global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __restrict__ x, int F,
+                                                              const int* __restrict__ lengths, float limit,
+                                                              float* __restrict__ wav) {
+  __shared__ float xin[kIstftThreads * 18];
+  __shared__ float fr[kIstftThreads][17];
+  __shared__ float cb[9][16], sb[9][16], w2[16];
+  const int b = blockIdx.y;
+  const int L = 4 * (F - 1);
+  const int Fb = lengths ? min(F, lengths[b] * (kSPF / 4) + 1) : F;
+  const int Lb = 4 * (Fb - 1);
+  const int m0 = blockIdx.x * (kIstftNew * 4);
+  const int fbase = m0 / 4 - 1;
+  for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
+    const int k = i / 16, n = i % 16;
+    const float win = 0.5f - 0.5f * cospif((float)n / 8.f);
+    const float ck = (k == 0 || k == 8) ? 1.f : 2.f;
+    const float ang = (float)((k * n) % 16) / 8.f;
+    cb[k][n] = win * ck * cospif(ang) * (1.f / 16.f);
+    sb[k][n] = (k == 0 || k == 8) ? 0.f : -win * ck * sinpif(ang) * (1.f / 16.f);
+    if (k == 0) w2[n] = win * win;
+  }
+  {
+    const long long lo = (long long)fbase * 18, total = (long long)F * 18;
+    const float* xb = x + (size_t)b * F * 18;
+    for (int i = threadIdx.x; i < kIstftThreads * 18; i += blockDim.x) {
+      const long long g = lo + i;
+      xin[i] = (g >= 0 && g < total) ? xb[g] : 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int f = fbase + threadIdx.x;
+    float re[9], im[9];
+    const bool live = f >= 0 && f < Fb;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float mag = fminf(expf(xin[threadIdx.x * 18 + k]), 100.f);
+      const float ph = sinf(xin[threadIdx.x * 18 + 9 + k]);
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      re[k] = live ? mag * cs : 0.f;
+      im[k] = live ? mag * sn : 0.f;
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        acc = fmaf(re[k], cb[k][n], acc);
+        acc = fmaf(im[k], sb[k][n], acc);
+      }
+      fr[threadIdx.x][n] = acc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kIstftNew) {
+    const int m = m0 + 4 * threadIdx.x;
+    if (m < L) {
+      const int fhi = m0 / 4 + 2 + threadIdx.x;      // newest frame covering padded sample m + 8
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float acc = 0.f, env = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = fhi - j;
+          if (f >= 0 && f < Fb) {
+            acc += fr[threadIdx.x + 3 - j][e + 4 * j];
+            env += w2[e + 4 * j];
+          }
+        }
+        float v = (m + e < Lb) ? acc / env : 0.f;
+        o[e] = fminf(fmaxf(v, -limit), limit);
+      }
+      *reinterpret_cast<float4*>(wav + (size_t)b * L + m) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+cudaError_t launch_istft(const float* x_nlc, int B, int F, const int* lengths, float limit, float* wav,
+                         cudaStream_t st) {
+  const int L = 4 * (F - 1);
+  if (L <= 0) return cudaSuccess;
+  dim3 grid((L + kIstftNew * 4 - 1) / (kIstftNew * 4), B);
+  istft_kernel<<<grid, kIstftThreads, 0, st>>>(x_nlc, F, lengths, limit, wav);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming tail: head fade / crossfade, clamp, float -> int16 pack.  6 B/sample (4 in, 2 out).
+// Every fp32 operation is an explicitly rounded intrinsic (no FMA contraction) so the result is
+// bit-identical to the numpy definition in oracle/tail_ref.py.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tail_one(float c, int i, int fade, const float* __restrict__ prev,
+                                          const float* __restrict__ fw, float limit) {
+  float v = c;
+  if (i < fade) {
+    const float w = fw[i];
+    if (prev) v = __fadd_rn(__fmul_rn(prev[i], __fsub_rn(1.0f, w)), __fmul_rn(c, w));
+    else v = __fmul_rn(c, w);
+  }
+  return fminf(fmaxf(v, -limit), limit);
+}
+__device__ __forceinline__ int16_t pack_i16(float v) {
+  int q = __float2int_rn(__fmul_rn(v, 32767.0f));
+  q = max(-32768, min(32767, q));
+  return (int16_t)q;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) pcm_tail_kernel(const float* __restrict__ cur, int64_t cur_stride,
+                                                        const float* __restrict__ prev,
+                                                        const float* __restrict__ fw, int n, int fade, float limit,
+                                                        int16_t* __restrict__ o16, float* __restrict__ o32,
+                                                        int64_t out_stride) {
+  const int row = blockIdx.y;
+  const float* c = cur + (size_t)row * cur_stride;
+  const float* p = prev ? prev + (size_t)row * fade : nullptr;
+  if constexpr (VEC) {
+    const int n4 = n >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+      const int i = q << 2;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(c + i));
+      float v0 = tail_one(x.x, i, fade, p, fw, limit), v1 = tail_one(x.y, i + 1, fade, p, fw, limit);
+      float v2 = tail_one(x.z, i + 2, fade, p, fw, limit), v3 = tail_one(x.w, i + 3, fade, p, fw, limit);
+      if (o32) *reinterpret_cast<float4*>(o32 + (size_t)row * out_stride + i) = make_float4(v0, v1, v2, v3);
+      if (o16) {
+        short4 s4 = make_short4(pack_i16(v0), pack_i16(v1), pack_i16(v2), pack_i16(v3));
+        *reinterpret_cast<short4*>(o16 + (size_t)row * out_stride + i) = s4;
+      }
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const float v = tail_one(c[i], i, fade, p, fw, limit);
+      if (o32) o32[(size_t)row * out_stride + i] = v;
+      if (o16) o16[(size_t)row * out_stride + i] = pack_i16(v);
+    }
+  }
+}
+
+cudaError_t launch_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, const float* fade_w,
+                            int rows, int n, int fade, float limit, int16_t* out_i16, float* out_f32,
+                            int64_t out_stride, cudaStream_t st) {
+  if (rows <= 0 || n <= 0) return cudaSuccess;
+  if (!fade_w) fade = 0;
+  const bool vec = (n % 4 == 0) && (((uintptr_t)cur & 15) == 0) && (cur_stride % 4 == 0) &&
+                   (out_stride % 4 == 0) && (!out_f32 || ((uintptr_t)out_f32 & 15) == 0) &&
+                   (!out_i16 || ((uintptr_t)out_i16 & 7) == 0);
+  const int per = vec ? n / 4 : n;
+  int bx = (per + 255) / 256;
+  const int cap = 148 * 8;                           // a few waves of the 148 SMs; grid-stride beyond
+  if (bx > cap) bx = cap;
+  dim3 grid(bx, rows);
+  if (vec)
+    pcm_tail_kernel<true><<<grid, 256, 0, st>>>(cur, cur_stride, prev_tail, fade_w, n, fade, limit, out_i16, out_f32,
+                                                 out_stride);
+  else
+    pcm_tail_kernel<false><<<grid, 256, 0, st>>>(cur, cur_stride, prev_tail, fade_w, n, fade, limit, out_i16,
+                                                  out_f32, out_stride);
+  return cudaGetLastError();
+}
+
+}  // namespace gnv

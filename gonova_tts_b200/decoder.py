@@ -1,0 +1,310 @@
+"""B200HiFT — the drop-in for the object the service's engine keeps at `model.s3gen.mel2wav`.
+
+Reference boundary (reference paths relative to the gonova-tts checkout):
+  services/tts/core/synthesizer.py:185      ChatterboxTTS.from_pretrained(...)   <- install after this line
+  services/tts/core/synthesizer.py:344-350  model.generate(...) -> S3Gen.inference -> mel2wav.inference(...)
+This class mirrors the upstream HiFTGenerator surface the engine uses on that path:
+  inference(speech_feat[B,80,T], cache_source[B,1,S]) -> (wav[B,480T], source[B,1,480T])
+  decode(x, s) -> wav;   f0_predictor(mel) -> f0[B,T];   sampling_rate / istft_params / audio_limit.
+All arithmetic runs in libgonova_hift.so (hand-written sm_100a kernels) through the C ABI in
+include/gonova_hift.h; torch only owns device memory and streams.  There is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _cabi
+from .weights import fold_state_dict, random_state_dict
+
+SAMPLES_PER_FRAME = 480
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _F0Predictor:
+    """Callable mirror of upstream ConvRNNF0Predictor: mel [B,80,T] -> f0 [B,T]."""
+
+    def __init__(self, owner: "B200HiFT"):
+        self._owner = owner
+
+    def __call__(self, mel: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._owner.predict_f0(mel, lengths)
+
+
+class _SourceModule:
+    """Callable mirror of upstream SourceModuleHnNSF on the x480-upsampled f0 path: f0 [B,T] -> s [B,1,480T]."""
+
+    def __init__(self, owner: "B200HiFT"):
+        self._owner = owner
+
+    def __call__(self, f0: torch.Tensor, seed: Optional[int] = None, phase_vec=None, noise=None) -> torch.Tensor:
+        return self._owner.source_from_f0(f0, seed=seed, phase_vec=phase_vec, noise=noise)
+
+
+class B200HiFT:
+    sampling_rate = 24000
+    istft_params = {"n_fft": 16, "hop_len": 4}
+    audio_limit = 0.99
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dtype: str = "bf16",
+                 simt_conv: bool = False, precise_act: bool = False, prefix: str = ""):
+        if dtype not in _cabi.DTYPE:
+            raise ValueError(f"dtype must be one of {sorted(_cabi.DTYPE)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("B200HiFT runs on a CUDA device only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200HiFT needs a CUDA device (B200, sm_100a); none is visible")
+        self.dtype = dtype
+        self._lib = _cabi.load()
+        folded = fold_state_dict(state_dict, prefix=prefix)
+        names = sorted(folded)
+        arr = (_cabi.GnvWeight * len(names))()
+        keep = []
+        for i, n in enumerate(names):
+            t = folded[n].contiguous()
+            keep.append(t)
+            arr[i].name = n.encode()
+            arr[i].data = C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float))
+            arr[i].ndim = t.dim()
+            for d in range(t.dim()):
+                arr[i].shape[d] = t.shape[d]
+        flags = (_cabi.FLAG_SIMT_CONV if simt_conv else 0) | (_cabi.FLAG_PRECISE_ACT if precise_act else 0)
+        h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        rc = self._lib.gnv_create(arr, len(names), dev_index, _cabi.DTYPE[dtype], flags, C.byref(h))
+        _cabi.check(rc, None, "gnv_create")
+        self._h = h
+        self._ws: Optional[torch.Tensor] = None
+        self._lock = threading.Lock()
+        self._seed = 0
+        self.f0_predictor = _F0Predictor(self)
+        self.m_source = _SourceModule(self)
+
+    # -- construction helpers ---------------------------------------------------------------------
+    @classmethod
+    def from_module(cls, mel2wav, device=None, dtype: str = "bf16", **kw) -> "B200HiFT":
+        """Build from the engine's existing `s3gen.mel2wav` nn.Module (weights are copied, folded)."""
+        sd = mel2wav.state_dict()
+        if device is None:
+            try:
+                device = next(mel2wav.parameters()).device
+            except StopIteration:
+                device = "cuda:0"
+            if torch.device(device).type != "cuda":
+                device = "cuda:0"
+        return cls(sd, device=device, dtype=dtype, **kw)
+
+    @classmethod
+    def random_init(cls, seed: int = 0, corners: bool = False, **kw) -> "B200HiFT":
+        return cls(random_state_dict(seed, corners), **kw)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.gnv_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # nn.Module-ish no-ops so the engine's `.to(device).eval()` chains keep working
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    # -- internals --------------------------------------------------------------------------------
+    def workspace_bytes(self, B: int, T: int) -> int:
+        n = C.c_size_t()
+        _cabi.check(self._lib.gnv_workspace_bytes(self._h, B, T, C.byref(n)), self._h, "gnv_workspace_bytes")
+        return n.value
+
+    def _workspace(self, B: int, T: int) -> torch.Tensor:
+        need = self.workspace_bytes(B, T)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _aligned(ws: torch.Tensor) -> Tuple[int, int]:
+        base = ws.data_ptr()
+        off = (-base) % 1024
+        return base + off, ws.numel() - off
+
+    def _check_in(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, the decoder is on {self.device}")
+        return t.to(torch.float32).contiguous()
+
+    def _lengths(self, lengths, B):
+        if lengths is None:
+            return None
+        lengths = torch.as_tensor(lengths, dtype=torch.int32, device=self.device).contiguous()
+        if lengths.shape != (B,):
+            raise ValueError("lengths must have shape [B]")
+        return lengths
+
+    # -- the upstream surface ---------------------------------------------------------------------
+    @torch.no_grad()
+    def predict_f0(self, mel: torch.Tensor, lengths=None) -> torch.Tensor:
+        mel = self._check_in(mel, "mel")
+        B, Cm, T = mel.shape
+        if Cm != 80:
+            raise ValueError("mel must be [B, 80, T]")
+        lengths = self._lengths(lengths, B)
+        with self._lock:
+            ws = self._workspace(B, T)
+            p, n = self._aligned(ws)
+            f0 = torch.empty(B, T, dtype=torch.float32, device=self.device)
+            rc = self._lib.gnv_f0(self._h, _ptr(mel), _ptr(lengths), B, T, _ptr(f0), C.c_void_p(p), n,
+                                  _stream_ptr(self.device))
+            _cabi.check(rc, self._h, "gnv_f0")
+        return f0
+
+    @torch.no_grad()
+    def source_from_f0(self, f0: torch.Tensor, seed: Optional[int] = None, phase_vec=None, noise=None) -> torch.Tensor:
+        f0 = self._check_in(f0, "f0")
+        B, T = f0.shape
+        if phase_vec is not None:
+            phase_vec = self._check_in(phase_vec, "phase_vec").reshape(B, 9)
+        if noise is not None:
+            noise = self._check_in(noise, "noise").reshape(B, 9, T * SAMPLES_PER_FRAME)
+        if seed is None:
+            self._seed += 1
+            seed = self._seed
+        s = torch.empty(B, 1, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        rc = self._lib.gnv_source(self._h, _ptr(f0), B, T, C.c_uint64(seed), _ptr(phase_vec), _ptr(noise), _ptr(s),
+                                  _stream_ptr(self.device))
+        _cabi.check(rc, self._h, "gnv_source")
+        return s
+
+    @torch.no_grad()
+    def decode(self, x: torch.Tensor, s: torch.Tensor, lengths=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """HiFTGenerator.decode(x=mel [B,80,T], s=source [B,1,480T]) -> wav [B,480T]."""
+        x = self._check_in(x, "x")
+        s = self._check_in(s, "s")
+        B, Cm, T = x.shape
+        if Cm != 80:
+            raise ValueError("x must be [B, 80, T]")
+        if s.numel() != B * T * SAMPLES_PER_FRAME:
+            raise ValueError(f"s must hold B*480*T = {B * T * SAMPLES_PER_FRAME} samples, got {s.numel()}")
+        lengths = self._lengths(lengths, B)
+        wav = out if out is not None else torch.empty(B, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        with self._lock:
+            ws = self._workspace(B, T)
+            p, n = self._aligned(ws)
+            rc = self._lib.gnv_decode(self._h, _ptr(x), _ptr(s), _ptr(lengths), B, T, _ptr(wav), C.c_void_p(p), n,
+                                      _stream_ptr(self.device))
+            _cabi.check(rc, self._h, "gnv_decode")
+        return wav
+
+    @torch.no_grad()
+    def inference(self, speech_feat: torch.Tensor, cache_source: Optional[torch.Tensor] = None, lengths=None,
+                  seed: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                  source_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """HiFTGenerator.inference(speech_feat, cache_source) -> (wav [B,480T], source [B,1,480T])."""
+        mel = self._check_in(speech_feat, "speech_feat")
+        B, Cm, T = mel.shape
+        if Cm != 80:
+            raise ValueError("speech_feat must be [B, 80, T]")
+        cache_len = 0
+        if cache_source is not None and cache_source.numel() != 0:
+            cache_source = self._check_in(cache_source, "cache_source").reshape(B, -1)
+            cache_len = cache_source.shape[1]
+        else:
+            cache_source = None
+        lengths = self._lengths(lengths, B)
+        if seed is None:
+            self._seed += 1
+            seed = self._seed
+        L = T * SAMPLES_PER_FRAME
+        wav = out if out is not None else torch.empty(B, L, dtype=torch.float32, device=self.device)
+        src = source_out if source_out is not None else torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
+        with self._lock:
+            ws = self._workspace(B, T)
+            p, n = self._aligned(ws)
+            rc = self._lib.gnv_inference(self._h, _ptr(mel), _ptr(cache_source), cache_len, _ptr(lengths), B, T,
+                                         C.c_uint64(seed), _ptr(wav), _ptr(src), C.c_void_p(p), n,
+                                         _stream_ptr(self.device))
+            _cabi.check(rc, self._h, "gnv_inference")
+        return wav, src
+
+    # -- extras -----------------------------------------------------------------------------------
+    def debug_tap(self, name: str, B: int, T: int) -> torch.Tensor:
+        """A named intermediate of the last decode of a (B, T) batch, as fp32 [B, C, L]."""
+        ws = self._workspace(B, T)
+        p, _ = self._aligned(ws)
+        cap = B * (120 * T + 1) * 256
+        out = torch.empty(cap, dtype=torch.float32, device=self.device)
+        shape = (C.c_int64 * 3)()
+        rc = self._lib.gnv_debug_tap(self._h, name.encode(), B, T, C.c_void_p(p), _ptr(out), cap, shape,
+                                     _stream_ptr(self.device))
+        _cabi.check(rc, self._h, "gnv_debug_tap")
+        b, c, l = int(shape[0]), int(shape[1]), int(shape[2])
+        return out[: b * c * l].view(b, c, l).clone()
+
+    def launches(self, B: int, T: int, inference: bool = True) -> int:
+        n = C.c_int()
+        fn = self._lib.gnv_inference_launches if inference else self._lib.gnv_decode_launches
+        _cabi.check(fn(self._h, B, T, C.byref(n)), self._h, "launch count")
+        return n.value
+
+
+# -------------------------------------------------------------------------------------------------
+# the streaming tail as a free function (no decoder handle needed)
+# -------------------------------------------------------------------------------------------------
+def fade_window(n: int = 480, device="cpu") -> torch.Tensor:
+    """(cos(linspace(pi, 0, n)) + 1) / 2 — the raised cosine of upstream S3Token2Wav.trim_fade."""
+    return ((torch.cos(torch.linspace(torch.pi, 0, n, dtype=torch.float32)) + 1) / 2).to(device)
+
+
+def trim_fade_window(device="cpu") -> torch.Tensor:
+    w = torch.zeros(960, dtype=torch.float32)
+    w[480:] = fade_window(480)
+    return w.to(device)
+
+
+@torch.no_grad()
+def pcm_tail(cur: torch.Tensor, prev_tail: Optional[torch.Tensor] = None, fade_w: Optional[torch.Tensor] = None,
+             limit: float = 0.99, want_i16: bool = True, want_f32: bool = False,
+             out_i16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
+    """cur [rows, n] fp32 (row stride free) -> (int16 [rows, n] | None, fp32 [rows, n] | None).
+    Head fade / crossfade with prev_tail [rows, fade], clamp(+-limit), round-half-even int16 pack."""
+    if cur.dim() != 2 or cur.dtype != torch.float32 or cur.device.type != "cuda":
+        raise ValueError("cur must be a 2-D fp32 CUDA tensor")
+    if cur.stride(1) != 1:
+        cur = cur.contiguous()
+    rows, n = cur.shape
+    fade = 0
+    if fade_w is not None:
+        fade = min(int(fade_w.numel()), n)
+        fade_w = fade_w.to(cur.device, torch.float32).reshape(-1)[:fade].contiguous()
+    if prev_tail is not None:
+        if fade_w is None:
+            raise ValueError("prev_tail needs fade_w")
+        prev_tail = prev_tail.to(torch.float32).reshape(rows, -1)[:, :fade].contiguous()
+    if want_i16 and out_i16 is None:
+        out_i16 = torch.empty(rows, n, dtype=torch.int16, device=cur.device)
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(rows, n, dtype=torch.float32, device=cur.device)
+    lib = _cabi.load()
+    with torch.cuda.device(cur.device):
+        rc = lib.gnv_pcm_tail(_ptr(cur), cur.stride(0) if rows > 1 else n, _ptr(prev_tail), _ptr(fade_w), rows, n,
+                              fade, C.c_float(limit), _ptr(out_i16), _ptr(out_f32), n, _stream_ptr(cur.device))
+    _cabi.check(rc, None, "gnv_pcm_tail")
+    return out_i16, out_f32

@@ -1,0 +1,82 @@
+"""Chunked decode + crossfade + PCM pack: the streaming tail of the service path.
+
+The reference service ships one float32 chunk per sentence (services/tts/core/synthesizer.py:320-321,
+:352-357; services/tts/server.py:150-155) and config.yaml:9 names a 50-token (= 100 mel frame, 2 s)
+chunk it never uses.  StreamingDecoder makes that chunking real for the vocoder: the source signal is
+generated once for the whole utterance (its phase is a running sum over time), then every chunk of
+`chunk` frames is decoded with a `halo`-frame context on both sides (the decoder's receptive field is
++-14.3 frames), its head is crossfaded with the previous chunk's look-ahead and the result is clamped
+and packed to int16 by one kernel."""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import torch
+
+from .decoder import B200HiFT, SAMPLES_PER_FRAME, fade_window, pcm_tail, trim_fade_window
+
+
+def chunk_plan(T: int, chunk: int = 100, halo: int = 16):
+    """Frame windows of a chunked decode.  Chunk c owns frames [c*chunk, min(T, (c+1)*chunk)); it is
+    decoded on [lo, hi) = owned frames +- halo plus one look-ahead frame whose 480 samples are held
+    back and crossfaded into the next chunk's head.  Yields (own_lo, own_hi, lo, hi, last)."""
+    c = 0
+    while c * chunk < T:
+        own_lo = c * chunk
+        own_hi = min(T, own_lo + chunk)
+        last = own_hi >= T
+        lo = max(0, own_lo - halo)
+        hi = T if last else min(T, own_hi + 1 + halo)
+        yield own_lo, own_hi, lo, hi, last
+        c += 1
+
+
+class StreamingDecoder:
+    def __init__(self, hift: B200HiFT, chunk: int = 100, halo: int = 16, fade: int = 480, limit: float = 0.99,
+                 trim_fade: bool = False):
+        self.hift = hift
+        self.chunk, self.halo, self.fade, self.limit = chunk, halo, fade, limit
+        self.trim_fade = trim_fade
+        self._w = fade_window(fade, hift.device)
+        self._tw = trim_fade_window(hift.device)
+
+    @torch.no_grad()
+    def stream(self, mel: torch.Tensor, s: Optional[torch.Tensor] = None, want_i16: bool = True,
+               want_f32: bool = False, seed: Optional[int] = None) -> Iterator[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]]:
+        """mel [B,80,T] on the decoder's device (+ optional source s [B,1,480T]).  Yields one
+        (int16 [B, n] | None, fp32 [B, n] | None) pair per chunk, in order."""
+        hift = self.hift
+        B, _, T = mel.shape
+        spf = SAMPLES_PER_FRAME
+        if s is None:
+            f0 = hift.predict_f0(mel)
+            s = hift.source_from_f0(f0, seed=seed)
+        s = s.reshape(B, 1, T * spf)
+        prev_tail = None
+        first = True
+        for own_lo, own_hi, lo, hi, last in chunk_plan(T, self.chunk, self.halo):
+            wav = hift.decode(mel[:, :, lo:hi], s[:, :, lo * spf:hi * spf])
+            a = (own_lo - lo) * spf
+            n_emit = (own_hi - own_lo) * spf
+            cur = wav[:, a:a + n_emit]
+            if prev_tail is not None:
+                out = pcm_tail(cur, prev_tail, self._w, self.limit, want_i16, want_f32)
+            elif first and self.trim_fade:
+                out = pcm_tail(cur, None, self._tw, self.limit, want_i16, want_f32)
+            else:
+                out = pcm_tail(cur, None, None, self.limit, want_i16, want_f32)
+            first = False
+            if not last:
+                prev_tail = wav[:, a + n_emit:a + n_emit + self.fade]
+            yield out
+
+    @torch.no_grad()
+    def decode_all(self, mel: torch.Tensor, s: Optional[torch.Tensor] = None, want_i16=True, want_f32=True,
+                   seed: Optional[int] = None):
+        i16s, f32s = [], []
+        for i16, f32 in self.stream(mel, s, want_i16, want_f32, seed):
+            if i16 is not None:
+                i16s.append(i16)
+            if f32 is not None:
+                f32s.append(f32)
+        return (torch.cat(i16s, 1) if i16s else None), (torch.cat(f32s, 1) if f32s else None)

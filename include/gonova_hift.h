@@ -1,0 +1,139 @@
+/*
+ * gonova_hift.h — C ABI of libgonova_hift.so, the B200 (sm_100a) waveform decoder.
+ *
+ * This is the drop-in boundary for ONE path of websines/gonova-tts: the neural vocoder the TTS
+ * service reaches through
+ *     self.model.generate(...)                     services/tts/core/synthesizer.py:344-350
+ *       -> ChatterboxTTS.generate -> S3Gen.inference -> self.mel2wav.inference(speech_feat, cache_source)
+ * (the engine is imported at synthesizer.py:167 and constructed at synthesizer.py:185; it is a
+ * third-party package that is not vendored, so the callee side is cited by its upstream name).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, non-zero on failure; gnv_last_error() gives the text.
+ *     Nothing aborts; nothing calls cudaDeviceSynchronize(); nothing allocates inside the decode
+ *     calls (safe to capture in a CUDA graph).
+ *   - the caller owns all input, output and workspace buffers and passes raw DEVICE pointers
+ *     (torch: tensor.data_ptr()).  The handle owns only re-packed weights.
+ *   - `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).
+ *   - tensors are fp32, contiguous, in the layouts of the upstream PyTorch module:
+ *     mel [B,80,T]  source s [B,1,480*T]  wav [B,480*T]  f0 [B,T].
+ */
+#ifndef GONOVA_HIFT_H_
+#define GONOVA_HIFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNV_ABI_VERSION 1
+
+/* arithmetic of the conv GEMMs (activations/weights as stored in HBM; accumulation is fp32) */
+#define GNV_DTYPE_TF32 0      /* tcgen05 kind::tf32 — the "fp32 parity" path                       */
+#define GNV_DTYPE_BF16 1      /* tcgen05 kind::f16 (bf16) — the throughput path                    */
+#define GNV_DTYPE_FP32 2      /* exact fp32 FMA on CUDA cores (validation path, no tensor cores)   */
+
+/* gnv_create flags */
+#define GNV_FLAG_SIMT_CONV   1u /* run the conv layers on the CUDA-core kernel in the chosen dtype */
+#define GNV_FLAG_PRECISE_ACT 2u /* Snake with libdevice sinf instead of MUFU.SIN (always on for FP32) */
+
+/* activation kinds accepted by gnv_conv1d (unit-test hook) */
+#define GNV_ACT_NONE  0
+#define GNV_ACT_SNAKE 1
+#define GNV_ACT_LRELU 2
+#define GNV_ACT_ELU   3
+#define GNV_ACT_SNAKE_FAST 4  /* Snake through MUFU.SIN, what the bf16 / tf32 decode uses */
+
+typedef struct gnv_decoder* gnv_handle;
+
+/* One named host tensor of the decoder's effective (weight-norm already folded) parameters.
+ * `name` is the upstream module path below `mel2wav.` — e.g. "conv_pre.weight", "ups.0.bias",
+ * "resblocks.4.convs1.2.weight", "resblocks.4.activations2.0.alpha",
+ * "source_downs.1.weight", "f0_predictor.condnet.0.weight", "f0_predictor.classifier.weight",
+ * "m_source.l_linear.weight".  `data` is HOST fp32, PyTorch layout
+ * (Conv1d [Cout,Cin,k]; ConvTranspose1d [Cin,Cout,k]; Linear [out,in]). */
+typedef struct {
+  const char*  name;
+  const float* data;
+  int32_t      ndim;
+  int64_t      shape[4];
+} GnvWeight;
+
+/* replaces: HiFTGenerator.__init__ + load_state_dict of `mel2wav.*` (reached from
+ * ChatterboxTTS.from_pretrained, synthesizer.py:185). */
+int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, unsigned flags,
+               gnv_handle* out);
+void gnv_destroy(gnv_handle h);
+/* h may be NULL: returns the calling thread's last error (e.g. from a failed gnv_create). */
+const char* gnv_last_error(gnv_handle h);
+int gnv_abi_version(void);
+
+/* bytes of scratch the decode calls need for a [B, 80, T] batch */
+int gnv_workspace_bytes(gnv_handle h, int B, int T, size_t* out_bytes);
+
+/* replaces: ConvRNNF0Predictor.forward (first statement of HiFTGenerator.inference). */
+int gnv_f0(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T, float* f0,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: f0_upsamp + SourceModuleHnNSF/SineGen (second statement of HiFTGenerator.inference).
+ * phase_vec [B,9] and noise [B,9,480*T] are optional (NULL -> counter-based Philox from `seed`);
+ * they exist so a test can drive the kernel and the oracle with the same random numbers. */
+int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed,
+               const float* phase_vec, const float* noise, float* s, void* stream);
+
+/* replaces: HiFTGenerator.decode(x=mel, s=s).  lengths [B] (int32, mel frames, device) or NULL
+ * for a rectangular batch; rows past an utterance's length decode as if the utterance ended
+ * there and come back as zeros. */
+int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* lengths,
+               int B, int T, float* wav, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: HiFTGenerator.inference(speech_feat, cache_source): f0 -> source -> overwrite the
+ * first cache_len samples of s with cache_source [B,1,cache_len] -> decode.  Writes s_out. */
+int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int cache_len,
+                  const int32_t* lengths, int B, int T, uint64_t seed,
+                  float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The streaming tail: optional fade/crossfade of the head, clamp(+-limit), optional int16 pack.
+ *   head i < fade:  v = prev_tail ? prev_tail[i]*(1-fade_w[i]) + cur[i]*fade_w[i] : cur[i]*fade_w[i]
+ *   (fade_w NULL or fade 0: no fade);  v = clamp(v, -limit, limit);
+ *   out_f32[i] = v;  out_i16[i] = sat_i16(rint(v * 32767.f))   (either output may be NULL).
+ * cur/out rows are `n` samples, row strides in elements.  prev_tail rows are `fade` samples.
+ * replaces: S3Token2Wav `wav[:, :960] *= trim_fade`, and the service's
+ * `.cpu().numpy().astype(float32)` / `.tobytes()` tail (synthesizer.py:352-357, server.py:150-155). */
+int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, const float* fade_w,
+                 int rows, int n, int fade, float limit,
+                 int16_t* out_i16, float* out_f32, int64_t out_stride, void* stream);
+
+/* ---- unit-test hooks (one kernel each; used by tests/, not by the service) -------------------- */
+
+/* HiFTGenerator._stft + cat(real, imag): s [B, L] -> spec [B, 18, L/4+1] (fp32, NCT). */
+int gnv_stft(const float* s, int B, int L, float* spec_nct, void* stream);
+/* exp / min(.,100) / sin / HiFTGenerator._istft / clamp: x [B, 18, F] (NCT) -> wav [B, 4*(F-1)]. */
+int gnv_istft(const float* x_nct, int B, int F, float limit, float* wav, void* stream);
+
+/* One Conv1d / ConvTranspose1d layer through the same kernels gnv_decode uses.
+ *   x [B,Cin,Lin] fp32 NCT, w PyTorch layout (HOST), bias (HOST or NULL), alpha (HOST, Snake) ->
+ *   y [B,Cout,Lout] fp32 NCT = act( conv(x) + bias + (res ? res : 0) ).  dtype/flags as gnv_create. */
+int gnv_conv1d(int device, int dtype, unsigned flags, int transposed,
+               const float* x, int B, int Cin, int Lin,
+               const float* w_host, const float* bias_host, int Cout, int k, int stride, int pad, int dil,
+               int act, const float* alpha_host, float slope, const float* res_nct,
+               float* y_nct, int Lout, void* stream);
+
+/* Copy a named intermediate of the LAST gnv_decode on (B, T, workspace) into out as fp32 NCT.
+ * names: "s_stft", "fuse{0,1,2}" (x + source branch, the input of stage i's ResBlocks),
+ * "stage{0,1,2}" (mean of the three ResBlocks), "conv_post".  The other intermediates are
+ * updated in place by later layers and no longer exist when the decode returns. */
+int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace, float* out_nct,
+                  size_t out_capacity_elems, int64_t* out_shape3, void* stream);
+
+/* number of kernel launches one gnv_decode / gnv_inference (B, T) issues (bench.py's gpu_launches) */
+int gnv_decode_launches(gnv_handle h, int B, int T, int* out);
+int gnv_inference_launches(gnv_handle h, int B, int T, int* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GONOVA_HIFT_H_ */
