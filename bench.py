@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds per second of the waveform decoder (mel -> int16 PCM) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                # the CPU path, same metric/config
+
+One step = one pass of the hot path over one batch of synthetic mel frames per GPU:
+  f0 predictor -> NSF source -> HiFT decode (conv GEMMs, STFT, iSTFT head) -> clamp + int16 pack.
+Workload per GPU = BASELINE.json configs[2]: 64 concurrent 10 s utterances (T = 500 mel frames each),
+bf16 operands / fp32 accumulate; at N GPUs every rank decodes its own 64 streams (request-level data
+parallelism, no collective on the data path; N = 8 is configs[3]'s 512 streams) -> "scaling": "weak".
+`value` times the device-resident path; `e2e` times the public API call with HOST buffers (pinned
+mel in, int16 PCM out, both copies inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 24000
+SPF = 480
+METRIC = "audio-sec/sec"
+UNIT = "audio-s/s (x real-time)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--frames", type=int, default=500, help="mel frames per utterance (50 per audio second)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-first-chunk", action="store_true")
+    ap.add_argument("--profile-table", default="", help="write the per-launch timing table to this path")
+    return ap.parse_args()
+
+
+def synthetic_mel(B: int, T: int, seed: int) -> torch.Tensor:
+    """Log-mel-like host input (same recipe as the parity tests): clamp(-5 + 2 randn, log 1e-5, 2.5),
+    3-tap moving average along time."""
+    g = torch.Generator().manual_seed(seed)
+    mel = torch.clamp(-5 + 2 * torch.randn(B, 80, T, generator=g), -11.513, 2.5)
+    pad = torch.nn.functional.pad(mel, (1, 1), mode="replicate")
+    return ((pad[..., :-2] + pad[..., 1:-1] + pad[..., 2:]) / 3).contiguous()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, \
+            "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms: the oracle port of the reference decoder on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_decode_rate(B: int, T: int, reps: int, warm: int = 1):
+    """Oracle (fp32 torch CPU restatement of the engine's HiFTGenerator + trim_fade) timed on all host
+    cores.  Returns (audio-s/s, seconds per call, cores)."""
+    from oracle import hift_ref as R
+    from gonova_tts_b200.weights import random_state_dict
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = R.load_model(random_state_dict(0, False))
+    mel = synthetic_mel(B, T, 1234)
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(warm):
+        R.hift_inference(model, mel, generator=gen)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        wav, _ = R.hift_inference(model, mel, generator=gen)
+        wav.numpy().astype("float32").tobytes()            # the reference's float32 wire format
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return B * T / 50.0 / best, best, cores, times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    B, T = 1, args.frames
+    from oracle import hift_ref as R
+    from gonova_tts_b200.weights import random_state_dict
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = R.load_model(random_state_dict(0, False))
+    mel = synthetic_mel(B, T, 1234)
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(args.warmup):
+        R.hift_inference(model, mel, generator=gen)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wav, _ = R.hift_inference(model, mel, generator=gen)
+        wav.numpy().astype("float32").tobytes()
+    dt = time.perf_counter() - t0
+    val = args.steps * B * T / 50.0 / dt
+    sample = f"{B} utterance x {T} mel frames ({B * T / 50:.0f} audio-s) per step, fp32, torch CPU (oneDNN), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "64 concurrent 10 s utterances per GPU (BASELINE configs[2]); the CPU arm decodes a "
+                               "bounded sample of it per step", "frames_per_utterance": T, "sample_rate": SR},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference engine (chatterbox) is not installable here; this is oracle/hift_ref.py, the CPU "
+                "restatement of its HiFTGenerator, run on the host cores",
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the decoder has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+
+    from gonova_tts_b200 import B200HiFT, pcm_tail, random_state_dict
+    from gonova_tts_b200 import _cabi
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    B, T = args.batch, args.frames
+    audio_s_per_gpu = B * T / 50.0
+    dec = B200HiFT(random_state_dict(0, False), device=dev, dtype=args.dtype)
+    # this rank's own streams (shard `rank` of world*B): different seed -> different utterances
+    mel_host = synthetic_mel(B, T, 1234 + rank).pin_memory()
+    mel = mel_host.to(dev)
+    L = T * SPF
+    wav = torch.empty(B, L, dtype=torch.float32, device=dev)
+    src = torch.empty(B, 1, L, dtype=torch.float32, device=dev)
+    pcm = torch.empty(B, L, dtype=torch.int16, device=dev)
+    pcm_host = torch.empty(B, L, dtype=torch.int16).pin_memory()
+    ws_bytes = dec.workspace_bytes(B, T)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident(i):
+        dec.inference(mel, seed=i + 1, out=wav, source_out=src)
+        pcm_tail(wav, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm)
+
+    def step_e2e(i):
+        m = mel_host.to(dev, non_blocking=True)
+        dec.inference(m, seed=i + 1, out=wav, source_out=src)
+        pcm_tail(wav, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm)
+        pcm_host.copy_(pcm, non_blocking=True)
+        stream.synchronize()                               # the host consumes this step's PCM
+
+    def timed(fn, steps, warmup, sampler=None):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        barrier()
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, clocks = timed(step_resident, args.steps, args.warmup, sampler)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup), None)
+    value = world * audio_s_per_gpu * args.steps / (ms_total / 1e3)
+    e2e_value = world * audio_s_per_gpu * args.steps / (ms_e2e / 1e3)
+
+    out = None
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        # ---- per-launch table: which kernel dominates, and its achieved rate ----
+        rows_acc = None
+        n_prof = 3
+        for r in range(n_prof + 1):
+            _, rows = dec.profile_inference(mel, seed=100 + r)
+            if r == 0:
+                continue                                   # warm the event path
+            if rows_acc is None:
+                rows_acc = [[n, k, 0.0, f] for (n, k, _, f) in rows]
+            for acc, row in zip(rows_acc, rows):
+                acc[2] += row[2] / n_prof
+        tc = [r for r in rows_acc if r[1] == _cabi.LAUNCH_CONV_TC]
+        simt = [r for r in rows_acc if r[1] == _cabi.LAUNCH_CONV_SIMT]
+        aux = [r for r in rows_acc if r[1] == _cabi.LAUNCH_AUX]
+        tc_ms, tc_flops = sum(r[2] for r in tc), sum(r[3] for r in tc)
+        step_ms_profiled = sum(r[2] for r in rows_acc)
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        if args.dtype != "bf16":
+            peak_tf = peak_tf / 2 if args.dtype == "tf32" else 75.0    # tf32 = half the bf16 rate; fp32 FMA nominal
+        achieved_tf = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        roofline = {
+            "kernel": f"conv_tc_kernel<{args.dtype}> (tcgen05 implicit-GEMM conv; {len(tc)} launches per step)",
+            "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "peak_source": peak_src + (" bf16 sustained" if args.dtype == "bf16" else " derived for " + args.dtype),
+            "algorithmic_flops_per_step": tc_flops, "kernel_ms_per_step": tc_ms,
+            "share_of_step": tc_ms / step_ms_profiled if step_ms_profiled else None,
+        }
+        breakdown = {"conv_tc_ms": tc_ms, "conv_simt_ms": sum(r[2] for r in simt), "aux_ms": sum(r[2] for r in aux),
+                     "profiled_step_ms": step_ms_profiled}
+        if args.profile_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile_table)), exist_ok=True)
+            with open(args.profile_table, "w") as f:
+                f.write(f"# per-launch device time, B={B} T={T} dtype={args.dtype}, mean of {n_prof} runs (CUDA events)\n")
+                f.write("idx,name,kind,ms,gflop,tflops\n")
+                kn = {0: "aux", 1: "conv_tc", 2: "conv_simt"}
+                for i, (n, k, ms_, fl) in enumerate(rows_acc):
+                    f.write(f"{i},{n},{kn[k]},{ms_:.4f},{fl / 1e9:.2f},{(fl / (ms_ / 1e3) / 1e12) if ms_ > 0 else 0:.1f}\n")
+
+        # ---- first-audio-chunk latency (BASELINE configs[1]): B=1, 100-frame chunk + 16 look-ahead ----
+        first_chunk = None
+        if not args.no_first_chunk:
+            Tc = 116
+            mel1 = synthetic_mel(1, Tc, 77).to(dev)
+            wav1 = torch.empty(1, Tc * SPF, dtype=torch.float32, device=dev)
+            src1 = torch.empty(1, 1, Tc * SPF, dtype=torch.float32, device=dev)
+            pcm1 = torch.empty(1, 100 * SPF, dtype=torch.int16, device=dev)
+            host1 = torch.empty(1, 100 * SPF, dtype=torch.int16).pin_memory()
+            lat = []
+            for it in range(220):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                dec.inference(mel1, seed=it + 1, out=wav1, source_out=src1)
+                pcm_tail(wav1[:, : 100 * SPF], None, None, 0.99, True, False, out_i16=pcm1)
+                host1.copy_(pcm1, non_blocking=True)
+                stream.synchronize()
+                if it >= 20:
+                    lat.append((time.perf_counter() - t0) * 1e3)
+            lat.sort()
+            first_chunk = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[int(len(lat) * 0.99) - 1], "iters": len(lat),
+                           "what": "B=1, 100 mel frames + 16 look-ahead, mel on device -> int16 PCM in pinned host "
+                                   "memory, wall clock", "dtype": args.dtype}
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sec, cores, times = cpu_decode_rate(2, T, reps=3)
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"2 utterances x {T} frames (20 audio-s) per call, best of 3 after 1 warm-up "
+                                      f"({sec:.2f} s per call), fp32 torch CPU oracle"}
+        launches_per_step = dec.launches(B, T, inference=True) + 1
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"{B} concurrent {T / 50:.0f} s utterances per GPU through the decoder "
+                            "(BASELINE configs[2]; N=8 is configs[3]'s 512 streams): f0 -> source -> HiFT decode -> int16",
+                "utterances_per_gpu": B, "frames_per_utterance": T, "sample_rate": SR,
+                "audio_seconds_per_step": world * audio_s_per_gpu, "weights": "seeded random init (no checkpoint)",
+                "l2": f"inputs larger than L2: {ws_bytes / 2**30:.1f} GiB of activations per step vs 126 MB L2",
+                "parallelism": f"dp{world} (request sharding, no collective)",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": world * mel_host.numel() * 4, "d2h_bytes_per_step": world * pcm_host.numel() * 2},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "breakdown": breakdown, "first_chunk": first_chunk, "cpu_baseline": cpu_baseline,
+        }
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

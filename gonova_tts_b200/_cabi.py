@@ -11,12 +11,13 @@ _LIB = None
 DTYPE = {"tf32": 0, "bf16": 1, "fp32": 2}
 FLAG_SIMT_CONV = 1
 FLAG_PRECISE_ACT = 2
+LAUNCH_AUX, LAUNCH_CONV_TC, LAUNCH_CONV_SIMT, LAUNCH_NAME_LEN = 0, 1, 2, 48
 ACT = {"none": 0, "snake": 1, "lrelu": 2, "elu": 3, "snake_fast": 4}
 
 # every symbol include/gonova_hift.h declares
 SYMBOLS = [
     "gnv_create", "gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_workspace_bytes", "gnv_f0",
-    "gnv_source", "gnv_decode", "gnv_inference", "gnv_pcm_tail", "gnv_stft", "gnv_istft", "gnv_conv1d",
+    "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_stft", "gnv_istft", "gnv_conv1d",
     "gnv_debug_tap", "gnv_decode_launches", "gnv_inference_launches",
 ]
 
@@ -55,6 +56,9 @@ def load():
     lib.gnv_decode.argtypes = [vp, f32p, f32p, i32p, C.c_int, C.c_int, f32p, vp, C.c_size_t, vp]
     lib.gnv_inference.argtypes = [vp, f32p, f32p, C.c_int, i32p, C.c_int, C.c_int, C.c_uint64, f32p, f32p, vp,
                                   C.c_size_t, vp]
+    lib.gnv_inference_profile.argtypes = [vp, f32p, i32p, C.c_int, C.c_int, C.c_uint64, f32p, f32p, vp, C.c_size_t, vp,
+                                          C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                          C.c_char_p, C.POINTER(C.c_int)]
     lib.gnv_pcm_tail.argtypes = [f32p, C.c_int64, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_float, i16p, f32p,
                                  C.c_int64, vp]
     lib.gnv_stft.argtypes = [f32p, C.c_int, C.c_int, f32p, vp]

@@ -92,7 +92,34 @@ struct ConvOp {
   const void* A = nullptr;
   const void* W = nullptr;
   int variant = SV_FFF;
+  std::string name;      // upstream module path of the layer ("resblocks.4.convs1.2")
+  double flops = 0.0;    // algorithmic: 2 * B * L_out * C_out * C_in * k (convT: 2 * B * L_in * ...)
 };
+
+// Optional per-launch timing (gnv_inference_profile): one CUDA event after every launch on the
+// launching stream; durations are differences of consecutive events.
+struct Profiler {
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  std::vector<int> kinds;       // GNV_LAUNCH_*
+  std::vector<double> flops;
+  cudaError_t err = cudaSuccess;
+  void begin(cudaStream_t s) { st = s; push_event(); }
+  void push_event() {
+    cudaEvent_t e = nullptr;
+    cudaError_t r = cudaEventCreate(&e);
+    if (r == cudaSuccess) r = cudaEventRecord(e, st);
+    if (r != cudaSuccess && err == cudaSuccess) err = r;
+    ev.push_back(e);
+  }
+  void mark(const std::string& name, int kind, double fl) {
+    names.push_back(name); kinds.push_back(kind); flops.push_back(fl);
+    push_event();
+  }
+  ~Profiler() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+inline void prof_mark(Profiler* p, const char* name, int kind, double fl = 0.0) { if (p) p->mark(name, kind, fl); }
 
 // Offsets (bytes) into the caller's workspace for one (B, T).
 struct WsLayout {
@@ -381,11 +408,16 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   auto P = [&](size_t off) { return (void*)(base + off); };
   auto Fp = [&](size_t off) { return (float*)(base + off); };
   std::string e;
-  auto add = [&](std::vector<ConvOp>& ops, const ConvLayer& L, const void* A, int L_in, const EpiSpec& es) {
+  auto add = [&](std::vector<ConvOp>& ops, const ConvLayer& L, const void* A, int L_in, const EpiSpec& es,
+                 const std::string& name) {
     if (!e.empty()) return;
     ConvOp op;
     e = make_op(h, L, A, B, L_in, es, &op);
-    if (e.empty()) ops.push_back(op);
+    if (!e.empty()) { e = name + ": " + e; return; }
+    op.name = name;
+    const double rows = L.transposed ? (double)L_in : (double)op.ep.L_store;
+    op.flops = 2.0 * B * rows * L.C_out * L.C_in * L.k;
+    ops.push_back(op);
   };
   const int snake = h->snake_kind;
   const int F = 120 * T + 1;
@@ -397,7 +429,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
     for (int i = 0; i < 5; ++i) {
       EpiSpec es;
       es.acts.push_back({ACT_ELU, nullptr, 0.f, P(outs[i & 1])});
-      add(plan->f0_ops, h->f0c[i], in, T, es);
+      add(plan->f0_ops, h->f0c[i], in, T, es, "f0_predictor.condnet." + std::to_string(2 * i));
       in = P(outs[i & 1]);
     }
   }
@@ -406,7 +438,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   {
     EpiSpec es;
     es.acts.push_back({ACT_LRELU, nullptr, 0.1f, P(w.X0)});
-    add(ops, h->conv_pre, P(w.melE), T, es);
+    add(ops, h->conv_pre, P(w.melE), T, es, "conv_pre");
   }
   const void* X = P(w.X0);
   int Lx = T;
@@ -416,12 +448,12 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
     float *F1 = Fp(w.F1[i]), *F2 = Fp(w.F2[i]), *F3 = Fp(w.F3[i]);
     void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
     auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
-                        int j) {
+                        int j, const std::string& rbname) {
       for (int d = 0; d < 3; ++d) {
         {
           EpiSpec es; es.len_mul = lm; es.len_add = la;
           es.acts.push_back({snake, R.a2[d], 0.f, E[3]});
-          add(ops, R.c1[d], EA, Ls, es);
+          add(ops, R.c1[d], EA, Ls, es, rbname + ".convs1." + std::to_string(d));
         }
         EpiSpec es; es.len_mul = lm; es.len_add = la;
         es.res = d == 0 ? res_first : raw_stream;
@@ -434,7 +466,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
           es.raw = F3; es.raw_scale = 1.f / 3.f; es.raw_accum = j > 0 ? 1 : 0;
           if (j == 2) es.acts.push_back({ACT_LRELU, nullptr, i == 2 ? 0.01f : 0.1f, E[0]});
         }
-        add(ops, R.c2[d], E[3], Ls, es);
+        add(ops, R.c2[d], E[3], Ls, es, rbname + ".convs2." + std::to_string(d));
       }
     };
     // source branch
@@ -442,24 +474,25 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
       EpiSpec es; es.len_mul = lm; es.len_add = la;
       es.raw = F1;
       es.acts.push_back({snake, h->srb[i].a1[0], 0.f, E[0]});
-      add(ops, h->sdown[i], P(w.spec), F, es);
+      add(ops, h->sdown[i], P(w.spec), F, es, "source_downs." + std::to_string(i));
     }
-    resblock(h->srb[i], E[0], F1, F1, false, 0);
+    resblock(h->srb[i], E[0], F1, F1, false, 0, "source_resblocks." + std::to_string(i));
     // upsampling + fuse
     {
       EpiSpec es; es.len_mul = lm; es.len_add = la;
       es.res = F1; es.raw = F2; es.reflect_front = (i == 2);
       for (int j = 0; j < 3; ++j) es.acts.push_back({snake, h->rb[3 * i + j].a1[0], 0.f, E[j]});
-      add(ops, h->ups[i], X, Lx, es);
+      add(ops, h->ups[i], X, Lx, es, "ups." + std::to_string(i));
     }
-    for (int j = 0; j < 3; ++j) resblock(h->rb[3 * i + j], E[j], F2, F1, true, j);
+    for (int j = 0; j < 3; ++j)
+      resblock(h->rb[3 * i + j], E[j], F2, F1, true, j, "resblocks." + std::to_string(3 * i + j));
     X = E[0];
     Lx = Ls;
   }
   {
     EpiSpec es; es.len_mul = 120; es.len_add = 1;
     es.raw = Fp(w.P);
-    add(ops, h->conv_post, X, Lx, es);
+    add(ops, h->conv_post, X, Lx, es, "conv_post");
   }
   return e;
 }
@@ -503,26 +536,39 @@ struct DeviceGuard {
   } while (0)
 
 int run_f0(gnv_handle h, Plan* plan, const float* mel, const int* lengths, int B, int T, float* f0, char* ws,
-           bool pack_mel, cudaStream_t st) {
+           bool pack_mel, cudaStream_t st, Profiler* prof = nullptr) {
   const WsLayout& w = plan->lay;
-  if (pack_mel)
+  if (pack_mel) {
     GNV_CK(h, "pack mel", launch_nct_to_nlc(mel, B, kMelC, T, lengths, ws + w.melE, h->conv_pre.C_in_ld, h->eb,
                                             h->dtype == GNV_DTYPE_TF32, st));
-  for (const ConvOp& op : plan->f0_ops) GNV_CK(h, "f0 conv", run_op(op, lengths, st));
+    prof_mark(prof, "pack_mel", GNV_LAUNCH_AUX);
+  }
+  for (const ConvOp& op : plan->f0_ops) {
+    GNV_CK(h, "f0 conv", run_op(op, lengths, st));
+    prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
+  }
   const void* hl = ws + (plan->f0_ops.size() % 2 ? w.H0 : w.H1);
   GNV_CK(h, "f0 head", launch_f0_head(hl, h->eb, B * T, 512, h->f0_w, h->f0_b, f0, st));
+  prof_mark(prof, "f0_predictor.classifier", GNV_LAUNCH_AUX, 2.0 * B * T * 512);
   return 0;
 }
 
 int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const int* lengths, int B, int T,
-               float* wav, char* ws, bool pack_mel, cudaStream_t st) {
+               float* wav, char* ws, bool pack_mel, cudaStream_t st, Profiler* prof = nullptr) {
   const WsLayout& w = plan->lay;
-  if (pack_mel)
+  if (pack_mel) {
     GNV_CK(h, "pack mel", launch_nct_to_nlc(mel, B, kMelC, T, lengths, ws + w.melE, h->conv_pre.C_in_ld, h->eb,
                                             h->dtype == GNV_DTYPE_TF32, st));
+    prof_mark(prof, "pack_mel", GNV_LAUNCH_AUX);
+  }
   GNV_CK(h, "stft", launch_stft(s, B, T * kSPF, lengths, (float*)(ws + w.spec), st));
-  for (const ConvOp& op : plan->decode_ops) GNV_CK(h, "conv", run_op(op, lengths, st));
+  prof_mark(prof, "stft", GNV_LAUNCH_AUX);
+  for (const ConvOp& op : plan->decode_ops) {
+    GNV_CK(h, "conv", run_op(op, lengths, st));
+    prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
+  }
   GNV_CK(h, "istft", launch_istft((const float*)(ws + w.P), B, 120 * T + 1, lengths, 0.99f, wav, st));
+  prof_mark(prof, "istft_head", GNV_LAUNCH_AUX);
   return 0;
 }
 
@@ -655,26 +701,61 @@ int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* le
   return run_decode(h, plan, mel, s, lengths, B, T, wav, (char*)workspace, true, (cudaStream_t)stream);
 }
 
-int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int cache_len, const int32_t* lengths,
-                  int B, int T, uint64_t seed, float* wav, float* s_out, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+static int inference_impl(gnv_handle h, const float* mel, const float* cache_source, int cache_len,
+                          const int32_t* lengths, int B, int T, uint64_t seed, float* wav, float* s_out,
+                          void* workspace, size_t workspace_bytes, cudaStream_t st, Profiler* prof) {
   if (!h || !mel || !wav || !s_out) return fail(h, "NULL argument");
   if (cache_len < 0 || (cache_len > 0 && !cache_source)) return fail(h, "bad cache_source");
   DeviceGuard dg(h->device);
   Plan* plan = nullptr;
   if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   float* f0 = (float*)(ws + plan->lay.f0);
-  if (int rc = run_f0(h, plan, mel, lengths, B, T, f0, ws, true, st)) return rc;
+  if (prof) prof->begin(st);
+  if (int rc = run_f0(h, plan, mel, lengths, B, T, f0, ws, true, st, prof)) return rc;
   GNV_CK(h, "source", launch_source(f0, B, T, seed, nullptr, nullptr, h->lin_w, h->lin_b, s_out, st));
+  prof_mark(prof, "m_source", GNV_LAUNCH_AUX);
   const size_t L = (size_t)T * kSPF;
   if (cache_len > 0) {
     const size_t n = (size_t)cache_len < L ? (size_t)cache_len : L;
     GNV_CK(h, "cache_source copy", cudaMemcpy2DAsync(s_out, L * 4, cache_source, (size_t)cache_len * 4, n * 4, B,
                                                      cudaMemcpyDeviceToDevice, st));
+    prof_mark(prof, "cache_source_copy", GNV_LAUNCH_AUX);
   }
-  return run_decode(h, plan, mel, s_out, lengths, B, T, wav, ws, false, st);
+  return run_decode(h, plan, mel, s_out, lengths, B, T, wav, ws, false, st, prof);
+}
+
+int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int cache_len, const int32_t* lengths,
+                  int B, int T, uint64_t seed, float* wav, float* s_out, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return inference_impl(h, mel, cache_source, cache_len, lengths, B, T, seed, wav, s_out, workspace, workspace_bytes,
+                        (cudaStream_t)stream, nullptr);
+}
+
+int gnv_inference_profile(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T, uint64_t seed,
+                          float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream,
+                          int capacity, float* ms_out, int32_t* kind_out, double* flops_out, char* names_out,
+                          int* n_out) {
+  if (!ms_out || !kind_out || !flops_out || !names_out || !n_out) return fail(h, "NULL argument");
+  Profiler prof;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = inference_impl(h, mel, nullptr, 0, lengths, B, T, seed, wav, s_out, workspace, workspace_bytes, st,
+                              &prof))
+    return rc;
+  if (prof.err != cudaSuccess) return fail_cuda(h, "profile events", prof.err);
+  GNV_CK(h, "profile sync", cudaStreamSynchronize(st));
+  const int n = (int)prof.names.size();
+  if (n > capacity) return fail(h, "profile arrays too small");
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    GNV_CK(h, "cudaEventElapsedTime", cudaEventElapsedTime(&ms, prof.ev[i], prof.ev[i + 1]));
+    ms_out[i] = ms;
+    kind_out[i] = prof.kinds[i];
+    flops_out[i] = prof.flops[i];
+    snprintf(names_out + (size_t)i * GNV_LAUNCH_NAME_LEN, GNV_LAUNCH_NAME_LEN, "%s", prof.names[i].c_str());
+  }
+  *n_out = n;
+  return 0;
 }
 
 int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, const float* fade_w, int rows, int n,

@@ -258,6 +258,35 @@ class B200HiFT:
         b, c, l = int(shape[0]), int(shape[1]), int(shape[2])
         return out[: b * c * l].view(b, c, l).clone()
 
+    @torch.no_grad()
+    def profile_inference(self, speech_feat: torch.Tensor, lengths=None, seed: int = 1):
+        """One inference() with per-launch device times (gnv_inference_profile).  Returns
+        (wav, [(name, kind, ms, algorithmic_flops), ...]); kind is _cabi.LAUNCH_*."""
+        mel = self._check_in(speech_feat, "speech_feat")
+        B, _, T = mel.shape
+        lengths = self._lengths(lengths, B)
+        L = T * SAMPLES_PER_FRAME
+        wav = torch.empty(B, L, dtype=torch.float32, device=self.device)
+        src = torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
+        cap = 256
+        ms = (C.c_float * cap)()
+        kinds = (C.c_int32 * cap)()
+        flops = (C.c_double * cap)()
+        names = C.create_string_buffer(cap * _cabi.LAUNCH_NAME_LEN)
+        n = C.c_int()
+        with self._lock:
+            ws = self._workspace(B, T)
+            p, nbytes = self._aligned(ws)
+            rc = self._lib.gnv_inference_profile(self._h, _ptr(mel), _ptr(lengths), B, T, C.c_uint64(seed), _ptr(wav),
+                                                 _ptr(src), C.c_void_p(p), nbytes, _stream_ptr(self.device), cap, ms,
+                                                 kinds, flops, names, C.byref(n))
+            _cabi.check(rc, self._h, "gnv_inference_profile")
+        rows = []
+        for i in range(n.value):
+            raw = names.raw[i * _cabi.LAUNCH_NAME_LEN:(i + 1) * _cabi.LAUNCH_NAME_LEN]
+            rows.append((raw.split(b"\0", 1)[0].decode(), int(kinds[i]), float(ms[i]), float(flops[i])))
+        return wav, rows
+
     def launches(self, B: int, T: int, inference: bool = True) -> int:
         n = C.c_int()
         fn = self._lib.gnv_inference_launches if inference else self._lib.gnv_decode_launches
@@ -302,6 +331,8 @@ def pcm_tail(cur: torch.Tensor, prev_tail: Optional[torch.Tensor] = None, fade_w
         out_i16 = torch.empty(rows, n, dtype=torch.int16, device=cur.device)
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(rows, n, dtype=torch.float32, device=cur.device)
+    if rows == 0 or n == 0:
+        return out_i16, out_f32
     lib = _cabi.load()
     with torch.cuda.device(cur.device):
         rc = lib.gnv_pcm_tail(_ptr(cur), cur.stride(0) if rows > 1 else n, _ptr(prev_tail), _ptr(fade_w), rows, n,

@@ -95,6 +95,20 @@ int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int
                   const int32_t* lengths, int B, int T, uint64_t seed,
                   float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook (bench.py's roofline): one gnv_inference with a CUDA event recorded after every
+ * launch on `stream`; synchronises the stream before returning.  For launch i < *n_out:
+ * ms_out[i] device time, kind_out[i] one of GNV_LAUNCH_*, flops_out[i] the layer's algorithmic flops
+ * (2 * B * L_out * C_out * C_in * k; 0 for the byte-moving kernels), names_out + i*GNV_LAUNCH_NAME_LEN
+ * the upstream module path of the layer.  All four arrays are HOST memory with `capacity` entries. */
+#define GNV_LAUNCH_AUX       0   /* bandwidth-bound kernels: packers, STFT, source, f0 head, iSTFT head */
+#define GNV_LAUNCH_CONV_TC   1   /* tcgen05 implicit-GEMM conv kernel */
+#define GNV_LAUNCH_CONV_SIMT 2   /* CUDA-core conv kernel (source_downs; validation path) */
+#define GNV_LAUNCH_NAME_LEN  48
+int gnv_inference_profile(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T, uint64_t seed,
+                          float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream,
+                          int capacity, float* ms_out, int32_t* kind_out, double* flops_out, char* names_out,
+                          int* n_out);
+
 /* The streaming tail: optional fade/crossfade of the head, clamp(+-limit), optional int16 pack.
  *   head i < fade:  v = prev_tail ? prev_tail[i]*(1-fade_w[i]) + cur[i]*fade_w[i] : cur[i]*fade_w[i]
  *   (fade_w NULL or fade 0: no fade);  v = clamp(v, -limit, limit);
