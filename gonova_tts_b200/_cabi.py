@@ -11,6 +11,7 @@ _LIB = None
 DTYPE = {"tf32": 0, "bf16": 1, "fp32": 2}
 FLAG_SIMT_CONV = 1
 FLAG_PRECISE_ACT = 2
+FLAG_TC_V1 = 4
 LAUNCH_AUX, LAUNCH_CONV_TC, LAUNCH_CONV_SIMT, LAUNCH_NAME_LEN = 0, 1, 2, 48
 ACT = {"none": 0, "snake": 1, "lrelu": 2, "elu": 3, "snake_fast": 4}
 

@@ -19,6 +19,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -30,6 +31,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "kernels.h"
 
 using namespace gnv;
@@ -40,6 +42,7 @@ thread_local std::string tl_error;
 
 constexpr int kSPF = 480;
 constexpr int kMelC = 80;
+constexpr int kPostPitch = 20;   // conv_post output [B, F, 18] is stored with a 16-byte-multiple channel pitch (TMA)
 
 struct HostT {
   const float* data = nullptr;
@@ -86,7 +89,9 @@ enum SimtVariant { SV_FFF = 0, SV_BBB = 1, SV_FFB = 2 };
 
 struct ConvOp {
   bool tc = false;
+  int tcv = 1;           // 1: conv_tc_kernel (one tile per CTA), 2: conv_tc2_kernel (persistent)
   ConvTcLaunch tcl;
+  ConvTc2Launch tc2l;
   ConvGeom g;
   EpiParams ep;
   const void* A = nullptr;
@@ -132,7 +137,36 @@ struct Plan {
   std::vector<ConvOp> decode_ops;
   std::vector<ConvOp> f0_ops;
   WsLayout lay;
+  void* d_maps = nullptr;          // device copy of every op's tensor maps (conv_tc2)
+  Plan() = default;
+  Plan(const Plan&) = delete;
+  Plan& operator=(const Plan&) = delete;
+  Plan(Plan&& o) noexcept { *this = std::move(o); }
+  Plan& operator=(Plan&& o) noexcept {
+    decode_ops = std::move(o.decode_ops); f0_ops = std::move(o.f0_ops); lay = o.lay;
+    d_maps = o.d_maps; o.d_maps = nullptr;
+    return *this;
+  }
+  ~Plan() { if (d_maps) cudaFree(d_maps); }
 };
+
+// Uploads the tensor maps of every conv_tc2 op to one device buffer and points the ops at it.
+std::string upload_maps(std::vector<ConvOp*>& ops, void** d_out) {
+  std::vector<ConvOp*> v2;
+  for (ConvOp* op : ops) if (op->tc && op->tcv == 2) v2.push_back(op);
+  *d_out = nullptr;
+  if (v2.empty()) return "";
+  std::vector<ConvTc2Maps> host(v2.size());
+  for (size_t i = 0; i < v2.size(); ++i) host[i] = v2[i]->tc2l.maps;
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, host.size() * sizeof(ConvTc2Maps));
+  if (e != cudaSuccess) return std::string("cudaMalloc(tensor maps): ") + cudaGetErrorString(e);
+  e = cudaMemcpy(d, host.data(), host.size() * sizeof(ConvTc2Maps), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return std::string("cudaMemcpy(tensor maps): ") + cudaGetErrorString(e); }
+  for (size_t i = 0; i < v2.size(); ++i) v2[i]->tc2l.d_maps = static_cast<const ConvTc2Maps*>(d) + i;
+  *d_out = d;
+  return "";
+}
 
 using PlanKey = std::tuple<int, int, const void*>;
 
@@ -143,6 +177,8 @@ struct gnv_decoder {
   unsigned flags = 0;
   int eb = 4;            // bytes per activation element E
   bool use_tc = true;
+  int tc_version = 2;
+  ConvTc2Options tc2opt;
   int snake_kind = ACT_SNAKE;
   std::string err;
   std::vector<void*> allocs;
@@ -161,7 +197,18 @@ int fail(gnv_handle h, const std::string& msg) {
   return 1;
 }
 int fail_cuda(gnv_handle h, const char* what, cudaError_t e) {
-  return fail(h, std::string(what) + ": " + cudaGetErrorString(e));
+  return fail(h, std::string(what) + ": " + cudaGetErrorString(e) + tc_debug_string());
+}
+
+// Tuning knobs for experiments on the GPU box (defaults are the production configuration).
+ConvTc2Options tc2_options_from_env() {
+  ConvTc2Options o;
+  if (const char* v = getenv("GONOVA_TC2_SLAB")) o.slab_mode = atoi(v);
+  if (const char* v = getenv("GONOVA_TC2_MH")) o.mh = atoi(v);
+  if (const char* v = getenv("GONOVA_TC2_CTAS")) o.max_ctas = atoi(v);
+  if (o.slab_mode < 0 || o.slab_mode > 2) o.slab_mode = 1;
+  if (o.max_ctas < 1) o.max_ctas = 148;
+  return o;
 }
 
 const int kStageC[3] = {256, 128, 64};
@@ -300,7 +347,7 @@ WsLayout make_layout(const gnv_decoder* h, int B, int T) {
   w.melE = take((size_t)B * T * h->conv_pre.C_in_ld * eb);
   w.spec = take((size_t)B * F * 18 * 4);
   w.X0 = take((size_t)B * T * 512 * eb);
-  w.P = take((size_t)B * F * 18 * 4);
+  w.P = take((size_t)B * F * kPostPitch * 4);
   w.H0 = take((size_t)B * T * 512 * eb);
   w.H1 = take((size_t)B * T * 512 * eb);
   w.f0 = take((size_t)B * T * 4);
@@ -331,6 +378,7 @@ struct EpiSpec {
   std::vector<ActSpec> acts;
   int len_mul = 1, len_add = 0;
   bool reflect_front = false;   // ReflectionPad1d((1,0)) after the last upsampling
+  int c_pitch = 0;              // output channel pitch; 0 = C_out
 };
 
 // Builds the GEMM geometry + fused epilogue of one layer on input [B, L_in, C_in_ld].
@@ -343,6 +391,7 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
   g.B = B; g.L_in = L_in; g.C_in = L.C_in; g.C_in_ld = L.C_in_ld; g.C_in_w = L.C_in_ld;
   g.N_total = L.N_total; g.n_taps = L.n_taps;
   ep.C_out = L.C_out; ep.N_valid = L.N_valid;
+  ep.C_pitch = es.c_pitch > 0 ? es.c_pitch : L.C_out;
   if (L.transposed) {
     g.off0 = 0; g.tap_step = -1; g.in_stride = 1;
     ep.up = L.stride; ep.pad_out = L.pad;
@@ -377,8 +426,10 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
   }
   if (h->use_tc) {
     op->tc = true;
-    const char* e = make_conv_tc_launch(&op->tcl, h->eb, A, L.w, L.N_total, g, ep, L.block_n);
-    return e;
+    op->tcv = h->tc_version;
+    if (h->tc_version == 2)
+      return make_conv_tc2_launch(&op->tc2l, h->eb, A, L.w, L.N_total, g, ep, ep.C_pitch, h->tc2opt);
+    return make_conv_tc_launch(&op->tcl, h->eb, A, L.w, L.N_total, g, ep, L.block_n);
   }
   op->tc = false;
   op->variant = h->eb == 2 ? SV_BBB : SV_FFF;
@@ -387,6 +438,7 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
 
 cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   if (op.tc) {
+    if (op.tcv == 2) return launch_conv_tc2(op.tc2l, lengths, st);
     if (!lengths) return launch_conv_tc(op.tcl, st);
     ConvTcLaunch L = op.tcl;
     L.p.ep.lengths = lengths;
@@ -492,9 +544,14 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   {
     EpiSpec es; es.len_mul = 120; es.len_add = 1;
     es.raw = Fp(w.P);
+    es.c_pitch = kPostPitch;
     add(ops, h->conv_post, X, Lx, es, "conv_post");
   }
-  return e;
+  if (!e.empty()) return e;
+  std::vector<ConvOp*> all;
+  for (ConvOp& op : plan->f0_ops) all.push_back(&op);
+  for (ConvOp& op : plan->decode_ops) all.push_back(&op);
+  return upload_maps(all, &plan->d_maps);
 }
 
 int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, Plan** out) {
@@ -508,7 +565,9 @@ int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, Plan** out) 
     Plan p;
     std::string e = build_plan(h, B, T, ws, &p);
     if (!e.empty()) return fail(h, e);
-    if (h->plans.size() > 64) h->plans.clear();
+    cudaError_t pe = cudaGetLastError();
+    (void)pe;
+    if (h->plans.size() > 24) h->plans.clear();
     it = h->plans.emplace(key, std::move(p)).first;
   }
   if (ws_bytes < it->second.lay.total) return fail(h, "workspace too small for (B, T)");
@@ -567,7 +626,7 @@ int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const
     GNV_CK(h, "conv", run_op(op, lengths, st));
     prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
   }
-  GNV_CK(h, "istft", launch_istft((const float*)(ws + w.P), B, 120 * T + 1, lengths, 0.99f, wav, st));
+  GNV_CK(h, "istft", launch_istft((const float*)(ws + w.P), B, 120 * T + 1, kPostPitch, lengths, 0.99f, wav, st));
   prof_mark(prof, "istft_head", GNV_LAUNCH_AUX);
   return 0;
 }
@@ -622,6 +681,8 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   h->device = device; h->dtype = dtype; h->flags = flags;
   h->eb = dtype == GNV_DTYPE_BF16 ? 2 : 4;
   h->use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV);
+  h->tc_version = (flags & GNV_FLAG_TC_V1) ? 1 : 2;
+  h->tc2opt = tc2_options_from_env();
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
   std::string err;
@@ -654,6 +715,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   }
   if (h->use_tc) {
     ce = conv_tc_init();
+    if (ce == cudaSuccess) ce = conv_tc2_init();
     if (ce != cudaSuccess) {
       gnv_destroy(h);
       return fail_cuda(nullptr, "conv_tc_init", ce);
@@ -805,7 +867,7 @@ int gnv_istft(const float* x_nct, int B, int F, float limit, float* wav, void* s
   float* nlc = (float*)sc.get((size_t)B * F * 18 * 4, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
   GNV_CK(nullptr, "pack", launch_nct_to_nlc(x_nct, B, 18, F, nullptr, nlc, 18, 4, 0, st));
-  GNV_CK(nullptr, "istft", launch_istft(nlc, B, F, nullptr, limit, wav, st));
+  GNV_CK(nullptr, "istft", launch_istft(nlc, B, F, 18, nullptr, limit, wav, st));
   GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
   return 0;
 }
@@ -824,12 +886,16 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
   tmp.eb = dtype == GNV_DTYPE_BF16 ? 2 : 4;
   const bool strided = !transposed && stride != 1;
   tmp.use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV) && !strided;
+  tmp.tc_version = (flags & GNV_FLAG_TC_V1) ? 1 : 2;
+  tmp.tc2opt = tc2_options_from_env();
+  const int Cp = (Cout + 3) & ~3;             // channel pitch of the outputs: rows are 16-byte multiples
   struct Cleanup {
     gnv_decoder* d;
     ~Cleanup() { for (void* p : d->allocs) cudaFree(p); }
   } cleanup{&tmp};
   if (tmp.use_tc) {
     cudaError_t ce = conv_tc_init();
+    if (ce == cudaSuccess) ce = conv_tc2_init();
     if (ce != cudaSuccess) return fail_cuda(nullptr, "conv_tc_init", ce);
   }
   std::vector<float> zero_bias((size_t)Cout, 0.f);
@@ -857,30 +923,36 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
   const int a_eb = strided ? 4 : tmp.eb;
   void* A = sc.get((size_t)B * Lin * L.C_in_ld * a_eb, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
-  float* raw = (float*)sc.get((size_t)B * Lout * Cout * 4, &e);
+  float* raw = (float*)sc.get((size_t)B * Lout * Cp * 4, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
-  void* actb = sc.get((size_t)B * Lout * Cout * tmp.eb, &e);
+  void* actb = sc.get((size_t)B * Lout * Cp * tmp.eb, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
   float* res = nullptr;
   if (res_nct) {
-    res = (float*)sc.get((size_t)B * Lout * Cout * 4, &e);
+    res = (float*)sc.get((size_t)B * Lout * Cp * 4, &e);
     if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
-    GNV_CK(nullptr, "pack res", launch_nct_to_nlc(res_nct, B, Cout, Lout, nullptr, res, Cout, 4, 0, st));
+    GNV_CK(nullptr, "pack res", launch_nct_to_nlc(res_nct, B, Cout, Lout, nullptr, res, Cp, 4, 0, st));
   }
   GNV_CK(nullptr, "pack x", launch_nct_to_nlc(x, B, Cin, Lin, nullptr, A, L.C_in_ld, a_eb,
                                               (!strided && dtype == GNV_DTYPE_TF32) ? 1 : 0, st));
   EpiSpec es;
   es.res = res;
   es.raw = raw;
+  es.c_pitch = Cp;
   if (act != GNV_ACT_NONE) es.acts.push_back({act, alpha_d, slope, actb});
   ConvOp op;
   std::string me = make_op(&tmp, L, A, B, Lin, es, &op);
   if (!me.empty()) return fail(nullptr, "gnv_conv1d: " + me);
+  std::vector<ConvOp*> one{&op};
+  void* d_maps = nullptr;
+  me = upload_maps(one, &d_maps);
+  if (!me.empty()) return fail(nullptr, "gnv_conv1d: " + me);
+  if (d_maps) sc.p.push_back(d_maps);
   GNV_CK(nullptr, "conv", run_op(op, nullptr, st));
   if (act != GNV_ACT_NONE)
-    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(actb, B, Lout, Cout, Cout, tmp.eb, y_nct, st));
+    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(actb, B, Lout, Cout, Cp, tmp.eb, y_nct, st));
   else
-    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(raw, B, Lout, Cout, Cout, 4, y_nct, st));
+    GNV_CK(nullptr, "unpack", launch_nlc_to_nct(raw, B, Lout, Cout, Cp, 4, y_nct, st));
   GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
   return 0;
 }
@@ -893,10 +965,10 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
   char* ws = (char*)workspace;
   const std::string n(name);
   const float* src = nullptr;
-  int L = 0, C = 0;
+  int L = 0, C = 0, Cld = 0;
   const int F = 120 * T + 1;
   if (n == "s_stft") { src = (const float*)(ws + w.spec); L = F; C = 18; }
-  else if (n == "conv_post") { src = (const float*)(ws + w.P); L = F; C = 18; }
+  else if (n == "conv_post") { src = (const float*)(ws + w.P); L = F; C = 18; Cld = kPostPitch; }
   else if (n.size() == 5 && n.compare(0, 4, "fuse") == 0 && n[4] >= '0' && n[4] <= '2') {
     const int i = n[4] - '0';
     src = (const float*)(ws + w.F2[i]); L = stage_len(i, T); C = kStageC[i];
@@ -908,7 +980,7 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
   }
   if ((size_t)B * L * C > out_capacity_elems) return fail(h, "tap output buffer too small");
   out_shape3[0] = B; out_shape3[1] = C; out_shape3[2] = L;
-  GNV_CK(h, "tap", launch_nlc_to_nct(src, B, L, C, C, 4, out_nct, (cudaStream_t)stream));
+  GNV_CK(h, "tap", launch_nlc_to_nct(src, B, L, C, Cld ? Cld : C, 4, out_nct, (cudaStream_t)stream));
   return 0;
 }
 

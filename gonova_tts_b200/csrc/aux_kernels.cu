@@ -279,10 +279,10 @@ cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, float*
 constexpr int kIstftThreads = 256;
 constexpr int kIstftNew = kIstftThreads - 3;
 
-__global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __restrict__ x, int F,
+__global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __restrict__ x, int F, int C_ld,
                                                               const int* __restrict__ lengths, float limit,
                                                               float* __restrict__ wav) {
-  __shared__ float xin[kIstftThreads * 18];
+  __shared__ float xin[kIstftThreads * 20];             // rows of C_ld (18 or 20) floats
   __shared__ float fr[kIstftThreads][17];
   __shared__ float cb[9][16], sb[9][16], w2[16];
   const int b = blockIdx.y;
@@ -301,9 +301,9 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
     if (k == 0) w2[n] = win * win;
   }
   {
-    const long long lo = (long long)fbase * 18, total = (long long)F * 18;
-    const float* xb = x + (size_t)b * F * 18;
-    for (int i = threadIdx.x; i < kIstftThreads * 18; i += blockDim.x) {
+    const long long lo = (long long)fbase * C_ld, total = (long long)F * C_ld;
+    const float* xb = x + (size_t)b * F * C_ld;
+    for (int i = threadIdx.x; i < kIstftThreads * C_ld; i += blockDim.x) {
       const long long g = lo + i;
       xin[i] = (g >= 0 && g < total) ? xb[g] : 0.f;
     }
@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
     const bool live = f >= 0 && f < Fb;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float mag = fminf(expf(xin[threadIdx.x * 18 + k]), 100.f);
-      const float ph = sinf(xin[threadIdx.x * 18 + 9 + k]);
+      const float mag = fminf(expf(xin[threadIdx.x * C_ld + k]), 100.f);
+      const float ph = sinf(xin[threadIdx.x * C_ld + 9 + k]);
       float sn, cs;
       sincosf(ph, &sn, &cs);
       re[k] = live ? mag * cs : 0.f;
@@ -358,12 +358,13 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
   }
 }
 
-cudaError_t launch_istft(const float* x_nlc, int B, int F, const int* lengths, float limit, float* wav,
+cudaError_t launch_istft(const float* x_nlc, int B, int F, int C_ld, const int* lengths, float limit, float* wav,
                          cudaStream_t st) {
   const int L = 4 * (F - 1);
   if (L <= 0) return cudaSuccess;
+  if (C_ld < 18 || C_ld > 20) return cudaErrorInvalidValue;
   dim3 grid((L + kIstftNew * 4 - 1) / (kIstftNew * 4), B);
-  istft_kernel<<<grid, kIstftThreads, 0, st>>>(x_nlc, F, lengths, limit, wav);
+  istft_kernel<<<grid, kIstftThreads, 0, st>>>(x_nlc, F, C_ld, lengths, limit, wav);
   return cudaGetLastError();
 }
 

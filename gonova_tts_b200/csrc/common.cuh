@@ -28,6 +28,7 @@ constexpr int kMaxAct = 3;
 // so the next conv sees exactly the zero padding it would see at the end of that utterance.
 struct EpiParams {
   int C_out, N_valid;
+  int C_pitch;            // channel pitch (elements) of the output tensors; == C_out except conv_post (18 -> 20)
   int up, pad_out, shift, dup_row;
   int L_store, L_out;
   const int* lengths;
@@ -127,7 +128,7 @@ __device__ __forceinline__ void epi_emit(const EpiParams& p, int b, int row, int
     valid_rows = lv < valid_rows ? lv : valid_rows;
   }
   const bool live = row < valid_rows;
-  const size_t base = ((size_t)b * p.L_out + row) * p.C_out + c;
+  const size_t base = ((size_t)b * p.L_out + row) * p.C_pitch + c;
   const bool vec = (nvalid == NC) && ((base % NC) == 0);
   float w[NC];
 #pragma unroll

@@ -39,7 +39,12 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int KBLK_BYTES = 128;                        // one swizzle-128B row
 constexpr int A_TILE_BYTES = BLOCK_M * KBLK_BYTES;     // 16 KiB
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+// Host-mapped debug words (set by tc_debug_init): a barrier wait that times out records
+// {0xDEAD0000 | role, blockIdx.x, barrier smem address, parity} before trapping, so the host can
+// say WHICH wait hung even though the context is lost.
+static __device__ uint32_t* g_tc_debug = nullptr;   // one copy per translation unit; each TU's init sets its own
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -51,7 +56,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
@@ -62,7 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > kSpinLimit) __trap();
+    if (++spins > kSpinLimit) {
+      if (g_tc_debug) {
+        g_tc_debug[1] = blockIdx.x; g_tc_debug[2] = bar; g_tc_debug[3] = parity;
+        g_tc_debug[0] = 0xDEAD0000u | tag;
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -243,5 +255,7 @@ const char* make_conv_tc_launch(ConvTcLaunch* out, int elem_bytes, const void* a
                                 const ConvGeom& g, const EpiParams& ep, int block_n);
 cudaError_t launch_conv_tc(const ConvTcLaunch& L, cudaStream_t st);
 cudaError_t conv_tc_init();           // sets the max-dynamic-smem attribute once per process/device
+const char* tc_debug_string();        // "" or a description of the barrier wait that timed out
+cudaError_t tc_debug_device_ptr(uint32_t** out);   // device address of the host-mapped debug words
 
 }  // namespace gnv

@@ -1,0 +1,502 @@
+// Persistent tcgen05 implicit-GEMM Conv1d / polyphase ConvTranspose1d for sm_100a — version 2.
+//
+//   D[m, n] = sum_{tap} sum_{ci} A[b, m + off0 + tap*tap_step, ci] * W[n, tap*C_in + ci]
+//
+// What changed against conv_tc.cuh (kept as the simple reference kernel, GNV_FLAG_TC_V1):
+//   * persistent: one CTA per SM walks a static round-robin list of (utterance, m-tile, n-tile)
+//     tiles, so barrier init / TMEM alloc / descriptor prefetch are paid once per launch, and the
+//     epilogue of tile i overlaps the main loop of tile i+1 (accumulators double-buffered in TMEM);
+//   * A "slab": one TMA box brings 128*mh + (taps-1)*dilation consecutive time rows of one 64-channel
+//     block; every tap's MMA reads the SAME slab through a shared-memory descriptor whose start
+//     address is advanced by tap*dilation rows (128 B per row in the K-major SWIZZLE_128B layout).
+//     L2 -> SMEM traffic for activations drops by the number of taps;
+//   * mh = 2: two 128-row accumulators share every weight tile (halves the weight traffic per FLOP);
+//   * the epilogue never touches global memory with per-thread strided accesses: the residual /
+//     running-sum tiles are prefetched by TMA into shared memory by a dedicated warp while the main
+//     loop runs, results are staged in (swizzled) shared memory and leave through TMA stores, which
+//     also clip rows past the tensor end.  The polyphase scatter of the ConvTranspose is a tensor map
+//     per phase (row stride = up * C), so it is a plain box store as well.
+//
+// Warp roles (256 threads): 0 = TMA producer (A slabs + W tiles), 1 = MMA issuer, 2 = TMEM
+// allocator, 3 = epilogue-input TMA loader, 4..7 = epilogue (one TMEM lane quarter each).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace gnv {
+
+constexpr int kMaxPhase = 8;
+constexpr int kMaxSlab = 12;
+constexpr int kEpiCols = 32;    // columns per epilogue chunk (one 128-byte fp32 row)
+
+enum { EPI_IN0 = 0, EPI_IN1 = 1, EPI_RAW = 2, EPI_ACT0 = 3 };   // index into ConvTc2Maps::epi[phase][.]
+
+struct ConvTc2Params {
+  int B, M_rows;
+  int n_taps, n_chunks;
+  int block_n, n_tiles_n, mh, tiles_m, total_tiles;
+  int transposed;                  // epilogue tensor maps are per phase (= n tile), columns start at 0
+  int row_adj[kMaxPhase];          // transposed: TMA row coordinate = m - row_adj[phase]
+  // A slabs: slab s of a channel block covers taps [slab_tap0[s], slab_tap0[s+1]) and holds
+  // a_n_boxes * a_box_rows rows starting at tile row m0 + slab_row0[s]; tap j reads tile rows m0 + tap_row[j] ...
+  int n_slabs;
+  int slab_tap0[kMaxSlab + 1];
+  int slab_row0[kMaxSlab];
+  int tap_row[kMaxSlab];
+  int a_box_rows, a_n_boxes;       // every slab is a_n_boxes TMA boxes of a_box_rows rows
+  int a_base_offset_mode;          // 1: descriptor base_offset = (start address >> 7) & 7
+  int sa, sw, n_out_bufs, acc_bufs;
+  int slab_bytes, w_bytes;
+  int tmem_cols;
+  uint32_t idesc;
+  int n_in, has_raw, n_act;
+  int act_bytes;                   // bytes of one staged activation tile (128 rows x 32 cols x sizeof(E))
+  int c_tab;                       // pitch of the per-channel tables (C_out rounded up to 32)
+  uint32_t off_a, off_w, off_in, off_out, off_tab, off_bar;   // shared-memory carve-up
+  EpiParams ep;
+};
+
+struct ConvTc2Maps {
+  CUtensorMap A, W;
+  CUtensorMap epi[kMaxPhase][6];   // in0 (residual), in1 (running sum), raw, act0..2
+};
+
+#ifdef __CUDACC__
+namespace tc2 {
+using namespace tc;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16-byte shared-memory accesses into a [128 rows][32 cols] tile as TMA lays it out:
+// fp32 rows are 128 B (SWIZZLE_128B: chunk ^= row & 7), bf16 rows are 64 B (SWIZZLE_64B: chunk ^= (row >> 1) & 3).
+__device__ __forceinline__ uint32_t tile_addr_f32(uint32_t tile, int row, int chunk) {
+  return tile + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint32_t tile_addr_b16(uint32_t tile, int row, int chunk) {
+  return tile + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+struct Ring {
+  int slot = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int depth) {
+    if (++slot == depth) { slot = 0; phase ^= 1u; }
+  }
+};
+
+}  // namespace tc2
+
+template <typename E>
+__global__ void __launch_bounds__(256, 1)
+conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ ConvTc2Params p) {
+  using namespace tc2;
+  const ConvTc2Maps& maps = *maps_g;          // tensor maps live in global memory (6.4 KB: too big for the
+                                              // 4 KB of classic parameter space the TMA unit can always reach)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sA = smem_base + p.off_a, sW = smem_base + p.off_w;
+  const uint32_t sIn = smem_base + p.off_in, sOut = smem_base + p.off_out;
+  float* tab = reinterpret_cast<float*>(smem_gen + p.off_tab);      // bias[C_out], then per act: alpha[C_out], inv[C_out]
+  // barriers (8 B each): a_full[sa] a_empty[sa] w_full[sw] w_empty[sw] acc_full[2] acc_empty[2] in_full[2] in_empty[2]
+  const uint32_t bar0 = smem_base + p.off_bar;
+  const uint32_t b_a_full = bar0, b_a_empty = b_a_full + 8u * p.sa;
+  const uint32_t b_w_full = b_a_empty + 8u * p.sa, b_w_empty = b_w_full + 8u * p.sw;
+  const uint32_t b_acc_full = b_w_empty + 8u * p.sw, b_acc_empty = b_acc_full + 16u;
+  const uint32_t b_in_full = b_acc_empty + 16u, b_in_empty = b_in_full + 16u;
+  const uint32_t tmem_slot = b_in_empty + 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KBE = KBLK_BYTES / (int)sizeof(E);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.A);
+    prefetch_tmap(&maps.W);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.sa; ++s) { mbar_init(b_a_full + 8u * s, 1); mbar_init(b_a_empty + 8u * s, 1); }
+    for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_acc_full + 8u * s, 1);
+      mbar_init(b_acc_empty + 8u * s, 4);
+      mbar_init(b_in_full + 8u * s, 1);
+      mbar_init(b_in_empty + 8u * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // per-channel epilogue tables: bias, then (alpha, 1/(alpha + 1e-9)) per fused activation
+  {
+    const int C = p.ep.C_out, Cp = p.c_tab;
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+      tab[c] = (c < C && p.ep.bias) ? p.ep.bias[c] : 0.f;
+      for (int a = 0; a < p.n_act; ++a) {
+        const float al = (c < C && p.ep.act_alpha[a]) ? p.ep.act_alpha[a][c] : 1.f;
+        tab[(1 + 2 * a) * Cp + c] = al;
+        tab[(2 + 2 * a) * Cp + c] = 1.0f / (al + 1e-9f);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int rows_per_tile = BLOCK_M * p.mh;
+  const int n_epi_chunks = p.block_n / kEpiCols;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: A slabs and W tiles, in the order the MMA issuer consumes them =====
+      Ring ra, rw;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int q = t;
+        const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
+        const int m_tile = q % p.tiles_m;
+        const int b = q / p.tiles_m;
+        // polyphase tiles start at the phase's first valid GEMM row (row_adj), so that every TMA store
+        // coordinate is non-negative
+        const int m0 = m_tile * rows_per_tile + (p.transposed ? p.row_adj[n_tile] : 0), n0 = n_tile * p.block_n;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int s = 0; s < p.n_slabs; ++s) {
+            mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u);
+            const uint32_t dst = sA + ra.slot * p.slab_bytes;
+            // a TMA box holds at most 256 rows: taller slabs arrive as two boxes of a_box_rows rows
+            mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES);
+            const int r0 = m0 + p.slab_row0[s];
+            for (int bx = 0; bx < p.a_n_boxes; ++bx)
+              tma_load_3d(&maps.A, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
+                          r0 + bx * p.a_box_rows, b);
+            ra.advance(p.sa);
+            for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; ++tap) {
+              mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u);
+              mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)p.w_bytes);
+              tma_load_2d(&maps.W, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_bytes,
+                          (tap * p.n_chunks + ch) * KBE, n0);
+              rw.advance(p.sw);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      Ring ra, rw, racc;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(b_acc_empty + 8u * racc.slot, racc.phase ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc0 = tmem_base + (uint32_t)(racc.slot * p.mh * p.block_n);
+        bool first = true;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int s = 0; s < p.n_slabs; ++s) {
+            mbar_wait(b_a_full + 8u * ra.slot, ra.phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t slab = sA + ra.slot * p.slab_bytes;
+            for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; ++tap) {
+              mbar_wait(b_w_full + 8u * rw.slot, rw.phase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t bd = umma_desc_sw128(sW + rw.slot * p.w_bytes);
+              for (int h = 0; h < p.mh; ++h) {
+                const uint32_t a_addr = slab + (uint32_t)(p.tap_row[tap] - p.slab_row0[s] + h * BLOCK_M) * KBLK_BYTES;
+                uint64_t ad = umma_desc_sw128(a_addr);
+                if (p.a_base_offset_mode) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
+#pragma unroll
+                for (int k = 0; k < KBLK_BYTES / 32; ++k)
+                  umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              umma_commit(b_w_empty + 8u * rw.slot);
+              rw.advance(p.sw);
+            }
+            umma_commit(b_a_empty + 8u * ra.slot);
+            ra.advance(p.sa);
+          }
+        }
+        umma_commit(b_acc_full + 8u * racc.slot);
+        racc.advance(p.acc_bufs);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0 && p.n_in > 0) {
+      // ===== epilogue-input loader: residual / running-sum tiles -> shared memory =====
+      Ring rin;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int q = t;
+        const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
+        const int m_tile = q % p.tiles_m;
+        const int b = q / p.tiles_m;
+        const int n0 = n_tile * p.block_n;
+        const int ph = p.transposed ? n_tile : 0;
+        const int cbase = p.transposed ? 0 : n0;
+        for (int h = 0; h < p.mh; ++h) {
+          const int mrow = m_tile * rows_per_tile + h * BLOCK_M;      // TMA row coordinate (GEMM row - row_adj)
+          for (int cc = 0; cc < n_epi_chunks; ++cc) {
+            mbar_wait(b_in_empty + 8u * rin.slot, rin.phase ^ 1u);
+            mbar_expect_tx(b_in_full + 8u * rin.slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
+            for (int i = 0; i < p.n_in; ++i)
+              tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * rin.slot,
+                          sIn + (rin.slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
+            rin.advance(2);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> bias / residual / activations -> shared -> TMA store =====
+    const int q = warp & 3;
+    const int erow = q * 32 + lane;                     // row inside a 128-row half == TMEM lane
+    const int etid = threadIdx.x - 128;
+    const int C = p.ep.C_out;
+    const int out_stride = (p.has_raw ? BLOCK_M * kEpiCols * 4 : 0) + p.n_act * p.act_bytes;
+    Ring racc, rin;
+    int ob = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int qq = t;
+      const int n_tile = qq % p.n_tiles_n; qq /= p.n_tiles_n;
+      const int m_tile = qq % p.tiles_m;
+      const int b = qq / p.tiles_m;
+      const int ph = p.transposed ? n_tile : 0;
+      const int m0 = m_tile * rows_per_tile + (p.transposed ? p.row_adj[ph] : 0), n0 = n_tile * p.block_n;
+      const int cbase = p.transposed ? 0 : n0;           // channel of the tile's first column
+      int valid_rows = p.ep.L_out;
+      if (p.ep.lengths) {
+        const int lv = p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
+        valid_rows = lv < valid_rows ? lv : valid_rows;
+      }
+      mbar_wait(b_acc_full + 8u * racc.slot, racc.phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int h = 0; h < p.mh; ++h) {
+        const int m = m0 + h * BLOCK_M + erow;
+        const int p0 = m * p.ep.up + (p.transposed ? n_tile : 0) - p.ep.pad_out;
+        const int row = p0 + p.ep.shift;
+        const bool live = (m < p.M_rows) && (p0 >= 0) && (p0 < p.ep.L_store) && (row < valid_rows);
+        const int mrow = m_tile * rows_per_tile + h * BLOCK_M;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
+                              (uint32_t)((racc.slot * p.mh + h) * p.block_n);
+        for (int cc = 0; cc < n_epi_chunks; ++cc) {
+          float v[32];
+          tmem_ld32(trow + (uint32_t)(cc * kEpiCols), v);
+          const int c0 = cbase + cc * kEpiCols;          // channel index of v[0]
+          // ---- bias, residual, running sum ----   (tables are padded to 32 columns: conv_post has C_out = 18)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += tab[c0 + i];
+          // ReflectionPad1d((1,0)): the conv row p0 == dup_row is ALSO output row 0, where it meets the
+          // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk.
+          if (p.ep.dup_row >= 0 && p0 == p.ep.dup_row && m < p.M_rows) {
+            const size_t g0 = (size_t)b * p.ep.L_out * p.ep.C_pitch + c0;
+            const bool live0 = 0 < valid_rows;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (c0 + i >= C) continue;
+              float u = v[i];
+              if (p.ep.res) u += p.ep.res[g0 + i];
+              u *= p.ep.raw_scale;
+              if (p.ep.raw_accum) u += p.ep.raw[g0 + i];
+              if (!live0) u = 0.f;
+              if (p.has_raw) p.ep.raw[g0 + i] = u;
+              for (int a = 0; a < p.n_act; ++a) {
+                const float y0 = live0 ? act_apply(p.ep.act_kind[a], u, tab[(1 + 2 * a) * p.c_tab + c0 + i],
+                                                   p.ep.act_slope[a]) : 0.f;
+                E* dst = reinterpret_cast<E*>(p.ep.act_out[a]) + g0 + i;
+                if constexpr (sizeof(E) == 4) ElemIO<E>::store(dst, p.ep.round_tf32 ? round_tf32(y0) : y0);
+                else ElemIO<E>::store(dst, y0);
+              }
+            }
+          }
+          if (p.n_in > 0) {
+            mbar_wait(b_in_full + 8u * rin.slot, rin.phase);
+            const uint32_t in0 = sIn + (rin.slot * p.n_in) * (BLOCK_M * kEpiCols * 4);
+            if (p.ep.res) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = lds128(tile_addr_f32(in0, erow, j));
+                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
+            if (p.ep.raw_accum) {
+              const uint32_t in1 = in0 + (p.ep.res ? BLOCK_M * kEpiCols * 4 : 0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = lds128(tile_addr_f32(in1, erow, j));
+                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_in_empty + 8u * rin.slot);
+            rin.advance(2);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
+          }
+          if (!live) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          // ---- stage the outputs ----
+          const uint32_t obase = sOut + ob * out_stride;
+          if (etid == 0) {
+            if (p.n_out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
+          epi_bar_sync();
+          uint32_t o = obase;
+          if (p.has_raw) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(tile_addr_f32(o, erow, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            o += BLOCK_M * kEpiCols * 4;
+          }
+          for (int a = 0; a < p.n_act; ++a) {
+            const int kind = p.ep.act_kind[a];
+            const float slope = p.ep.act_slope[a];
+            const float* al = tab + (1 + 2 * a) * p.c_tab;
+            const float* iv = tab + (2 + 2 * a) * p.c_tab;
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = v[i];
+              float r;
+              if (kind == ACT_SNAKE_FAST) {
+                const float s = __sinf(x * al[c0 + i]);
+                r = fmaf(iv[c0 + i], s * s, x);
+              } else if (kind == ACT_SNAKE) {
+                const float s = sinf(x * al[c0 + i]);
+                r = x + iv[c0 + i] * (s * s);
+              } else if (kind == ACT_LRELU) {
+                r = x > 0.f ? x : x * slope;
+              } else if (kind == ACT_ELU) {
+                r = x > 0.f ? x : expm1f(x);
+              } else {
+                r = x;
+              }
+              y[i] = live ? r : 0.f;
+            }
+            if constexpr (sizeof(E) == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128u(tile_addr_b16(o, erow, j), ElemIO<E>::pack2(y[8 * j], y[8 * j + 1]),
+                        ElemIO<E>::pack2(y[8 * j + 2], y[8 * j + 3]), ElemIO<E>::pack2(y[8 * j + 4], y[8 * j + 5]),
+                        ElemIO<E>::pack2(y[8 * j + 6], y[8 * j + 7]));
+            } else {
+              if (p.ep.round_tf32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = round_tf32(y[i]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(tile_addr_f32(o, erow, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            }
+            o += p.act_bytes;
+          }
+          fence_async_smem();
+          epi_bar_sync();
+          if (etid == 0) {
+            uint32_t src = obase;
+            const int cs = cbase + cc * kEpiCols;
+            if (p.has_raw) {
+              tma_store_3d(&maps.epi[ph][EPI_RAW], src, cs, mrow, b);
+              src += BLOCK_M * kEpiCols * 4;
+            }
+            for (int a = 0; a < p.n_act; ++a) {
+              tma_store_3d(&maps.epi[ph][EPI_ACT0 + a], src, cs, mrow, b);
+              src += p.act_bytes;
+            }
+            bulk_commit();
+          }
+          if (++ob == p.n_out_bufs) ob = 0;
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_acc_empty + 8u * racc.slot);
+      racc.advance(p.acc_bufs);
+    }
+    if (etid == 0) bulk_wait_read<0>();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+#endif  // __CUDACC__
+
+// ---- host side --------------------------------------------------------------------------------
+struct ConvTc2Launch {
+  ConvTc2Maps maps;                 // host copy; the caller uploads it and sets d_maps before launching
+  const ConvTc2Maps* d_maps = nullptr;
+  ConvTc2Params p;
+  int grid;
+  size_t smem_bytes;
+  int elem_bytes;
+};
+
+struct ConvTc2Options {
+  int slab_mode = 1;     // 0: one slab per tap; 1: one slab per channel block, taps by descriptor row offset (base_offset 0 — measured correct); 2: same with base_offset set (measured WRONG on B200, kept for the record)
+  int mh = 0;            // 0 = choose
+  int max_ctas = 148;
+};
+
+// `act` = A tensor [B, L_in, C_in_ld] (E); `w` = packed weights [w_rows_alloc, n_taps*C_in_ld] (E).
+// Output tensors are [B, ep.L_out, ep.C_out] with channel pitch `c_pitch_out` elements (== C_out except conv_post).
+const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void* act, const void* w, int w_rows_alloc,
+                                 const ConvGeom& g, const EpiParams& ep, int c_pitch_out, const ConvTc2Options& opt);
+cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStream_t st);
+cudaError_t conv_tc2_init();
+
+}  // namespace gnv

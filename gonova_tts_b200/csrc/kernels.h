@@ -19,8 +19,9 @@ cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const fl
                           const float* lin_w /*[9]*/, const float* lin_b /*[1]*/, float* s, cudaStream_t st);
 // STFT n_fft 16 hop 4, periodic Hann, center/reflect: s [B, L] (row stride L) -> spec [B, F=L/4+1, 18] fp32
 cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, float* spec_nlc, cudaStream_t st);
-// exp/min/sin + iSTFT + clamp: x [B, F, 18] fp32 -> wav [B, 4(F-1)]
-cudaError_t launch_istft(const float* x_nlc, int B, int F, const int* lengths, float limit, float* wav, cudaStream_t st);
+// exp/min/sin + iSTFT + clamp: x [B, F, C_ld >= 18] fp32 (first 18 channels used) -> wav [B, 4(F-1)]
+cudaError_t launch_istft(const float* x_nlc, int B, int F, int C_ld, const int* lengths, float limit, float* wav,
+                         cudaStream_t st);
 // streaming tail
 cudaError_t launch_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, const float* fade_w,
                             int rows, int n, int fade, float limit, int16_t* out_i16, float* out_f32,

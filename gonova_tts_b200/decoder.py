@@ -56,7 +56,7 @@ class B200HiFT:
     audio_limit = 0.99
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dtype: str = "bf16",
-                 simt_conv: bool = False, precise_act: bool = False, prefix: str = ""):
+                 simt_conv: bool = False, precise_act: bool = False, tc_v1: bool = False, prefix: str = ""):
         if dtype not in _cabi.DTYPE:
             raise ValueError(f"dtype must be one of {sorted(_cabi.DTYPE)}")
         self.device = torch.device(device)
@@ -78,7 +78,8 @@ class B200HiFT:
             arr[i].ndim = t.dim()
             for d in range(t.dim()):
                 arr[i].shape[d] = t.shape[d]
-        flags = (_cabi.FLAG_SIMT_CONV if simt_conv else 0) | (_cabi.FLAG_PRECISE_ACT if precise_act else 0)
+        flags = ((_cabi.FLAG_SIMT_CONV if simt_conv else 0) | (_cabi.FLAG_PRECISE_ACT if precise_act else 0) |
+                 (_cabi.FLAG_TC_V1 if tc_v1 else 0))
         h = C.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", dev_index)
