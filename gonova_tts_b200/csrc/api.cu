@@ -7,7 +7,7 @@
 //   s -> spec [B,F,18] fp32                                 STFT kernel
 //   conv_pre            melE -> X0 = lrelu(.)               conv GEMM, activation fused
 //   per stage i (C = 256/128/64, L = 8T/40T/120T+1):
-//     source_downs[i]   spec -> F1 (raw), E0 = snake        strided conv (CUDA cores, K = 18k)
+//     source_downs[i]   spec -> F1 (raw), E0 = snake        GEMM over k consecutive STFT frames (K = k*Cs)
 //     source_resblock   6 conv GEMMs, residual stream F1 updated in place
 //     ups[i]            X_i -> F2 = convT + bias + F1,  E0/E1/E2 = snake_j(F2)   (polyphase GEMM)
 //     resblocks 3i+j    6 conv GEMMs each on (E_j, E3, F1); the last one accumulates F3 += x/3 and,
@@ -42,6 +42,8 @@ thread_local std::string tl_error;
 
 constexpr int kSPF = 480;
 constexpr int kMelC = 80;
+constexpr int kSpecFront = 8;    // zero rows before / after the STFT frames of each utterance (conv + GEMM-K padding)
+constexpr int kSpecBack = 40;
 constexpr int kPostPitch = 20;   // conv_post output [B, F, 18] is stored with a 16-byte-multiple channel pitch (TMA)
 
 struct HostT {
@@ -70,7 +72,10 @@ inline float host_round_tf32(float x) {
 struct ConvLayer {
   int C_in = 0, C_out = 0, k = 1, stride = 1, pad = 0, dil = 1;
   bool transposed = false;
-  bool strided_simt = false;   // source_downs: fp32 operands, strided rows, CUDA cores only
+  bool strided_simt = false;   // source_downs on CUDA cores: strided rows, K = 18*k
+  bool flat = false;           // source_downs as a GEMM over k consecutive STFT frames (tensor cores)
+  int conv_k = 0, conv_stride = 0, conv_pad = 0;   // the real conv geometry behind a flat layer
+  double flops_per_row = 0.0;  // algorithmic flops per output row (0 = 2*C_out*C_in*k)
   int C_in_ld = 0;             // channel stride of the A operand (and of each tap in the packed W)
   int n_taps = 0;
   int N_valid = 0, N_total = 0, block_n = 0;
@@ -182,7 +187,8 @@ struct gnv_decoder {
   int snake_kind = ACT_SNAKE;
   std::string err;
   std::vector<void*> allocs;
-  ConvLayer conv_pre, ups[3], sdown[3], conv_post, f0c[5];
+  ConvLayer conv_pre, ups[3], sdown[3], sdown_flat[3], conv_post, f0c[5];
+  int spec_cs = 20;      // channel pitch of the STFT buffer (18 -> 24 bf16 / 20 fp32: 16-byte multiples)
   ResBlockW rb[9], srb[3];
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr;
   std::map<PlanKey, Plan> plans;
@@ -267,7 +273,7 @@ bool pack_layer(gnv_handle h, Uploader& up, const WeightMap& wm, const std::stri
   if (!shape_ok) { *err = "bad shape for '" + prefix + "'"; return false; }
   L.C_in = C_in; L.C_out = C_out; L.k = k; L.stride = stride; L.pad = pad; L.dil = dil;
   L.transposed = transposed; L.strided_simt = strided_simt;
-  const int eb = strided_simt ? 4 : h->eb;
+  const int eb = h->eb;
   const int kbe = 128 / eb;
   L.C_in_ld = strided_simt ? C_in : (int)align_up(C_in, kbe);
   L.w_elem = eb;
@@ -302,7 +308,42 @@ bool pack_layer(gnv_handle h, Uploader& up, const WeightMap& wm, const std::stri
     for (size_t i = 0; i < P.size(); ++i) Q[i] = __float2bfloat16_rn(P[i]);
     L.w = up.put(Q.data(), Q.size() * 2);
   } else {
-    if (!strided_simt && h->dtype == GNV_DTYPE_TF32)
+    if (h->dtype == GNV_DTYPE_TF32)
+      for (auto& v : P) v = host_round_tf32(v);
+    L.w = up.put(P.data(), P.size() * 4);
+  }
+  L.bias = (float*)up.put(b->data, (size_t)C_out * 4);
+  return up.ok;
+}
+
+// source_downs[i] as a plain GEMM: the STFT buffer is [rows, Cs] with Cs*elem a 16-byte multiple, so
+// the k frames a strided conv reads for output row m are ONE contiguous run of k*Cs elements starting
+// at frame (m*stride - pad).  The A operand is the overlapping-row view {row stride = stride*Cs};
+// W[n, j*Cs + c] = w[n, c, j], zero for the padding channels and up to the 128-byte K block.
+bool pack_flat(gnv_handle h, Uploader& up, const WeightMap& wm, const std::string& prefix, ConvLayer& L, int C_in,
+               int C_out, int k, int stride, int pad, std::string* err) {
+  const HostT* w = find(wm, prefix + ".weight", err);
+  const HostT* b = find(wm, prefix + ".bias", err);
+  if (!w || !b) return false;
+  if (w->numel() != (int64_t)C_in * C_out * k || b->numel() != C_out) { *err = "bad shape for '" + prefix + "'"; return false; }
+  const int eb = h->eb, kbe = 128 / eb, Cs = h->spec_cs;
+  const int K = (int)align_up((size_t)k * Cs, kbe);
+  L = ConvLayer();
+  L.C_in = K; L.C_out = C_out; L.k = 1; L.stride = 1; L.pad = 0; L.dil = 1;
+  L.flat = true; L.conv_k = k; L.conv_stride = stride; L.conv_pad = pad;
+  L.flops_per_row = 2.0 * C_out * C_in * k;
+  L.C_in_ld = K; L.w_elem = eb; L.n_taps = 1;
+  L.N_valid = C_out; L.block_n = choose_block_n(C_out); L.N_total = (int)align_up(C_out, L.block_n);
+  std::vector<float> P((size_t)L.N_total * K, 0.f);
+  for (int co = 0; co < C_out; ++co)
+    for (int ci = 0; ci < C_in; ++ci)
+      for (int j = 0; j < k; ++j) P[(size_t)co * K + (size_t)j * Cs + ci] = w->data[((size_t)co * C_in + ci) * k + j];
+  if (eb == 2) {
+    std::vector<__nv_bfloat16> Q(P.size());
+    for (size_t i = 0; i < P.size(); ++i) Q[i] = __float2bfloat16_rn(P[i]);
+    L.w = up.put(Q.data(), Q.size() * 2);
+  } else {
+    if (h->dtype == GNV_DTYPE_TF32)
       for (auto& v : P) v = host_round_tf32(v);
     L.w = up.put(P.data(), P.size() * 4);
   }
@@ -345,7 +386,7 @@ WsLayout make_layout(const gnv_decoder* h, int B, int T) {
   const size_t eb = h->eb;
   const int F = 120 * T + 1;
   w.melE = take((size_t)B * T * h->conv_pre.C_in_ld * eb);
-  w.spec = take((size_t)B * F * 18 * 4);
+  w.spec = take((size_t)B * (F + kSpecFront + kSpecBack) * h->spec_cs * eb);
   w.X0 = take((size_t)B * T * 512 * eb);
   w.P = take((size_t)B * F * kPostPitch * 4);
   w.H0 = take((size_t)B * T * 512 * eb);
@@ -383,13 +424,14 @@ struct EpiSpec {
 
 // Builds the GEMM geometry + fused epilogue of one layer on input [B, L_in, C_in_ld].
 std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int B, int L_in, const EpiSpec& es,
-                    ConvOp* op) {
+                    ConvOp* op, long long a_row_stride = 0, long long a_batch_stride = 0) {
   ConvGeom& g = op->g;
   EpiParams& ep = op->ep;
   memset(&g, 0, sizeof(g));
   memset(&ep, 0, sizeof(ep));
   g.B = B; g.L_in = L_in; g.C_in = L.C_in; g.C_in_ld = L.C_in_ld; g.C_in_w = L.C_in_ld;
   g.N_total = L.N_total; g.n_taps = L.n_taps;
+  g.a_row_stride = a_row_stride; g.a_batch_stride = a_batch_stride;
   ep.C_out = L.C_out; ep.N_valid = L.N_valid;
   ep.C_pitch = es.c_pitch > 0 ? es.c_pitch : L.C_out;
   if (L.transposed) {
@@ -421,7 +463,7 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
   op->A = A; op->W = L.w;
   if (L.strided_simt) {
     op->tc = false;
-    op->variant = h->eb == 2 ? SV_FFB : SV_FFF;
+    op->variant = h->eb == 2 ? SV_BBB : SV_FFF;
     return "";
   }
   if (h->use_tc) {
@@ -461,15 +503,16 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   auto Fp = [&](size_t off) { return (float*)(base + off); };
   std::string e;
   auto add = [&](std::vector<ConvOp>& ops, const ConvLayer& L, const void* A, int L_in, const EpiSpec& es,
-                 const std::string& name) {
-    if (!e.empty()) return;
+                 const std::string& name, long long a_row_stride = 0, long long a_batch_stride = 0) -> bool {
+    if (!e.empty()) return false;
     ConvOp op;
-    e = make_op(h, L, A, B, L_in, es, &op);
-    if (!e.empty()) { e = name + ": " + e; return; }
+    std::string me = make_op(h, L, A, B, L_in, es, &op, a_row_stride, a_batch_stride);
+    if (!me.empty()) { e = name + ": " + me; return false; }
     op.name = name;
     const double rows = L.transposed ? (double)L_in : (double)op.ep.L_store;
-    op.flops = 2.0 * B * rows * L.C_out * L.C_in * L.k;
+    op.flops = L.flops_per_row > 0 ? B * rows * L.flops_per_row : 2.0 * B * rows * L.C_out * L.C_in * L.k;
     ops.push_back(op);
+    return true;
   };
   const int snake = h->snake_kind;
   const int F = 120 * T + 1;
@@ -526,7 +569,18 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
       EpiSpec es; es.len_mul = lm; es.len_add = la;
       es.raw = F1;
       es.acts.push_back({snake, h->srb[i].a1[0], 0.f, E[0]});
-      add(ops, h->sdown[i], P(w.spec), F, es, "source_downs." + std::to_string(i));
+      // STFT buffer: [B, front + F + back, Cs] of E; frame f of utterance b is row front + f
+      const int Cs = h->spec_cs, Fp = F + kSpecFront + kSpecBack;
+      const char* spec0 = (const char*)P(w.spec);
+      const std::string nm = "source_downs." + std::to_string(i);
+      bool done = false;
+      if (h->use_tc && h->tc_version == 2) {
+        const ConvLayer& Lf = h->sdown_flat[i];
+        const void* Av = spec0 + (size_t)(kSpecFront - Lf.conv_pad) * Cs * h->eb;
+        done = add(ops, Lf, Av, Ls, es, nm, (long long)Lf.conv_stride * Cs, (long long)Fp * Cs);
+        if (!done) e.clear();          // tensor map refused (overlapping rows): fall back to the CUDA-core kernel
+      }
+      if (!done) add(ops, h->sdown[i], spec0 + (size_t)kSpecFront * Cs * h->eb, F, es, nm, Cs, (long long)Fp * Cs);
     }
     resblock(h->srb[i], E[0], F1, F1, false, 0, "source_resblocks." + std::to_string(i));
     // upsampling + fuse
@@ -620,7 +674,8 @@ int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const
                                             h->dtype == GNV_DTYPE_TF32, st));
     prof_mark(prof, "pack_mel", GNV_LAUNCH_AUX);
   }
-  GNV_CK(h, "stft", launch_stft(s, B, T * kSPF, lengths, (float*)(ws + w.spec), st));
+  GNV_CK(h, "stft", launch_stft(s, B, T * kSPF, lengths, ws + w.spec, h->eb, h->dtype == GNV_DTYPE_TF32, h->spec_cs,
+                                kSpecFront, 120 * T + 1 + kSpecFront + kSpecBack, st));
   prof_mark(prof, "stft", GNV_LAUNCH_AUX);
   for (const ConvOp& op : plan->decode_ops) {
     GNV_CK(h, "conv", run_op(op, lengths, st));
@@ -680,6 +735,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   gnv_decoder* h = new gnv_decoder();
   h->device = device; h->dtype = dtype; h->flags = flags;
   h->eb = dtype == GNV_DTYPE_BF16 ? 2 : 4;
+  h->spec_cs = dtype == GNV_DTYPE_BF16 ? 24 : 20;
   h->use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV);
   h->tc_version = (flags & GNV_FLAG_TC_V1) ? 1 : 2;
   h->tc2opt = tc2_options_from_env();
@@ -695,6 +751,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
                           (kUpK[i] - kUpRate[i]) / 2, 1, true, false, &err);
     ok = ok && pack_layer(h, up, wm, "source_downs." + si, h->sdown[i], 18, cout, kSdK[i], kSdS[i], kSdP[i], 1, false,
                           true, &err);
+    ok = ok && pack_flat(h, up, wm, "source_downs." + si, h->sdown_flat[i], 18, cout, kSdK[i], kSdS[i], kSdP[i], &err);
     ok = ok && pack_resblock(h, up, wm, "source_resblocks." + si, h->srb[i], cout, kSrbK[i], &err);
     for (int j = 0; ok && j < 3; ++j)
       ok = ok && pack_resblock(h, up, wm, "resblocks." + std::to_string(3 * i + j), h->rb[3 * i + j], cout, kRbK[j],
@@ -853,7 +910,7 @@ int gnv_stft(const float* s, int B, int L, float* spec_nct, void* stream) {
   cudaError_t e;
   float* nlc = (float*)sc.get((size_t)B * F * 18 * 4, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
-  GNV_CK(nullptr, "stft", launch_stft(s, B, L, nullptr, nlc, st));
+  GNV_CK(nullptr, "stft", launch_stft(s, B, L, nullptr, nlc, 4, 0, 18, 0, F, st));
   GNV_CK(nullptr, "unpack", launch_nlc_to_nct(nlc, B, F, 18, 18, 4, spec_nct, st));
   GNV_CK(nullptr, "sync", cudaStreamSynchronize(st));
   return 0;
@@ -920,7 +977,7 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
   if (!up.ok) return fail(nullptr, up.msg);
   Scratch sc;
   cudaError_t e;
-  const int a_eb = strided ? 4 : tmp.eb;
+  const int a_eb = tmp.eb;
   void* A = sc.get((size_t)B * Lin * L.C_in_ld * a_eb, &e);
   if (e != cudaSuccess) return fail_cuda(nullptr, "cudaMalloc", e);
   float* raw = (float*)sc.get((size_t)B * Lout * Cp * 4, &e);
@@ -934,7 +991,7 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
     GNV_CK(nullptr, "pack res", launch_nct_to_nlc(res_nct, B, Cout, Lout, nullptr, res, Cp, 4, 0, st));
   }
   GNV_CK(nullptr, "pack x", launch_nct_to_nlc(x, B, Cin, Lin, nullptr, A, L.C_in_ld, a_eb,
-                                              (!strided && dtype == GNV_DTYPE_TF32) ? 1 : 0, st));
+                                              dtype == GNV_DTYPE_TF32 ? 1 : 0, st));
   EpiSpec es;
   es.res = res;
   es.raw = raw;
@@ -967,7 +1024,14 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
   const float* src = nullptr;
   int L = 0, C = 0, Cld = 0;
   const int F = 120 * T + 1;
-  if (n == "s_stft") { src = (const float*)(ws + w.spec); L = F; C = 18; }
+  if (n == "s_stft") {
+    if ((size_t)B * F * 18 > out_capacity_elems) return fail(h, "tap output buffer too small");
+    out_shape3[0] = B; out_shape3[1] = 18; out_shape3[2] = F;
+    const int Cs = h->spec_cs;
+    GNV_CK(h, "tap", launch_nlc_to_nct(ws + w.spec + (size_t)kSpecFront * Cs * h->eb, B, F, 18, Cs, h->eb, out_nct,
+                                       (cudaStream_t)stream, (long long)(F + kSpecFront + kSpecBack) * Cs));
+    return 0;
+  }
   else if (n == "conv_post") { src = (const float*)(ws + w.P); L = F; C = 18; Cld = kPostPitch; }
   else if (n.size() == 5 && n.compare(0, 4, "fuse") == 0 && n[4] >= '0' && n[4] <= '2') {
     const int i = n[4] - '0';

@@ -32,13 +32,14 @@ __global__ void nct_to_nlc_kernel(const float* __restrict__ in, int C, int L, co
 }
 
 template <typename E>
-__global__ void nlc_to_nct_kernel(const E* __restrict__ in, int L, int C, int C_ld, float* __restrict__ out) {
+__global__ void nlc_to_nct_kernel(const E* __restrict__ in, int L, int C, int C_ld, long long in_batch_stride,
+                                  float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (int i = ty; i < 32; i += 8) {
     const int l = l0 + i, c = c0 + tx;
-    tile[i][tx] = (l < L && c < C) ? ElemIO<E>::load(in + ((size_t)b * L + l) * C_ld + c) : 0.f;
+    tile[i][tx] = (l < L && c < C) ? ElemIO<E>::load(in + (size_t)b * in_batch_stride + (size_t)l * C_ld + c) : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -58,12 +59,13 @@ cudaError_t launch_nct_to_nlc(const float* in, int B, int C, int L, const int* l
 }
 
 cudaError_t launch_nlc_to_nct(const void* in, int B, int L, int C, int C_ld, int elem_bytes, float* out,
-                              cudaStream_t st) {
+                              cudaStream_t st, long long in_batch_stride) {
   dim3 grid((L + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  if (in_batch_stride <= 0) in_batch_stride = (long long)L * C_ld;
   if (elem_bytes == 2)
-    nlc_to_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, L, C, C_ld, out);
+    nlc_to_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, L, C, C_ld, in_batch_stride, out);
   else
-    nlc_to_nct_kernel<float><<<grid, block, 0, st>>>((const float*)in, L, C, C_ld, out);
+    nlc_to_nct_kernel<float><<<grid, block, 0, st>>>((const float*)in, L, C, C_ld, in_batch_stride, out);
   return cudaGetLastError();
 }
 
@@ -216,15 +218,19 @@ cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const fl
 // ------------------------------------------------------------------------------------------------
 constexpr int kStftFrames = 256;
 
+// Output rows: [front zero rows | F frames | back zero rows] = total_rows rows of C_ld elements of E
+// (channels >= 18 are zero).  The padding rows are what lets the strided source_downs convs read their
+// conv padding (and the K padding of the GEMM view) as plain zeros.
+template <typename E>
 __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restrict__ s, int L,
-                                                           const int* __restrict__ lengths,
-                                                           float* __restrict__ spec) {
+                                                           const int* __restrict__ lengths, E* __restrict__ spec,
+                                                           int C_ld, int front, int total_rows, int round) {
   __shared__ float x_s[kStftFrames * 4 + 12];
   __shared__ float cw[9][16], sw[9][16];
-  __shared__ float out_s[kStftFrames * 18];
-  const int b = blockIdx.y, fb = blockIdx.x * kStftFrames;
-  const int F = L / 4 + 1;
-  const int Lb = lengths ? min(L, lengths[b] * kSPF) : L;     // this utterance's samples
+  __shared__ float out_s[kStftFrames * 24];
+  const int b = blockIdx.y, rb = blockIdx.x * kStftFrames;     // first output row of this block
+  const int fb = rb - front;                                   // its frame index (may be negative)
+  const int Lb = lengths ? min(L, lengths[b] * kSPF) : L;      // this utterance's samples
   const int Fb = Lb / 4 + 1;
   const float* sb = s + (size_t)b * L;
   for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
@@ -236,8 +242,8 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
   }
   for (int i = threadIdx.x; i < kStftFrames * 4 + 12; i += blockDim.x) {
     int idx = fb * 4 - 8 + i;
-    if (idx < 0) idx = -idx;
-    if (idx >= Lb) idx = 2 * (Lb - 1) - idx;
+    if (idx < 0 && idx >= -8) idx = -idx;
+    if (idx >= Lb && idx < Lb + 8) idx = 2 * (Lb - 1) - idx;
     x_s[i] = (idx >= 0 && idx < Lb) ? sb[idx] : 0.f;
   }
   __syncthreads();
@@ -245,7 +251,7 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
   float x[16];
 #pragma unroll
   for (int n = 0; n < 16; ++n) x[n] = x_s[threadIdx.x * 4 + n];
-  const bool live = f < Fb;
+  const bool live = f >= 0 && f < Fb;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     float re = 0.f, im = 0.f;
@@ -254,19 +260,29 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
       re = fmaf(x[n], cw[k][n], re);
       im = fmaf(x[n], sw[k][n], im);
     }
-    out_s[threadIdx.x * 18 + k] = live ? re : 0.f;
-    out_s[threadIdx.x * 18 + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
+    out_s[threadIdx.x * C_ld + k] = live ? re : 0.f;
+    out_s[threadIdx.x * C_ld + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
   }
+  for (int c = 18; c < C_ld; ++c) out_s[threadIdx.x * C_ld + c] = 0.f;
   __syncthreads();
-  const int nf = min(kStftFrames, F - fb);
-  float* ob = spec + ((size_t)b * F + fb) * 18;
-  for (int i = threadIdx.x; i < nf * 18; i += blockDim.x) ob[i] = out_s[i];
+  const int nr = min(kStftFrames, total_rows - rb);
+  E* ob = spec + ((size_t)b * total_rows + rb) * C_ld;
+  for (int i = threadIdx.x; i < nr * C_ld; i += blockDim.x) {
+    float v = out_s[i];
+    if constexpr (sizeof(E) == 4) { if (round) v = round_tf32(v); }
+    ElemIO<E>::store(ob + i, v);
+  }
 }
 
-cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, float* spec_nlc, cudaStream_t st) {
-  const int F = L / 4 + 1;
-  dim3 grid((F + kStftFrames - 1) / kStftFrames, B);
-  stft_kernel<<<grid, kStftFrames, 0, st>>>(s, L, lengths, spec_nlc);
+cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, void* spec_nlc, int elem_bytes, int round,
+                        int C_ld, int front_rows, int total_rows, cudaStream_t st) {
+  if (C_ld < 18 || C_ld > 24 || front_rows < 0 || total_rows < front_rows + L / 4 + 1) return cudaErrorInvalidValue;
+  dim3 grid((total_rows + kStftFrames - 1) / kStftFrames, B);
+  if (elem_bytes == 2)
+    stft_kernel<__nv_bfloat16><<<grid, kStftFrames, 0, st>>>(s, L, lengths, (__nv_bfloat16*)spec_nlc, C_ld, front_rows,
+                                                            total_rows, 0);
+  else
+    stft_kernel<float><<<grid, kStftFrames, 0, st>>>(s, L, lengths, (float*)spec_nlc, C_ld, front_rows, total_rows, round);
   return cudaGetLastError();
 }
 

@@ -58,6 +58,10 @@ struct ConvGeom {
   int M_rows;     // GEMM rows per batch element
   int N_total;    // GEMM columns (weights rows)
   int n_taps, off0, tap_step, in_stride;
+  // A as a strided view (elements): row r of utterance b starts at A + b*a_batch_stride + r*a_row_stride.
+  // 0 = dense [B, L_in, C_in_ld].  Rows may overlap (a_row_stride < C_in_ld): that is how the strided
+  // source_downs convs become plain GEMMs (one GEMM row = k consecutive STFT frames).
+  long long a_row_stride, a_batch_stride;
 };
 
 #ifdef __CUDACC__

@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const Ein* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const Ein* Ab = A + (size_t)b * g.L_in * g.C_in_ld;
+  const long long row_stride = g.a_row_stride ? g.a_row_stride : g.C_in_ld;
+  const Ein* Ab = A + (size_t)b * (g.a_batch_stride ? g.a_batch_stride : (long long)g.L_in * g.C_in_ld);
   for (int tap = 0; tap < g.n_taps; ++tap) {
     const int in_row = (m0 + lrow) * g.in_stride + g.off0 + tap * g.tap_step;
     const bool row_ok = (m0 + lrow) < g.M_rows && in_row >= 0 && in_row < g.L_in;
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const Ein* __restrict__ 
         const int ci = c0 + lk + i;
         float a = 0.f, w = 0.f;
         if (ci < g.C_in) {
-          if (row_ok) a = ElemIO<Ein>::load(Ab + (size_t)in_row * g.C_in_ld + ci);
+          if (row_ok) a = ElemIO<Ein>::load(Ab + (size_t)in_row * row_stride + ci);
           if (n_ok) w = ElemIO<Ew>::load(W + (size_t)(n0 + lrow) * Kw + tap * g.C_in_w + ci);
         }
         As[lk + i][lrow] = a;

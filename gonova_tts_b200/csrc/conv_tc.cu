@@ -66,6 +66,7 @@ const char* make_conv_tc_launch(ConvTcLaunch* out, int elem_bytes, const void* a
   if (g.C_in_ld % kbe) return "conv_tc: channel stride is not a multiple of the 128-byte K block";
   if (g.C_in_w != g.C_in_ld) return "conv_tc: weight K stride must equal the activation channel stride";
   if (g.in_stride != 1) return "conv_tc: strided input rows are not supported on the tensor-core path";
+  if (g.a_row_stride || g.a_batch_stride) return "conv_tc: strided A views need the persistent kernel";
   if (block_n % 16 || block_n < 16 || block_n > 256) return "conv_tc: block_n must be a multiple of 16 in [16,256]";
   if (g.N_total % block_n) return "conv_tc: N_total must be a multiple of block_n";
   if (w_rows_alloc < g.N_total) return "conv_tc: packed weights have fewer rows than N_total";

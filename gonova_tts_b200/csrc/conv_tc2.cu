@@ -179,8 +179,11 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   // ---- tensor maps ----
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   {
+    const long long rs = g.a_row_stride ? g.a_row_stride : g.C_in_ld;
+    const long long bs = g.a_batch_stride ? g.a_batch_stride : (long long)g.L_in * g.C_in_ld;
+    if ((rs * elem_bytes) % 16 || (bs * elem_bytes) % 16) return "conv_tc2: A view strides must be multiples of 16 bytes";
     cuuint64_t dims[3] = {(cuuint64_t)g.C_in_ld, (cuuint64_t)g.L_in, (cuuint64_t)g.B};
-    cuuint64_t strides[2] = {(cuuint64_t)g.C_in_ld * elem_bytes, (cuuint64_t)g.L_in * g.C_in_ld * elem_bytes};
+    cuuint64_t strides[2] = {(cuuint64_t)rs * elem_bytes, (cuuint64_t)bs * elem_bytes};
     cuuint32_t box[3] = {(cuuint32_t)kbe, (cuuint32_t)p.a_box_rows, 1u};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&out->maps.A, dt, 3, const_cast<void*>(act), dims, strides, box, es,

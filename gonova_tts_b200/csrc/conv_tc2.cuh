@@ -329,8 +329,14 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
           tmem_ld32(trow + (uint32_t)(cc * kEpiCols), v);
           const int c0 = cbase + cc * kEpiCols;          // channel index of v[0]
           // ---- bias, residual, running sum ----   (tables are padded to 32 columns: conv_post has C_out = 18)
+          {
+            const uint32_t bt = smem_u32(tab + c0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += tab[c0 + i];
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = lds128(bt + 16 * j);
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
           // ReflectionPad1d((1,0)): the conv row p0 == dup_row is ALSO output row 0, where it meets the
           // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk.
           if (p.ep.dup_row >= 0 && p0 == p.ep.dup_row && m < p.M_rows) {
@@ -364,8 +370,10 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
                 v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
               }
             }
+            if (p.ep.raw_scale != 1.0f) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
+              for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
+            }
             if (p.ep.raw_accum) {
               const uint32_t in1 = in0 + (p.ep.res ? BLOCK_M * kEpiCols * 4 : 0);
 #pragma unroll
@@ -377,7 +385,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(b_in_empty + 8u * rin.slot);
             rin.advance(2);
-          } else {
+          } else if (p.ep.raw_scale != 1.0f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
           }
@@ -399,29 +407,43 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
             o += BLOCK_M * kEpiCols * 4;
           }
           for (int a = 0; a < p.n_act; ++a) {
+            // The activation kind is uniform for the launch: one tight loop per kind (a per-element
+            // switch makes the compiler evaluate every variant and select).  Every activation maps
+            // 0 -> 0, so rows that are not live (v == 0) need no extra select.
             const int kind = p.ep.act_kind[a];
-            const float slope = p.ep.act_slope[a];
-            const float* al = tab + (1 + 2 * a) * p.c_tab;
-            const float* iv = tab + (2 + 2 * a) * p.c_tab;
+            const uint32_t al = smem_u32(tab + (1 + 2 * a) * p.c_tab + c0);
+            const uint32_t iv = smem_u32(tab + (2 + 2 * a) * p.c_tab + c0);
             float y[32];
+            if (kind == ACT_SNAKE_FAST) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = v[i];
-              float r;
-              if (kind == ACT_SNAKE_FAST) {
-                const float s = __sinf(x * al[c0 + i]);
-                r = fmaf(iv[c0 + i], s * s, x);
-              } else if (kind == ACT_SNAKE) {
-                const float s = sinf(x * al[c0 + i]);
-                r = x + iv[c0 + i] * (s * s);
-              } else if (kind == ACT_LRELU) {
-                r = x > 0.f ? x : x * slope;
-              } else if (kind == ACT_ELU) {
-                r = x > 0.f ? x : expm1f(x);
-              } else {
-                r = x;
+              for (int j = 0; j < 8; ++j) {
+                const float4 a4 = lds128(al + 16 * j), i4 = lds128(iv + 16 * j);
+                float s;
+                s = __sinf(v[4 * j] * a4.x);     y[4 * j]     = fmaf(i4.x, s * s, v[4 * j]);
+                s = __sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = fmaf(i4.y, s * s, v[4 * j + 1]);
+                s = __sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = fmaf(i4.z, s * s, v[4 * j + 2]);
+                s = __sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = fmaf(i4.w, s * s, v[4 * j + 3]);
               }
-              y[i] = live ? r : 0.f;
+            } else if (kind == ACT_LRELU) {
+              const float slope = p.ep.act_slope[a];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+            } else if (kind == ACT_SNAKE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 a4 = lds128(al + 16 * j), i4 = lds128(iv + 16 * j);
+                float s;
+                s = sinf(v[4 * j] * a4.x);     y[4 * j]     = v[4 * j] + i4.x * (s * s);
+                s = sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = v[4 * j + 1] + i4.y * (s * s);
+                s = sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = v[4 * j + 2] + i4.z * (s * s);
+                s = sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = v[4 * j + 3] + i4.w * (s * s);
+              }
+            } else if (kind == ACT_ELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = v[i];
             }
             if constexpr (sizeof(E) == 2) {
 #pragma unroll
