@@ -157,13 +157,13 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   bool grew = true;
   while (grew) {
     grew = false;
+    if (nob < 2 && total(sa, sw, nob + 1) <= kMaxDynSmem2) { ++nob; grew = true; }
     if (sa < 2 && sa < max_sa && total(sa + 1, sw, nob) <= kMaxDynSmem2) { ++sa; grew = true; }
     if (sw < 3 && sw < max_sw && total(sa, sw + 1, nob) <= kMaxDynSmem2) { ++sw; grew = true; }
-    if (nob < 2 && total(sa, sw, nob + 1) <= kMaxDynSmem2) { ++nob; grew = true; }
     if (!grew && sw < max_sw && total(sa, sw + 1, nob) <= kMaxDynSmem2) { ++sw; grew = true; }
     if (!grew && sa < max_sa && total(sa + 1, sw, nob) <= kMaxDynSmem2) { ++sa; grew = true; }
   }
-  p.sa = sa; p.sw = sw; p.n_out_bufs = nob;
+  p.sa = sa; p.sw = sw; p.n_epi_wg = nob;
   uint32_t off = 0;
   p.off_a = off; off += (uint32_t)sa * p.slab_bytes;
   p.off_w = off; off += (uint32_t)sw * p.w_bytes;
@@ -236,9 +236,9 @@ cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStre
   ConvTc2Params p = L.p;
   p.ep.lengths = lengths;
   if (L.elem_bytes == 2)
-    conv_tc2_kernel<__nv_bfloat16><<<L.grid, 256, L.smem_bytes, st>>>(L.d_maps, p);
+    conv_tc2_kernel<__nv_bfloat16><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
   else
-    conv_tc2_kernel<float><<<L.grid, 256, L.smem_bytes, st>>>(L.d_maps, p);
+    conv_tc2_kernel<float><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
   return cudaGetLastError();
 }
 

@@ -17,8 +17,9 @@
 //     also clip rows past the tensor end.  The polyphase scatter of the ConvTranspose is a tensor map
 //     per phase (row stride = up * C), so it is a plain box store as well.
 //
-// Warp roles (256 threads): 0 = TMA producer (A slabs + W tiles), 1 = MMA issuer, 2 = TMEM
-// allocator, 3 = epilogue-input TMA loader, 4..7 = epilogue (one TMEM lane quarter each).
+// Warp roles (384 threads): 0 = TMA producer (A slabs + W tiles), 1 = MMA issuer, 2 = TMEM
+// allocator, 3 = epilogue-input TMA loader, 4..7 and 8..11 = two epilogue warpgroups (one TMEM lane
+// quarter per warp) that take alternate 32-column chunks of a tile.
 #pragma once
 #include <cuda.h>
 
@@ -47,7 +48,7 @@ struct ConvTc2Params {
   int tap_row[kMaxSlab];
   int a_box_rows, a_n_boxes;       // every slab is a_n_boxes TMA boxes of a_box_rows rows
   int a_base_offset_mode;          // 1: descriptor base_offset = (start address >> 7) & 7
-  int sa, sw, n_out_bufs, acc_bufs;
+  int sa, sw, n_epi_wg, acc_bufs;   // n_epi_wg: epilogue warpgroups in use (1 or 2) == output staging buffers
   int slab_bytes, w_bytes;
   int tmem_cols;
   uint32_t idesc;
@@ -81,7 +82,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -130,7 +131,7 @@ struct Ring {
 }  // namespace tc2
 
 template <typename E>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ ConvTc2Params p) {
   using namespace tc2;
   const ConvTc2Maps& maps = *maps_g;          // tensor maps live in global memory (6.4 KB: too big for the
@@ -162,7 +163,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_acc_full + 8u * s, 1);
-      mbar_init(b_acc_empty + 8u * s, 4);
+      mbar_init(b_acc_empty + 8u * s, 4 * p.n_epi_wg);
       mbar_init(b_in_full + 8u * s, 1);
       mbar_init(b_in_empty + 8u * s, 4);
     }
@@ -270,7 +271,11 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   } else if (warp == 3) {
     if (lane == 0 && p.n_in > 0) {
       // ===== epilogue-input loader: residual / running-sum tiles -> shared memory =====
-      Ring rin;
+      // Ring of two slots.  With two epilogue warpgroups item i of a tile goes to slot i % 2 (the
+      // warpgroup that will consume it); with one, slots simply alternate.  Phases are per slot.
+      uint32_t slot_phase[2] = {0u, 0u};
+      int seq = 0;
+      const int n_items = p.mh * n_epi_chunks;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int q = t;
         const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
@@ -279,28 +284,33 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int n0 = n_tile * p.block_n;
         const int ph = p.transposed ? n_tile : 0;
         const int cbase = p.transposed ? 0 : n0;
-        for (int h = 0; h < p.mh; ++h) {
+        for (int item = 0; item < n_items; ++item, ++seq) {
+          const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
           const int mrow = m_tile * rows_per_tile + h * BLOCK_M;      // TMA row coordinate (GEMM row - row_adj)
-          for (int cc = 0; cc < n_epi_chunks; ++cc) {
-            mbar_wait(b_in_empty + 8u * rin.slot, rin.phase ^ 1u);
-            mbar_expect_tx(b_in_full + 8u * rin.slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
-            for (int i = 0; i < p.n_in; ++i)
-              tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * rin.slot,
-                          sIn + (rin.slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
-            rin.advance(2);
-          }
+          const int slot = p.n_epi_wg == 2 ? (item & 1) : (seq & 1);
+          mbar_wait(b_in_empty + 8u * slot, slot_phase[slot] ^ 1u, 3);
+          mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
+          for (int i = 0; i < p.n_in; ++i)
+            tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * slot,
+                        sIn + (slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
+          slot_phase[slot] ^= 1u;
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (warp - 4) / 4 < p.n_epi_wg) {
     // ===== epilogue: TMEM -> registers -> bias / residual / activations -> shared -> TMA store =====
+    // Up to two warpgroups of 4 warps; the (half, 32-column chunk) items of a tile alternate between
+    // them.  Each warpgroup owns one input slot (the loader's ring of two), one output staging buffer,
+    // one named barrier and its own bulk-store groups, so the two never synchronise with each other.
+    const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int erow = q * 32 + lane;                     // row inside a 128-row half == TMEM lane
-    const int etid = threadIdx.x - 128;
+    const bool elected = ((threadIdx.x - 128) & 127) == 0;
     const int C = p.ep.C_out;
     const int out_stride = (p.has_raw ? BLOCK_M * kEpiCols * 4 : 0) + p.n_act * p.act_bytes;
-    Ring racc, rin;
-    int ob = 0;
+    const uint32_t obase = sOut + wg * out_stride;
+    Ring racc, rin;                                     // rin: this warpgroup's view of the input ring
+    const int n_items = p.mh * n_epi_chunks;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       int qq = t;
       const int n_tile = qq % p.n_tiles_n; qq /= p.n_tiles_n;
@@ -314,9 +324,10 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int lv = p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
         valid_rows = lv < valid_rows ? lv : valid_rows;
       }
-      mbar_wait(b_acc_full + 8u * racc.slot, racc.phase);
+      mbar_wait(b_acc_full + 8u * racc.slot, racc.phase, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int h = 0; h < p.mh; ++h) {
+      for (int item = (p.n_epi_wg == 2 ? wg : 0); item < n_items; item += p.n_epi_wg) {
+        const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
         const int m = m0 + h * BLOCK_M + erow;
         const int p0 = m * p.ep.up + (p.transposed ? n_tile : 0) - p.ep.pad_out;
         const int row = p0 + p.ep.shift;
@@ -324,160 +335,157 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int mrow = m_tile * rows_per_tile + h * BLOCK_M;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)((racc.slot * p.mh + h) * p.block_n);
-        for (int cc = 0; cc < n_epi_chunks; ++cc) {
-          float v[32];
-          tmem_ld32(trow + (uint32_t)(cc * kEpiCols), v);
-          const int c0 = cbase + cc * kEpiCols;          // channel index of v[0]
-          // ---- bias, residual, running sum ----   (tables are padded to 32 columns: conv_post has C_out = 18)
-          {
-            const uint32_t bt = smem_u32(tab + c0);
+        float v[32];
+        tmem_ld32(trow + (uint32_t)(cc * kEpiCols), v);
+        const int c0 = cbase + cc * kEpiCols;          // channel index of v[0]
+        // ---- bias ----   (tables are padded to 32 columns: conv_post has C_out = 18)
+        {
+          const float4* bt = reinterpret_cast<const float4*>(tab + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bt[j];
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+        // ReflectionPad1d((1,0)): the conv row p0 == dup_row is ALSO output row 0, where it meets the
+        // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk.
+        if (p.ep.dup_row >= 0 && p0 == p.ep.dup_row && m < p.M_rows) {
+          const size_t g0 = (size_t)b * p.ep.L_out * p.ep.C_pitch + c0;
+          const bool live0 = 0 < valid_rows;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c0 + i >= C) continue;
+            float u = v[i];
+            if (p.ep.res) u += p.ep.res[g0 + i];
+            u *= p.ep.raw_scale;
+            if (p.ep.raw_accum) u += p.ep.raw[g0 + i];
+            if (!live0) u = 0.f;
+            if (p.has_raw) p.ep.raw[g0 + i] = u;
+            for (int a = 0; a < p.n_act; ++a) {
+              const float y0 = live0 ? act_apply(p.ep.act_kind[a], u, tab[(1 + 2 * a) * p.c_tab + c0 + i],
+                                                 p.ep.act_slope[a]) : 0.f;
+              E* dst = reinterpret_cast<E*>(p.ep.act_out[a]) + g0 + i;
+              if constexpr (sizeof(E) == 4) ElemIO<E>::store(dst, p.ep.round_tf32 ? round_tf32(y0) : y0);
+              else ElemIO<E>::store(dst, y0);
+            }
+          }
+        }
+        // ---- residual, scale, running sum ----
+        if (p.n_in > 0) {
+          // two warpgroups: this one owns slot `wg` of the loader's ring of two; one: it uses both in turn
+          const int in_slot = p.n_epi_wg == 2 ? wg : rin.slot;
+          const uint8_t* in_tile = smem_gen + p.off_in + (size_t)in_slot * p.n_in * (BLOCK_M * kEpiCols * 4);
+          mbar_wait(b_in_full + 8u * in_slot, rin.phase, 5);
+          if (p.ep.res) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b4 = lds128(bt + 16 * j);
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              const float4 r = *reinterpret_cast<const float4*>(in_tile + erow * 128 + ((j ^ (erow & 7)) << 4));
+              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
             }
           }
-          // ReflectionPad1d((1,0)): the conv row p0 == dup_row is ALSO output row 0, where it meets the
-          // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk.
-          if (p.ep.dup_row >= 0 && p0 == p.ep.dup_row && m < p.M_rows) {
-            const size_t g0 = (size_t)b * p.ep.L_out * p.ep.C_pitch + c0;
-            const bool live0 = 0 < valid_rows;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (c0 + i >= C) continue;
-              float u = v[i];
-              if (p.ep.res) u += p.ep.res[g0 + i];
-              u *= p.ep.raw_scale;
-              if (p.ep.raw_accum) u += p.ep.raw[g0 + i];
-              if (!live0) u = 0.f;
-              if (p.has_raw) p.ep.raw[g0 + i] = u;
-              for (int a = 0; a < p.n_act; ++a) {
-                const float y0 = live0 ? act_apply(p.ep.act_kind[a], u, tab[(1 + 2 * a) * p.c_tab + c0 + i],
-                                                   p.ep.act_slope[a]) : 0.f;
-                E* dst = reinterpret_cast<E*>(p.ep.act_out[a]) + g0 + i;
-                if constexpr (sizeof(E) == 4) ElemIO<E>::store(dst, p.ep.round_tf32 ? round_tf32(y0) : y0);
-                else ElemIO<E>::store(dst, y0);
-              }
-            }
-          }
-          if (p.n_in > 0) {
-            mbar_wait(b_in_full + 8u * rin.slot, rin.phase);
-            const uint32_t in0 = sIn + (rin.slot * p.n_in) * (BLOCK_M * kEpiCols * 4);
-            if (p.ep.res) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = lds128(tile_addr_f32(in0, erow, j));
-                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-              }
-            }
-            if (p.ep.raw_scale != 1.0f) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
-            }
-            if (p.ep.raw_accum) {
-              const uint32_t in1 = in0 + (p.ep.res ? BLOCK_M * kEpiCols * 4 : 0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 r = lds128(tile_addr_f32(in1, erow, j));
-                v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(b_in_empty + 8u * rin.slot);
-            rin.advance(2);
-          } else if (p.ep.raw_scale != 1.0f) {
+          if (p.ep.raw_scale != 1.0f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
           }
-          if (!live) {
+          if (p.ep.raw_accum) {
+            const uint8_t* in1 = in_tile + (p.ep.res ? BLOCK_M * kEpiCols * 4 : 0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = *reinterpret_cast<const float4*>(in1 + erow * 128 + ((j ^ (erow & 7)) << 4));
+              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
           }
-          // ---- stage the outputs ----
-          const uint32_t obase = sOut + ob * out_stride;
-          if (etid == 0) {
-            if (p.n_out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(b_in_empty + 8u * in_slot);
+          if (p.n_epi_wg == 2) rin.phase ^= 1u; else rin.advance(2);
+        } else if (p.ep.raw_scale != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
+        }
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        // ---- stage the outputs (the previous store from this buffer must have drained) ----
+        if (elected) bulk_wait_read<0>();
+        epi_bar_sync(wg);
+        uint32_t o = obase;
+        if (p.has_raw) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(tile_addr_f32(o, erow, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          o += BLOCK_M * kEpiCols * 4;
+        }
+        for (int a = 0; a < p.n_act; ++a) {
+          // The activation kind is uniform for the launch: one tight loop per kind (a per-element
+          // switch makes the compiler evaluate every variant and select).  Every activation maps
+          // 0 -> 0, so rows that are not live (v == 0) need no extra select.
+          const int kind = p.ep.act_kind[a];
+          const float4* al = reinterpret_cast<const float4*>(tab + (1 + 2 * a) * p.c_tab + c0);
+          const float4* iv = reinterpret_cast<const float4*>(tab + (2 + 2 * a) * p.c_tab + c0);
+          float y[32];
+          if (kind == ACT_SNAKE_FAST) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a4 = al[j], i4 = iv[j];
+              float s;
+              s = __sinf(v[4 * j] * a4.x);     y[4 * j]     = fmaf(i4.x, s * s, v[4 * j]);
+              s = __sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = fmaf(i4.y, s * s, v[4 * j + 1]);
+              s = __sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = fmaf(i4.z, s * s, v[4 * j + 2]);
+              s = __sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = fmaf(i4.w, s * s, v[4 * j + 3]);
+            }
+          } else if (kind == ACT_LRELU) {
+            const float slope = p.ep.act_slope[a];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+          } else if (kind == ACT_SNAKE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a4 = al[j], i4 = iv[j];
+              float s;
+              s = sinf(v[4 * j] * a4.x);     y[4 * j]     = v[4 * j] + i4.x * (s * s);
+              s = sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = v[4 * j + 1] + i4.y * (s * s);
+              s = sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = v[4 * j + 2] + i4.z * (s * s);
+              s = sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = v[4 * j + 3] + i4.w * (s * s);
+            }
+          } else if (kind == ACT_ELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = v[i];
           }
-          epi_bar_sync();
-          uint32_t o = obase;
-          if (p.has_raw) {
+          if constexpr (sizeof(E) == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(tile_addr_b16(o, erow, j), ElemIO<E>::pack2(y[8 * j], y[8 * j + 1]),
+                      ElemIO<E>::pack2(y[8 * j + 2], y[8 * j + 3]), ElemIO<E>::pack2(y[8 * j + 4], y[8 * j + 5]),
+                      ElemIO<E>::pack2(y[8 * j + 6], y[8 * j + 7]));
+          } else {
+            if (p.ep.round_tf32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = round_tf32(y[i]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              sts128(tile_addr_f32(o, erow, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            o += BLOCK_M * kEpiCols * 4;
+              sts128(tile_addr_f32(o, erow, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          }
+          o += p.act_bytes;
+        }
+        fence_async_smem();
+        epi_bar_sync(wg);
+        if (elected) {
+          uint32_t src = obase;
+          const int cs = cbase + cc * kEpiCols;
+          if (p.has_raw) {
+            tma_store_3d(&maps.epi[ph][EPI_RAW], src, cs, mrow, b);
+            src += BLOCK_M * kEpiCols * 4;
           }
           for (int a = 0; a < p.n_act; ++a) {
-            // The activation kind is uniform for the launch: one tight loop per kind (a per-element
-            // switch makes the compiler evaluate every variant and select).  Every activation maps
-            // 0 -> 0, so rows that are not live (v == 0) need no extra select.
-            const int kind = p.ep.act_kind[a];
-            const uint32_t al = smem_u32(tab + (1 + 2 * a) * p.c_tab + c0);
-            const uint32_t iv = smem_u32(tab + (2 + 2 * a) * p.c_tab + c0);
-            float y[32];
-            if (kind == ACT_SNAKE_FAST) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 a4 = lds128(al + 16 * j), i4 = lds128(iv + 16 * j);
-                float s;
-                s = __sinf(v[4 * j] * a4.x);     y[4 * j]     = fmaf(i4.x, s * s, v[4 * j]);
-                s = __sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = fmaf(i4.y, s * s, v[4 * j + 1]);
-                s = __sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = fmaf(i4.z, s * s, v[4 * j + 2]);
-                s = __sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = fmaf(i4.w, s * s, v[4 * j + 3]);
-              }
-            } else if (kind == ACT_LRELU) {
-              const float slope = p.ep.act_slope[a];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
-            } else if (kind == ACT_SNAKE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 a4 = lds128(al + 16 * j), i4 = lds128(iv + 16 * j);
-                float s;
-                s = sinf(v[4 * j] * a4.x);     y[4 * j]     = v[4 * j] + i4.x * (s * s);
-                s = sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = v[4 * j + 1] + i4.y * (s * s);
-                s = sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = v[4 * j + 2] + i4.z * (s * s);
-                s = sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = v[4 * j + 3] + i4.w * (s * s);
-              }
-            } else if (kind == ACT_ELU) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = v[i];
-            }
-            if constexpr (sizeof(E) == 2) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128u(tile_addr_b16(o, erow, j), ElemIO<E>::pack2(y[8 * j], y[8 * j + 1]),
-                        ElemIO<E>::pack2(y[8 * j + 2], y[8 * j + 3]), ElemIO<E>::pack2(y[8 * j + 4], y[8 * j + 5]),
-                        ElemIO<E>::pack2(y[8 * j + 6], y[8 * j + 7]));
-            } else {
-              if (p.ep.round_tf32) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = round_tf32(y[i]);
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                sts128(tile_addr_f32(o, erow, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            }
-            o += p.act_bytes;
+            tma_store_3d(&maps.epi[ph][EPI_ACT0 + a], src, cs, mrow, b);
+            src += p.act_bytes;
           }
-          fence_async_smem();
-          epi_bar_sync();
-          if (etid == 0) {
-            uint32_t src = obase;
-            const int cs = cbase + cc * kEpiCols;
-            if (p.has_raw) {
-              tma_store_3d(&maps.epi[ph][EPI_RAW], src, cs, mrow, b);
-              src += BLOCK_M * kEpiCols * 4;
-            }
-            for (int a = 0; a < p.n_act; ++a) {
-              tma_store_3d(&maps.epi[ph][EPI_ACT0 + a], src, cs, mrow, b);
-              src += p.act_bytes;
-            }
-            bulk_commit();
-          }
-          if (++ob == p.n_out_bufs) ob = 0;
+          bulk_commit();
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA issuer
@@ -486,7 +494,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       if (lane == 0) mbar_arrive(b_acc_empty + 8u * racc.slot);
       racc.advance(p.acc_bufs);
     }
-    if (etid == 0) bulk_wait_read<0>();
+    if (elected) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
