@@ -174,8 +174,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "64 concurrent 10 s utterances per GPU (BASELINE configs[2]); the CPU arm decodes a "
-                               "bounded sample of it per step", "frames_per_utterance": T, "sample_rate": SR},
+        "config": {"workload": f"64 concurrent {T / 50:.0f} s utterances per GPU through the decoder "
+                               "(BASELINE configs[2]; N=8 is configs[3]'s 512 streams): f0 -> source -> HiFT decode -> int16",
+                   "utterances_per_gpu": 64, "frames_per_utterance": T, "sample_rate": SR,
+                   "cpu_arm": "decodes a bounded sample of that workload per step (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference engine (chatterbox) is not installable here; this is oracle/hift_ref.py, the CPU "
@@ -290,7 +292,7 @@ def main():
             peak_tf = peak_tf / 2 if args.dtype == "tf32" else 75.0    # tf32 = half the bf16 rate; fp32 FMA nominal
         achieved_tf = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
         roofline = {
-            "kernel": f"conv_tc_kernel<{args.dtype}> (tcgen05 implicit-GEMM conv; {len(tc)} launches per step)",
+            "kernel": f"conv_tc2_kernel<{args.dtype}> (persistent tcgen05 implicit-GEMM conv; {len(tc)} launches per step)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
             "peak_source": peak_src + (" bf16 sustained" if args.dtype == "bf16" else " derived for " + args.dtype),

@@ -994,7 +994,7 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
                                               dtype == GNV_DTYPE_TF32 ? 1 : 0, st));
   EpiSpec es;
   es.res = res;
-  es.raw = raw;
+  es.raw = (act != GNV_ACT_NONE && (flags & GNV_FLAG_HOOK_NO_RAW)) ? nullptr : raw;
   es.c_pitch = Cp;
   if (act != GNV_ACT_NONE) es.acts.push_back({act, alpha_d, slope, actb});
   ConvOp op;

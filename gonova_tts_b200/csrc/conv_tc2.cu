@@ -146,7 +146,7 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
 
   // ---- shared-memory budget: grow the rings while they fit ----
   const int k_iters = p.n_chunks * g.n_taps;
-  int sa = 1, sw = 2, nob = 1;
+  int sa = 1, sw = 2, nob = 1;          // nob = staging buffers in total = warpgroups * buffers per warpgroup
   auto total = [&](int sa_, int sw_, int nob_) {
     return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
            bar_bytes + 1024 /*alignment slack*/;
@@ -160,10 +160,11 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
     if (nob < 2 && total(sa, sw, nob + 1) <= kMaxDynSmem2) { ++nob; grew = true; }
     if (sa < 2 && sa < max_sa && total(sa + 1, sw, nob) <= kMaxDynSmem2) { ++sa; grew = true; }
     if (sw < 3 && sw < max_sw && total(sa, sw + 1, nob) <= kMaxDynSmem2) { ++sw; grew = true; }
+    if (nob == 2 && total(sa, sw, 4) <= kMaxDynSmem2) { nob = 4; grew = true; }
     if (!grew && sw < max_sw && total(sa, sw + 1, nob) <= kMaxDynSmem2) { ++sw; grew = true; }
     if (!grew && sa < max_sa && total(sa + 1, sw, nob) <= kMaxDynSmem2) { ++sa; grew = true; }
   }
-  p.sa = sa; p.sw = sw; p.n_epi_wg = nob;
+  p.sa = sa; p.sw = sw; p.n_epi_wg = nob >= 2 ? 2 : 1; p.out_bufs = nob == 4 ? 2 : 1;
   uint32_t off = 0;
   p.off_a = off; off += (uint32_t)sa * p.slab_bytes;
   p.off_w = off; off += (uint32_t)sw * p.w_bytes;

@@ -48,7 +48,8 @@ struct ConvTc2Params {
   int tap_row[kMaxSlab];
   int a_box_rows, a_n_boxes;       // every slab is a_n_boxes TMA boxes of a_box_rows rows
   int a_base_offset_mode;          // 1: descriptor base_offset = (start address >> 7) & 7
-  int sa, sw, n_epi_wg, acc_bufs;   // n_epi_wg: epilogue warpgroups in use (1 or 2) == output staging buffers
+  int sa, sw, n_epi_wg, acc_bufs;   // n_epi_wg: epilogue warpgroups in use (1 or 2)
+  int out_bufs;                     // output staging buffers per warpgroup (1 or 2)
   int slab_bytes, w_bytes;
   int tmem_cols;
   uint32_t idesc;
@@ -128,6 +129,19 @@ struct Ring {
   }
 };
 
+}  // namespace tc2
+
+struct ConvTc2Params;
+namespace tc2 {
+// Rare, long code paths stay out of line so that the epilogue loop fits the instruction cache.
+static __device__ __noinline__ float snake_precise(float x, float alpha, float inv) {
+  const float s = sinf(x * alpha);
+  return x + inv * (s * s);
+}
+static __device__ __noinline__ float elu_precise(float x) { return x > 0.f ? x : expm1f(x); }
+template <typename E>
+__device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab, const float (&v)[32], int b, int c0,
+                                       bool live0);
 }  // namespace tc2
 
 template <typename E>
@@ -306,9 +320,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     const int q = warp & 3;
     const int erow = q * 32 + lane;                     // row inside a 128-row half == TMEM lane
     const bool elected = ((threadIdx.x - 128) & 127) == 0;
-    const int C = p.ep.C_out;
     const int out_stride = (p.has_raw ? BLOCK_M * kEpiCols * 4 : 0) + p.n_act * p.act_bytes;
-    const uint32_t obase = sOut + wg * out_stride;
+    const uint32_t obase_wg = sOut + wg * p.out_bufs * out_stride;
+    int ob = 0;
     Ring racc, rin;                                     // rin: this warpgroup's view of the input ring
     const int n_items = p.mh * n_epi_chunks;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -348,27 +362,13 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
           }
         }
         // ReflectionPad1d((1,0)): the conv row p0 == dup_row is ALSO output row 0, where it meets the
-        // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk.
+        // residual of row 0 (x = pad(ups(x)); x = x + si).  One thread per utterance and channel chunk;
+        // out of line so that its math is never speculated into the hot path.
         if (p.ep.dup_row >= 0 && p0 == p.ep.dup_row && m < p.M_rows) {
-          const size_t g0 = (size_t)b * p.ep.L_out * p.ep.C_pitch + c0;
-          const bool live0 = 0 < valid_rows;
+          float tmp[32];                                   // a copy: v itself must stay in registers
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c0 + i >= C) continue;
-            float u = v[i];
-            if (p.ep.res) u += p.ep.res[g0 + i];
-            u *= p.ep.raw_scale;
-            if (p.ep.raw_accum) u += p.ep.raw[g0 + i];
-            if (!live0) u = 0.f;
-            if (p.has_raw) p.ep.raw[g0 + i] = u;
-            for (int a = 0; a < p.n_act; ++a) {
-              const float y0 = live0 ? act_apply(p.ep.act_kind[a], u, tab[(1 + 2 * a) * p.c_tab + c0 + i],
-                                                 p.ep.act_slope[a]) : 0.f;
-              E* dst = reinterpret_cast<E*>(p.ep.act_out[a]) + g0 + i;
-              if constexpr (sizeof(E) == 4) ElemIO<E>::store(dst, p.ep.round_tf32 ? round_tf32(y0) : y0);
-              else ElemIO<E>::store(dst, y0);
-            }
-          }
+          for (int i = 0; i < 32; ++i) tmp[i] = v[i];
+          tc2::emit_row0<E>(p, tab, tmp, b, c0, 0 < valid_rows);
         }
         // ---- residual, scale, running sum ----
         if (p.n_in > 0) {
@@ -406,8 +406,11 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        // ---- stage the outputs (the previous store from this buffer must have drained) ----
-        if (elected) bulk_wait_read<0>();
+        // ---- stage the outputs (the store that last used this staging buffer must have drained) ----
+        const uint32_t obase = obase_wg + ob * out_stride;
+        if (elected) {
+          if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
         epi_bar_sync(wg);
         uint32_t o = obase;
         if (p.has_raw) {
@@ -442,15 +445,14 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 a4 = al[j], i4 = iv[j];
-              float s;
-              s = sinf(v[4 * j] * a4.x);     y[4 * j]     = v[4 * j] + i4.x * (s * s);
-              s = sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = v[4 * j + 1] + i4.y * (s * s);
-              s = sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = v[4 * j + 2] + i4.z * (s * s);
-              s = sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = v[4 * j + 3] + i4.w * (s * s);
+              y[4 * j]     = snake_precise(v[4 * j], a4.x, i4.x);
+              y[4 * j + 1] = snake_precise(v[4 * j + 1], a4.y, i4.y);
+              y[4 * j + 2] = snake_precise(v[4 * j + 2], a4.z, i4.z);
+              y[4 * j + 3] = snake_precise(v[4 * j + 3], a4.w, i4.w);
             }
           } else if (kind == ACT_ELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : expm1f(v[i]);
+            for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] = v[i];
@@ -487,6 +489,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
           }
           bulk_commit();
         }
+        if (++ob == p.out_bufs) ob = 0;
       }
       // accumulator drained: hand the TMEM buffer back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -503,6 +506,29 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
                  : "memory");
   }
 }
+
+namespace tc2 {
+template <typename E>
+__device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab, const float (&v)[32], int b, int c0,
+                                       bool live0) {
+  const int C = p.ep.C_out;
+  const size_t g0 = (size_t)b * p.ep.L_out * p.ep.C_pitch + c0;
+  for (int i = 0; i < 32 && c0 + i < C; ++i) {
+    float u = v[i];
+    if (p.ep.res) u += p.ep.res[g0 + i];
+    u *= p.ep.raw_scale;
+    if (p.ep.raw_accum) u += p.ep.raw[g0 + i];
+    if (!live0) u = 0.f;
+    if (p.has_raw) p.ep.raw[g0 + i] = u;
+    for (int a = 0; a < p.n_act; ++a) {
+      const float y0 = live0 ? act_apply(p.ep.act_kind[a], u, tab[(1 + 2 * a) * p.c_tab + c0 + i], p.ep.act_slope[a]) : 0.f;
+      E* dst = reinterpret_cast<E*>(p.ep.act_out[a]) + g0 + i;
+      if constexpr (sizeof(E) == 4) ElemIO<E>::store(dst, p.ep.round_tf32 ? round_tf32(y0) : y0);
+      else ElemIO<E>::store(dst, y0);
+    }
+  }
+}
+}  // namespace tc2
 
 #endif  // __CUDACC__
 

@@ -38,6 +38,7 @@ extern "C" {
 /* gnv_create flags */
 #define GNV_FLAG_SIMT_CONV   1u /* run the conv layers on the CUDA-core kernel in the chosen dtype */
 #define GNV_FLAG_PRECISE_ACT 2u /* Snake with libdevice sinf instead of MUFU.SIN (always on for FP32) */
+#define GNV_FLAG_HOOK_NO_RAW 8u /* gnv_conv1d only: do not write the fp32 (pre-activation) output tensor */
 #define GNV_FLAG_TC_V1       4u /* use the simple one-tile-per-CTA tcgen05 kernel instead of the persistent one */
 
 /* activation kinds accepted by gnv_conv1d (unit-test hook) */
