@@ -17,7 +17,7 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libgonova_hift.so"
 INCLUDE = PKG.parent / "include"
 
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "aux_kernels.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "aux_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v",

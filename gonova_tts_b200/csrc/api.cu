@@ -32,6 +32,7 @@
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_pair.cuh"
 #include "kernels.h"
 
 using namespace gnv;
@@ -94,9 +95,10 @@ enum SimtVariant { SV_FFF = 0, SV_BBB = 1, SV_FFB = 2 };
 
 struct ConvOp {
   bool tc = false;
-  int tcv = 1;           // 1: conv_tc_kernel (one tile per CTA), 2: conv_tc2_kernel (persistent)
+  int tcv = 1;           // 1: conv_tc_kernel (one tile per CTA), 2: conv_tc2_kernel (persistent), 3: conv_pair_kernel
   ConvTcLaunch tcl;
   ConvTc2Launch tc2l;
+  ConvPairLaunch pairl;
   ConvGeom g;
   EpiParams ep;
   const void* A = nullptr;
@@ -155,20 +157,31 @@ struct Plan {
   ~Plan() { if (d_maps) cudaFree(d_maps); }
 };
 
-// Uploads the tensor maps of every conv_tc2 op to one device buffer and points the ops at it.
+// Uploads the tensor maps of every persistent-kernel op to one device buffer and points the ops at it.
 std::string upload_maps(std::vector<ConvOp*>& ops, void** d_out) {
-  std::vector<ConvOp*> v2;
-  for (ConvOp* op : ops) if (op->tc && op->tcv == 2) v2.push_back(op);
   *d_out = nullptr;
-  if (v2.empty()) return "";
-  std::vector<ConvTc2Maps> host(v2.size());
-  for (size_t i = 0; i < v2.size(); ++i) host[i] = v2[i]->tc2l.maps;
+  size_t bytes = 0;
+  for (ConvOp* op : ops) {
+    if (op->tc && op->tcv == 2) bytes += sizeof(ConvTc2Maps);
+    if (op->tc && op->tcv == 3) bytes += sizeof(ConvPairMaps);
+  }
+  if (!bytes) return "";
+  std::vector<char> host(bytes);
+  size_t off = 0;
+  for (ConvOp* op : ops) {
+    if (op->tc && op->tcv == 2) { memcpy(host.data() + off, &op->tc2l.maps, sizeof(ConvTc2Maps)); off += sizeof(ConvTc2Maps); }
+    if (op->tc && op->tcv == 3) { memcpy(host.data() + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
+  }
   void* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, host.size() * sizeof(ConvTc2Maps));
+  cudaError_t e = cudaMalloc(&d, bytes);
   if (e != cudaSuccess) return std::string("cudaMalloc(tensor maps): ") + cudaGetErrorString(e);
-  e = cudaMemcpy(d, host.data(), host.size() * sizeof(ConvTc2Maps), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(d); return std::string("cudaMemcpy(tensor maps): ") + cudaGetErrorString(e); }
-  for (size_t i = 0; i < v2.size(); ++i) v2[i]->tc2l.d_maps = static_cast<const ConvTc2Maps*>(d) + i;
+  off = 0;
+  for (ConvOp* op : ops) {
+    if (op->tc && op->tcv == 2) { op->tc2l.d_maps = reinterpret_cast<const ConvTc2Maps*>((char*)d + off); off += sizeof(ConvTc2Maps); }
+    if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)d + off); off += sizeof(ConvPairMaps); }
+  }
   *d_out = d;
   return "";
 }
@@ -183,6 +196,8 @@ struct gnv_decoder {
   int eb = 4;            // bytes per activation element E
   bool use_tc = true;
   int tc_version = 2;
+  bool fuse_pairs = true;   // conv1 + Snake + conv2 + residual of a ResBlock step in one kernel (C <= 128)
+  std::map<std::pair<int, int>, int> launch_counts;   // (B, T) -> conv launches of the last plan built
   ConvTc2Options tc2opt;
   int snake_kind = ACT_SNAKE;
   std::string err;
@@ -478,8 +493,18 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
   return "";
 }
 
+// Geometry + epilogue parameters of a layer without building a launch (the fused pair builds its own).
+std::string make_epi_only(const gnv_decoder* h, const ConvLayer& L, int B, int L_in, const EpiSpec& es, ConvOp* op) {
+  gnv_decoder tmp_h;
+  tmp_h.dtype = h->dtype; tmp_h.eb = h->eb; tmp_h.use_tc = false;   // no launch object
+  ConvLayer Lc = L;
+  Lc.strided_simt = false;
+  return make_op(&tmp_h, Lc, nullptr, B, L_in, es, op);
+}
+
 cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   if (op.tc) {
+    if (op.tcv == 3) return launch_conv_pair(op.pairl, lengths, st);
     if (op.tcv == 2) return launch_conv_tc2(op.tc2l, lengths, st);
     if (!lengths) return launch_conv_tc(op.tcl, st);
     ConvTcLaunch L = op.tcl;
@@ -544,24 +569,64 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
     void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
     auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
                         int j, const std::string& rbname) {
+      void* cur = EA;                 // the (activated) input of the next dilation step
       for (int d = 0; d < 3; ++d) {
-        {
-          EpiSpec es; es.len_mul = lm; es.len_add = la;
-          es.acts.push_back({snake, R.a2[d], 0.f, E[3]});
-          add(ops, R.c1[d], EA, Ls, es, rbname + ".convs1." + std::to_string(d));
-        }
         EpiSpec es; es.len_mul = lm; es.len_add = la;
         es.res = d == 0 ? res_first : raw_stream;
+        ActSpec next_act;             // what the step emits for its successor (none for the last step of j < 2)
+        bool has_next = false;
         if (d < 2) {
           es.raw = raw_stream;
-          es.acts.push_back({snake, R.a1[d + 1], 0.f, EA});
+          next_act = {snake, R.a1[d + 1], 0.f, nullptr};
+          has_next = true;
         } else if (!final_to_sum) {
           es.raw = raw_stream;
         } else {
           es.raw = F3; es.raw_scale = 1.f / 3.f; es.raw_accum = j > 0 ? 1 : 0;
-          if (j == 2) es.acts.push_back({ACT_LRELU, nullptr, i == 2 ? 0.01f : 0.1f, E[0]});
+          if (j == 2) { next_act = {ACT_LRELU, nullptr, i == 2 ? 0.01f : 0.1f, E[0]}; has_next = true; }
         }
-        add(ops, R.c2[d], E[3], Ls, es, rbname + ".convs2." + std::to_string(d));
+        // ---- fused: one kernel, the intermediate stays in shared memory.  The step reads `cur` with a
+        // halo while other tiles write the successor's input, so input and output ping-pong (cur <-> E3).
+        if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() && kStageC[i] <= 128) {
+          EpiSpec ef = es;
+          void* out_buf = (cur == E[3]) ? EA : E[3];
+          if (has_next) {
+            ActSpec a = next_act;
+            if (!a.out) a.out = out_buf;
+            ef.acts.push_back(a);
+          }
+          ConvOp op;
+          // build conv2's epilogue parameters through make_op's common path (geometry of a plain k-tap conv)
+          ConvOp tmp_op;
+          std::string me = make_epi_only(h, R.c2[d], B, Ls, ef, &tmp_op);
+          if (me.empty()) {
+            const char* pe = make_conv_pair_launch(&op.pairl, h->eb, cur, R.c1[d].w, R.c2[d].w, B, Ls, R.c1[d].C_in,
+                                                   R.c1[d].C_in_ld, R.c1[d].k, R.c1[d].dil, R.c1[d].bias, R.a2[d], snake,
+                                                   tmp_op.ep, h->tc2opt.max_ctas, h->tc2opt.mh);
+            if (!*pe) {
+              op.tc = true; op.tcv = 3;
+              op.g = tmp_op.g; op.ep = tmp_op.ep;
+              op.name = rbname + ".pair" + std::to_string(d);
+              op.flops = 2.0 * (2.0 * B * (double)Ls * R.c1[d].C_out * R.c1[d].C_in * R.c1[d].k);
+              ops.push_back(op);
+              if (has_next && next_act.out == nullptr) cur = out_buf;
+              continue;
+            }
+          }
+        }
+        // ---- two launches: conv1 -> E3, conv2 -> (raw, next act written over the step's own input)
+        {
+          EpiSpec e1; e1.len_mul = lm; e1.len_add = la;
+          void* mid = (cur == E[3]) ? EA : E[3];
+          e1.acts.push_back({snake, R.a2[d], 0.f, mid});
+          add(ops, R.c1[d], cur, Ls, e1, rbname + ".convs1." + std::to_string(d));
+          if (has_next) {
+            ActSpec a = next_act;
+            if (!a.out) a.out = cur;
+            es.acts.push_back(a);
+          }
+          add(ops, R.c2[d], mid, Ls, es, rbname + ".convs2." + std::to_string(d));
+        }
       }
     };
     // source branch
@@ -605,6 +670,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   std::vector<ConvOp*> all;
   for (ConvOp& op : plan->f0_ops) all.push_back(&op);
   for (ConvOp& op : plan->decode_ops) all.push_back(&op);
+  h->launch_counts[{B, T}] = (int)plan->decode_ops.size();
   return upload_maps(all, &plan->d_maps);
 }
 
@@ -739,6 +805,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   h->use_tc = dtype != GNV_DTYPE_FP32 && !(flags & GNV_FLAG_SIMT_CONV);
   h->tc_version = (flags & GNV_FLAG_TC_V1) ? 1 : 2;
   h->tc2opt = tc2_options_from_env();
+  if (const char* v = getenv("GONOVA_FUSE_PAIRS")) h->fuse_pairs = atoi(v) != 0;
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
   std::string err;
@@ -773,6 +840,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   if (h->use_tc) {
     ce = conv_tc_init();
     if (ce == cudaSuccess) ce = conv_tc2_init();
+    if (ce == cudaSuccess) ce = conv_pair_init();
     if (ce != cudaSuccess) {
       gnv_destroy(h);
       return fail_cuda(nullptr, "conv_tc_init", ce);
@@ -1050,9 +1118,16 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
 
 int gnv_decode_launches(gnv_handle h, int B, int T, int* out) {
   if (!h || !out) return fail(h, "NULL argument");
-  (void)B; (void)T;
-  // pack mel + STFT + conv_pre + 3 x (source_down + 6 + ups + 18) + conv_post + iSTFT
-  *out = 2 + 1 + 3 * (1 + 6 + 1 + 18) + 1 + 1;
+  // pack mel + STFT + iSTFT head + the conv launches of the plan (unfused: conv_pre + 3 x (source_down + 6 +
+  // ups + 18) + conv_post = 80; fused ResBlock pairs in stages 1 and 2 make it 56)
+  int convs = 1 + 3 * (1 + 6 + 1 + 18) + 1;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto it = h->launch_counts.find({B, T});
+    if (it != h->launch_counts.end()) convs = it->second;
+    else if (h->use_tc && h->tc_version == 2 && h->fuse_pairs) convs -= 2 * 4 * 3;
+  }
+  *out = 3 + convs;
   return 0;
 }
 

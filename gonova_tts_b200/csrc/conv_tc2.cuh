@@ -139,6 +139,147 @@ static __device__ __noinline__ float snake_precise(float x, float alpha, float i
   return x + inv * (s * s);
 }
 static __device__ __noinline__ float elu_precise(float x) { return x > 0.f ? x : expm1f(x); }
+
+// The part of the epilogue every conv kernel shares: given one 128-row x 32-column chunk of
+// (accumulator + bias) in registers, add the residual / running-sum tiles the loader warp staged,
+// scale, zero dead rows, stage the fp32 result and its activated copies in (swizzled) shared memory
+// and hand them to TMA stores.  Called by all threads of one epilogue warpgroup.
+struct EpiCtx {
+  const EpiParams* ep;
+  const float* tab;            // bias[c_tab], then (alpha[c_tab], 1/(alpha+1e-9)[c_tab]) per activation
+  int c_tab, n_in, has_raw, n_act, act_bytes, n_epi_wg, out_bufs;
+  uint8_t* smem_in;            // the loader's ring of two input slots
+  uint32_t b_in_full, b_in_empty;
+  uint32_t obase_wg;           // this warpgroup's staging buffers
+  int out_stride;
+  int wg, erow, lane;
+  bool elected;
+};
+
+template <typename E>
+__device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32], bool live, int c0,
+                                                const CUtensorMap* maps6, int cs, int mrow, int b, Ring& rin, int& ob) {
+    // ---- residual, scale, running sum ----
+    if (c.n_in > 0) {
+      // two warpgroups: this one owns slot `wg` of the loader's ring of two; one: it uses both in turn
+      const int in_slot = c.n_epi_wg == 2 ? c.wg : rin.slot;
+      const uint8_t* in_tile = c.smem_in + (size_t)in_slot * c.n_in * (BLOCK_M * kEpiCols * 4);
+      mbar_wait(c.b_in_full + 8u * in_slot, rin.phase, 5);
+      if (c.ep->res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = *reinterpret_cast<const float4*>(in_tile + c.erow * 128 + ((j ^ (c.erow & 7)) << 4));
+          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      }
+      if (c.ep->raw_scale != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= c.ep->raw_scale;
+      }
+      if (c.ep->raw_accum) {
+        const uint8_t* in1 = in_tile + (c.ep->res ? BLOCK_M * kEpiCols * 4 : 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 r = *reinterpret_cast<const float4*>(in1 + c.erow * 128 + ((j ^ (c.erow & 7)) << 4));
+          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      }
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(c.b_in_empty + 8u * in_slot);
+      if (c.n_epi_wg == 2) rin.phase ^= 1u; else rin.advance(2);
+    } else if (c.ep->raw_scale != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= c.ep->raw_scale;
+    }
+    if (!live) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    // ---- stage the outputs (the store that last used this staging buffer must have drained) ----
+    const uint32_t obase = c.obase_wg + ob * c.out_stride;
+    if (c.elected) {
+      if (c.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+    }
+    epi_bar_sync(c.wg);
+    uint32_t o = obase;
+    if (c.has_raw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(tile_addr_f32(o, c.erow, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      o += BLOCK_M * kEpiCols * 4;
+    }
+    for (int a = 0; a < c.n_act; ++a) {
+      // The activation kind is uniform for the launch: one tight loop per kind (a per-element
+      // switch makes the compiler evaluate every variant and select).  Every activation maps
+      // 0 -> 0, so rows that are not live (v == 0) need no extra select.
+      const int kind = c.ep->act_kind[a];
+      const float4* al = reinterpret_cast<const float4*>(c.tab + (1 + 2 * a) * c.c_tab + c0);
+      const float4* iv = reinterpret_cast<const float4*>(c.tab + (2 + 2 * a) * c.c_tab + c0);
+      float y[32];
+      if (kind == ACT_SNAKE_FAST) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a4 = al[j], i4 = iv[j];
+          float s;
+          s = __sinf(v[4 * j] * a4.x);     y[4 * j]     = fmaf(i4.x, s * s, v[4 * j]);
+          s = __sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = fmaf(i4.y, s * s, v[4 * j + 1]);
+          s = __sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = fmaf(i4.z, s * s, v[4 * j + 2]);
+          s = __sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = fmaf(i4.w, s * s, v[4 * j + 3]);
+        }
+      } else if (kind == ACT_LRELU) {
+        const float slope = c.ep->act_slope[a];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+      } else if (kind == ACT_SNAKE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 a4 = al[j], i4 = iv[j];
+          y[4 * j]     = snake_precise(v[4 * j], a4.x, i4.x);
+          y[4 * j + 1] = snake_precise(v[4 * j + 1], a4.y, i4.y);
+          y[4 * j + 2] = snake_precise(v[4 * j + 2], a4.z, i4.z);
+          y[4 * j + 3] = snake_precise(v[4 * j + 3], a4.w, i4.w);
+        }
+      } else if (kind == ACT_ELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = v[i];
+      }
+      if constexpr (sizeof(E) == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128u(tile_addr_b16(o, c.erow, j), ElemIO<E>::pack2(y[8 * j], y[8 * j + 1]),
+                  ElemIO<E>::pack2(y[8 * j + 2], y[8 * j + 3]), ElemIO<E>::pack2(y[8 * j + 4], y[8 * j + 5]),
+                  ElemIO<E>::pack2(y[8 * j + 6], y[8 * j + 7]));
+      } else {
+        if (c.ep->round_tf32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = round_tf32(y[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(tile_addr_f32(o, c.erow, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+      o += c.act_bytes;
+    }
+    fence_async_smem();
+    epi_bar_sync(c.wg);
+    if (c.elected) {
+      uint32_t src = obase;
+                if (c.has_raw) {
+        tma_store_3d(maps6 + EPI_RAW, src, cs, mrow, b);
+        src += BLOCK_M * kEpiCols * 4;
+      }
+      for (int a = 0; a < c.n_act; ++a) {
+        tma_store_3d(maps6 + EPI_ACT0 + a, src, cs, mrow, b);
+        src += c.act_bytes;
+      }
+      bulk_commit();
+    }
+    if (++ob == c.out_bufs) ob = 0;
+}
+
 template <typename E>
 __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab, const float (&v)[32], int b, int c0,
                                        bool live0);
@@ -325,6 +466,12 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     int ob = 0;
     Ring racc, rin;                                     // rin: this warpgroup's view of the input ring
     const int n_items = p.mh * n_epi_chunks;
+    EpiCtx ectx;
+    ectx.ep = &p.ep; ectx.tab = tab; ectx.c_tab = p.c_tab; ectx.n_in = p.n_in; ectx.has_raw = p.has_raw;
+    ectx.n_act = p.n_act; ectx.act_bytes = p.act_bytes; ectx.n_epi_wg = p.n_epi_wg; ectx.out_bufs = p.out_bufs;
+    ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty;
+    ectx.obase_wg = obase_wg; ectx.out_stride = out_stride; ectx.wg = wg; ectx.erow = erow; ectx.lane = lane;
+    ectx.elected = elected;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       int qq = t;
       const int n_tile = qq % p.n_tiles_n; qq /= p.n_tiles_n;
@@ -370,126 +517,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) tmp[i] = v[i];
           tc2::emit_row0<E>(p, tab, tmp, b, c0, 0 < valid_rows);
         }
-        // ---- residual, scale, running sum ----
-        if (p.n_in > 0) {
-          // two warpgroups: this one owns slot `wg` of the loader's ring of two; one: it uses both in turn
-          const int in_slot = p.n_epi_wg == 2 ? wg : rin.slot;
-          const uint8_t* in_tile = smem_gen + p.off_in + (size_t)in_slot * p.n_in * (BLOCK_M * kEpiCols * 4);
-          mbar_wait(b_in_full + 8u * in_slot, rin.phase, 5);
-          if (p.ep.res) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = *reinterpret_cast<const float4*>(in_tile + erow * 128 + ((j ^ (erow & 7)) << 4));
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-          if (p.ep.raw_scale != 1.0f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
-          }
-          if (p.ep.raw_accum) {
-            const uint8_t* in1 = in_tile + (p.ep.res ? BLOCK_M * kEpiCols * 4 : 0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = *reinterpret_cast<const float4*>(in1 + erow * 128 + ((j ^ (erow & 7)) << 4));
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(b_in_empty + 8u * in_slot);
-          if (p.n_epi_wg == 2) rin.phase ^= 1u; else rin.advance(2);
-        } else if (p.ep.raw_scale != 1.0f) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.ep.raw_scale;
-        }
-        if (!live) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        // ---- stage the outputs (the store that last used this staging buffer must have drained) ----
-        const uint32_t obase = obase_wg + ob * out_stride;
-        if (elected) {
-          if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-        }
-        epi_bar_sync(wg);
-        uint32_t o = obase;
-        if (p.has_raw) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(tile_addr_f32(o, erow, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          o += BLOCK_M * kEpiCols * 4;
-        }
-        for (int a = 0; a < p.n_act; ++a) {
-          // The activation kind is uniform for the launch: one tight loop per kind (a per-element
-          // switch makes the compiler evaluate every variant and select).  Every activation maps
-          // 0 -> 0, so rows that are not live (v == 0) need no extra select.
-          const int kind = p.ep.act_kind[a];
-          const float4* al = reinterpret_cast<const float4*>(tab + (1 + 2 * a) * p.c_tab + c0);
-          const float4* iv = reinterpret_cast<const float4*>(tab + (2 + 2 * a) * p.c_tab + c0);
-          float y[32];
-          if (kind == ACT_SNAKE_FAST) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 a4 = al[j], i4 = iv[j];
-              float s;
-              s = __sinf(v[4 * j] * a4.x);     y[4 * j]     = fmaf(i4.x, s * s, v[4 * j]);
-              s = __sinf(v[4 * j + 1] * a4.y); y[4 * j + 1] = fmaf(i4.y, s * s, v[4 * j + 1]);
-              s = __sinf(v[4 * j + 2] * a4.z); y[4 * j + 2] = fmaf(i4.z, s * s, v[4 * j + 2]);
-              s = __sinf(v[4 * j + 3] * a4.w); y[4 * j + 3] = fmaf(i4.w, s * s, v[4 * j + 3]);
-            }
-          } else if (kind == ACT_LRELU) {
-            const float slope = p.ep.act_slope[a];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
-          } else if (kind == ACT_SNAKE) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 a4 = al[j], i4 = iv[j];
-              y[4 * j]     = snake_precise(v[4 * j], a4.x, i4.x);
-              y[4 * j + 1] = snake_precise(v[4 * j + 1], a4.y, i4.y);
-              y[4 * j + 2] = snake_precise(v[4 * j + 2], a4.z, i4.z);
-              y[4 * j + 3] = snake_precise(v[4 * j + 3], a4.w, i4.w);
-            }
-          } else if (kind == ACT_ELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = v[i];
-          }
-          if constexpr (sizeof(E) == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128u(tile_addr_b16(o, erow, j), ElemIO<E>::pack2(y[8 * j], y[8 * j + 1]),
-                      ElemIO<E>::pack2(y[8 * j + 2], y[8 * j + 3]), ElemIO<E>::pack2(y[8 * j + 4], y[8 * j + 5]),
-                      ElemIO<E>::pack2(y[8 * j + 6], y[8 * j + 7]));
-          } else {
-            if (p.ep.round_tf32) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = round_tf32(y[i]);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(tile_addr_f32(o, erow, j), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-          }
-          o += p.act_bytes;
-        }
-        fence_async_smem();
-        epi_bar_sync(wg);
-        if (elected) {
-          uint32_t src = obase;
-          const int cs = cbase + cc * kEpiCols;
-          if (p.has_raw) {
-            tma_store_3d(&maps.epi[ph][EPI_RAW], src, cs, mrow, b);
-            src += BLOCK_M * kEpiCols * 4;
-          }
-          for (int a = 0; a < p.n_act; ++a) {
-            tma_store_3d(&maps.epi[ph][EPI_ACT0 + a], src, cs, mrow, b);
-            src += p.act_bytes;
-          }
-          bulk_commit();
-        }
-        if (++ob == p.out_bufs) ob = 0;
+        tc2::epi_finish_item<E>(ectx, v, live, c0, &maps.epi[ph][0], cbase + cc * kEpiCols, mrow, b, rin, ob);
       }
       // accumulator drained: hand the TMEM buffer back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
