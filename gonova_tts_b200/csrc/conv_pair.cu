@@ -85,6 +85,8 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   }
   p.slab_bytes = (int)up1024((uint32_t)(p.a_n_boxes * p.a_box_rows) * 128u);
   p.w_bytes = C * 128;
+  p.w_group = std::max(1, std::min(4, 32768 / p.w_bytes));
+  p.w_slot_bytes = p.w_group * p.w_bytes;
   p.h_kb_bytes = 128 * mh * 128;
   // conv2's taps read up to k-1 rows past the slab's last K block: keep that inside the allocation
   const uint32_t h_bytes = up1024((uint32_t)p.n_chunks * p.h_kb_bytes + (uint32_t)(k - 1) * 128u);
@@ -103,17 +105,17 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
 
   int sa = 1, sw = 2, nob = 1;
   auto total = [&](int sa_, int sw_, int nob_) {
-    return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_bytes + h_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
+    return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_slot_bytes + h_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
            bar_bytes + 1024;
   };
   if (total(sa, sw, nob) > kMaxDynSmemPair) return "conv_pair: shared memory budget exceeded";
   const int max_sa = std::min(3, p.n_chunks + 1);
-  const int max_sw = 8;
+  const int max_sw = 6;
   bool grew = true;
   while (grew) {
     grew = false;
     if (nob < 2 && total(sa, sw, nob + 1) <= kMaxDynSmemPair) { ++nob; grew = true; }
-    if (sw < 4 && total(sa, sw + 1, nob) <= kMaxDynSmemPair) { ++sw; grew = true; }
+    if (sw < 3 && total(sa, sw + 1, nob) <= kMaxDynSmemPair) { ++sw; grew = true; }
     if (sa < 2 && sa < max_sa && total(sa + 1, sw, nob) <= kMaxDynSmemPair) { ++sa; grew = true; }
     if (nob == 2 && total(sa, sw, 4) <= kMaxDynSmemPair) { nob = 4; grew = true; }
     if (!grew && sw < max_sw && total(sa, sw + 1, nob) <= kMaxDynSmemPair) { ++sw; grew = true; }
@@ -122,7 +124,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   p.sa = sa; p.sw = sw; p.n_epi_wg = nob >= 2 ? 2 : 1; p.out_bufs = nob == 4 ? 2 : 1;
   uint32_t off = 0;
   p.off_a = off; off += (uint32_t)sa * p.slab_bytes;
-  p.off_w = off; off += (uint32_t)sw * p.w_bytes;
+  p.off_w = off; off += (uint32_t)sw * p.w_slot_bytes;
   p.off_h = off; off += h_bytes;
   p.off_in = off; off += in_bytes;
   p.off_out = off; off += (uint32_t)nob * out_buf;

@@ -33,6 +33,7 @@ struct ConvPairParams {
   int a_box_rows, a_n_boxes, slab_bytes;
   int h_kb_bytes;                  // one K block of the h slab: 128*mh rows x 128 B
   int w_bytes;                     // one weight tile: C rows x 128 B
+  int w_group, w_slot_bytes;       // taps per weight barrier / ring slot
   int sa, sw, n_epi_wg, out_bufs;
   uint32_t idesc;
   int n_in, has_raw, n_act, act_bytes, c_tab;
@@ -78,12 +79,12 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KBE = KBLK_BYTES / (int)sizeof(E);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     prefetch_tmap(&maps.X);
     prefetch_tmap(&maps.W1);
     prefetch_tmap(&maps.W2);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpLoader && lane == 0) {
     for (int s = 0; s < p.sa; ++s) { mbar_init(b_a_full + 8u * s, 1); mbar_init(b_a_empty + 8u * s, 1); }
     for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
     mbar_init(b_acc1_full, 1);
@@ -97,7 +98,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == kWarpTmem) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -126,10 +127,21 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   const int n_epi_chunks = p.C / kEpiCols;
   const int G = gridDim.x;
 
-  if (warp == 0) {
+  if (warp == kWarpProducer) {
     if (lane == 0) {
-      // ===== TMA producer: x slabs + W1 tiles for M1, W2 tiles for M2, in the issuer's order =====
+      // ===== TMA producer: x slabs + W1 tile groups for M1, W2 tile groups for M2, in the issuer's order =====
       Ring ra, rw;
+      auto load_w_groups = [&](const CUtensorMap* wm, int ch) {
+        for (int tap = 0; tap < p.k; tap += p.w_group) {
+          const int ng = min(p.w_group, p.k - tap);
+          mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
+          mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes));
+          for (int g = 0; g < ng; ++g)
+            tma_load_2d(wm, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                        ((tap + g) * p.n_chunks + ch) * KBE, 0);
+          rw.advance(p.sw);
+        }
+      };
       auto load_m1 = [&](int t) {
         const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
         const int r0 = m_tile * p.Mo - p.p2 - p.p1;                 // first x row of the slab
@@ -141,22 +153,11 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
             tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
                         r0 + bx * p.a_box_rows, b);
           ra.advance(p.sa);
-          for (int tap = 0; tap < p.k; ++tap) {
-            mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
-            mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)p.w_bytes);
-            tma_load_2d(&maps.W1, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_bytes, (tap * p.n_chunks + ch) * KBE, 0);
-            rw.advance(p.sw);
-          }
+          load_w_groups(&maps.W1, ch);
         }
       };
       auto load_m2 = [&]() {
-        for (int ch = 0; ch < p.n_chunks; ++ch)
-          for (int tap = 0; tap < p.k; ++tap) {
-            mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
-            mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)p.w_bytes);
-            tma_load_2d(&maps.W2, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_bytes, (tap * p.n_chunks + ch) * KBE, 0);
-            rw.advance(p.sw);
-          }
+        for (int ch = 0; ch < p.n_chunks; ++ch) load_w_groups(&maps.W2, ch);
       };
       if ((int)blockIdx.x < p.total_tiles) load_m1(blockIdx.x);
       for (int t = blockIdx.x; t < p.total_tiles; t += G) {
@@ -164,31 +165,38 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         if (t + G < p.total_tiles) load_m1(t + G);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     if (lane == 0) {
       // ===== MMA issuer =====
+      const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW), h_desc0 = umma_desc_sw128(sH);
       Ring ra, rw;
+      // one K block (channel block ch) of a conv: every tap group's weights against row-shifted views of `a_base`
+      auto issue_taps = [&](uint64_t a_base, int row_step, uint32_t acc0, uint32_t& accum) {
+        for (int tap = 0; tap < p.k; tap += p.w_group) {
+          const int ng = min(p.w_group, p.k - tap);
+          mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int g = 0; g < ng; ++g) {
+            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
+            const uint64_t ad0 = a_base + (uint64_t)((uint32_t)((tap + g) * row_step) * (KBLK_BYTES >> 4));
+            for (int h = 0; h < p.mh; ++h) {
+              const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
+              const uint32_t acc = acc0 + (uint32_t)(h * p.C);
+              umma<E>(acc, ad, bd, p.idesc, accum);
+#pragma unroll
+              for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+            }
+            accum = 1u;
+          }
+          umma_commit(b_w_empty + 8u * rw.slot);
+          rw.advance(p.sw);
+        }
+      };
       auto issue_m1 = [&]() {
-        bool first = true;
+        uint32_t accum = 0u;
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t slab = sA + ra.slot * p.slab_bytes;
-          for (int tap = 0; tap < p.k; ++tap) {
-            mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t bd = umma_desc_sw128(sW + rw.slot * p.w_bytes);
-            for (int h = 0; h < p.mh; ++h) {
-              const uint64_t ad = umma_desc_sw128(slab + (uint32_t)(tap * p.d1 + h * BLOCK_M) * KBLK_BYTES);
-              const uint32_t acc = tmem_base + acc1_col + (uint32_t)(h * p.C);
-#pragma unroll
-              for (int kk = 0; kk < KBLK_BYTES / 32; ++kk)
-                umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
-            }
-            first = false;
-            umma_commit(b_w_empty + 8u * rw.slot);
-            rw.advance(p.sw);
-          }
+          issue_taps(a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4), p.d1, tmem_base + acc1_col, accum);
           umma_commit(b_a_empty + 8u * ra.slot);
           ra.advance(p.sa);
         }
@@ -197,24 +205,10 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       auto issue_m2 = [&](int i) {
         const int buf = i & 1;
         mbar_wait(b_acc2_empty + 8u * buf, (uint32_t)((i >> 1) & 1) ^ 1u, 2);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        bool first = true;
+        uint32_t accum = 0u;
         for (int ch = 0; ch < p.n_chunks; ++ch)
-          for (int tap = 0; tap < p.k; ++tap) {
-            mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t bd = umma_desc_sw128(sW + rw.slot * p.w_bytes);
-            for (int h = 0; h < p.mh; ++h) {
-              const uint64_t ad = umma_desc_sw128(sH + (uint32_t)ch * p.h_kb_bytes + (uint32_t)(tap + h * BLOCK_M) * KBLK_BYTES);
-              const uint32_t acc = tmem_base + acc2_col0 + (uint32_t)((buf * p.mh + h) * p.C);
-#pragma unroll
-              for (int kk = 0; kk < KBLK_BYTES / 32; ++kk)
-                umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, (first && kk == 0) ? 0u : 1u);
-            }
-            first = false;
-            umma_commit(b_w_empty + 8u * rw.slot);
-            rw.advance(p.sw);
-          }
+          issue_taps(h_desc0 + (uint64_t)((uint32_t)(ch * p.h_kb_bytes) >> 4), 1,
+                     tmem_base + acc2_col0 + (uint32_t)(buf * p.mh * p.C), accum);
         umma_commit(b_acc2_full + 8u * buf);
         umma_commit(b_h_empty);
       };
@@ -227,7 +221,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         if (t + G < p.total_tiles) issue_m1();
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == kWarpLoader) {
     if (lane == 0 && p.n_in > 0) {
       // ===== epilogue-2 input loader (same ring protocol as conv_tc2) =====
       uint32_t slot_phase[2] = {0u, 0u};
@@ -248,12 +242,12 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4 && (warp - 4) / 4 < p.n_epi_wg) {
+  } else if (warp < 8 && (warp >> 2) < p.n_epi_wg) {
     // ===== epilogue warpgroups: E1(i) then E2(i-1) =====
-    const int wg = (warp - 4) >> 2;
+    const int wg = warp >> 2;
     const int q = warp & 3;
     const int erow = q * 32 + lane;
-    const bool elected = ((threadIdx.x - 128) & 127) == 0;
+    const bool elected = (threadIdx.x & 127) == 0;
     const int out_stride = (p.has_raw ? BLOCK_M * kEpiCols * 4 : 0) + p.n_act * p.act_bytes;
     Ring rin;
     int ob = 0;
@@ -386,7 +380,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kWarpTmem) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }

@@ -130,6 +130,9 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   }
   p.slab_bytes = (int)up1024((uint32_t)(p.a_n_boxes * p.a_box_rows) * 128u);
   p.w_bytes = block_n * 128;
+  p.w_group = std::max(1, std::min(4, 32768 / p.w_bytes));
+  if (opt.w_group > 0) p.w_group = std::min(opt.w_group, 4);
+  p.w_slot_bytes = p.w_group * p.w_bytes;
 
   // ---- epilogue staging ----
   p.n_in = (ep.res ? 1 : 0) + (ep.raw_accum ? 1 : 0);
@@ -148,12 +151,12 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   const int k_iters = p.n_chunks * g.n_taps;
   int sa = 1, sw = 2, nob = 1;          // nob = staging buffers in total = warpgroups * buffers per warpgroup
   auto total = [&](int sa_, int sw_, int nob_) {
-    return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
+    return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_slot_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
            bar_bytes + 1024 /*alignment slack*/;
   };
   if (total(sa, sw, nob) > kMaxDynSmem2) return "conv_tc2: shared memory budget exceeded";
   const int max_sa = std::min(p.n_slabs == 1 ? 3 : 6, p.n_chunks * p.n_slabs + 1);
-  const int max_sw = std::min(6, k_iters + 1);
+  const int max_sw = std::min(6, (k_iters + p.w_group - 1) / p.w_group + 1);
   bool grew = true;
   while (grew) {
     grew = false;
@@ -167,7 +170,7 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   p.sa = sa; p.sw = sw; p.n_epi_wg = nob >= 2 ? 2 : 1; p.out_bufs = nob == 4 ? 2 : 1;
   uint32_t off = 0;
   p.off_a = off; off += (uint32_t)sa * p.slab_bytes;
-  p.off_w = off; off += (uint32_t)sw * p.w_bytes;
+  p.off_w = off; off += (uint32_t)sw * p.w_slot_bytes;
   p.off_in = off; off += in_bytes;
   p.off_out = off; off += (uint32_t)nob * out_buf;
   off = up1024(off);
