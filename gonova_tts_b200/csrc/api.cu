@@ -196,7 +196,10 @@ struct gnv_decoder {
   int eb = 4;            // bytes per activation element E
   bool use_tc = true;
   int tc_version = 2;
-  bool fuse_pairs = true;   // conv1 + Snake + conv2 + residual of a ResBlock step in one kernel (C <= 128)
+  bool fuse_pairs = true;   // conv1 + Snake + conv2 + residual of a ResBlock step in one kernel
+  int fuse_max_c = 64;      // ... for stages with at most this many channels.  Measured (B=64, T=500, bf16): C=64
+                            // pairs are 5-28 % faster fused; C=128 pairs must drop to 128-row tiles to fit TMEM
+                            // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
   std::map<std::pair<int, int>, int> launch_counts;   // (B, T) -> conv launches of the last plan built
   ConvTc2Options tc2opt;
   int snake_kind = ACT_SNAKE;
@@ -588,7 +591,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
         }
         // ---- fused: one kernel, the intermediate stays in shared memory.  The step reads `cur` with a
         // halo while other tiles write the successor's input, so input and output ping-pong (cur <-> E3).
-        if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() && kStageC[i] <= 128) {
+        if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() && kStageC[i] <= h->fuse_max_c) {
           EpiSpec ef = es;
           void* out_buf = (cur == E[3]) ? EA : E[3];
           if (has_next) {
@@ -807,6 +810,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   h->tc_version = (flags & GNV_FLAG_TC_V1) ? 1 : 2;
   h->tc2opt = tc2_options_from_env();
   if (const char* v = getenv("GONOVA_FUSE_PAIRS")) h->fuse_pairs = atoi(v) != 0;
+  if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
   std::string err;
@@ -1126,7 +1130,7 @@ int gnv_decode_launches(gnv_handle h, int B, int T, int* out) {
     std::lock_guard<std::mutex> lk(h->mu);
     auto it = h->launch_counts.find({B, T});
     if (it != h->launch_counts.end()) convs = it->second;
-    else if (h->use_tc && h->tc_version == 2 && h->fuse_pairs) convs -= 2 * 4 * 3;
+    else if (h->use_tc && h->tc_version == 2 && h->fuse_pairs) convs -= 4 * 3 * (h->fuse_max_c >= 128 ? 2 : 1);
   }
   *out = 3 + convs;
   return 0;

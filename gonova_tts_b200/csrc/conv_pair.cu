@@ -108,6 +108,10 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
     return (size_t)sa_ * p.slab_bytes + (size_t)sw_ * p.w_slot_bytes + h_bytes + in_bytes + (size_t)nob_ * out_buf + tab_bytes +
            bar_bytes + 1024;
   };
+  while (total(sa, sw, nob) > kMaxDynSmemPair && p.w_group > 1) {       // smaller weight ring slots first
+    p.w_group >>= 1;
+    p.w_slot_bytes = p.w_group * p.w_bytes;
+  }
   if (total(sa, sw, nob) > kMaxDynSmemPair) return "conv_pair: shared memory budget exceeded";
   const int max_sa = std::min(3, p.n_chunks + 1);
   const int max_sw = 6;
