@@ -291,10 +291,26 @@ def main():
         if args.dtype != "bf16":
             peak_tf = peak_tf / 2 if args.dtype == "tf32" else 75.0    # tf32 = half the bf16 rate; fp32 FMA nominal
         achieved_tf = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        # DRAM bytes of the same launches from the committed ncu capture (profiles/), valid for the default workload
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+                tj = json.load(f)
+            if (B, T, args.dtype) == (64, 500, "bf16"):
+                traffic, traffic_src = tj["traffic_bytes"], "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write, all conv launches of one step)"
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         roofline = {
-            "kernel": f"conv_tc2_kernel<{args.dtype}> (persistent tcgen05 implicit-GEMM conv; {len(tc)} launches per step)",
+            "kernel": f"conv_tc2_kernel + conv_pair_kernel <{args.dtype}> (persistent tcgen05 implicit-GEMM convs; "
+                      f"{len(tc)} launches per step, timed as a family)",
             "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": traffic_src,
+            "hbm_view": None if traffic is None else {
+                "achieved_GBps": traffic / (tc_ms / 1e3) / 1e9, "peak_GBps": hbm_peak,
+                "frac": traffic / (tc_ms / 1e3) / 1e9 / hbm_peak,
+                "note": "the family is close to balanced: the same launches at the HBM peak would take "
+                        f"{traffic / hbm_peak / 1e6:.1f} ms, at the tensor peak {tc_flops / peak_tf / 1e9:.1f} ms"},
             "peak_source": peak_src + (" bf16 sustained" if args.dtype == "bf16" else " derived for " + args.dtype),
             "algorithmic_flops_per_step": tc_flops, "kernel_ms_per_step": tc_ms,
             "share_of_step": tc_ms / step_ms_profiled if step_ms_profiled else None,
