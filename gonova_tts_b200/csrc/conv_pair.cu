@@ -63,12 +63,12 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
 
   int mh = mh_opt;
   if (mh != 1 && mh != 2) {
-    mh = 3 * 2 * C <= 512 ? 2 : 1;
+    mh = 4 * 2 * C <= 512 ? 2 : 1;
     const long tiles2 = (long)B * ((L + (256 - (k - 1)) - 1) / (256 - (k - 1)));
     if (tiles2 < 2L * max_ctas) mh = 1;
   }
-  if (3 * mh * C > 512) mh = 1;
-  if (3 * mh * C > 512) return "conv_pair: accumulators do not fit TMEM";
+  if (4 * mh * C > 512) mh = 1;
+  if (4 * mh * C > 512) return "conv_pair: accumulators do not fit TMEM";
   p.mh = mh;
   p.Mo = 128 * mh - (k - 1);
   p.tiles_m = (L + p.Mo - 1) / p.Mo;
@@ -137,7 +137,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   p.off_bar = off; off += bar_bytes;
   out->smem_bytes = (size_t)off + 1024;
   if (out->smem_bytes > kMaxDynSmemPair) return "conv_pair: shared memory budget exceeded";
-  if (8 * (2 * sa + 2 * sw + 12) + 16 > (int)bar_bytes) return "conv_pair: barrier area too small";
+  if (8 * (2 * sa + 2 * sw + 13) + 16 > (int)bar_bytes) return "conv_pair: barrier area too small";
 
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if (((uintptr_t)x & 15) || ((uintptr_t)w1 & 15) || ((uintptr_t)w2 & 15)) return "conv_pair: operand pointers must be 16-byte aligned";

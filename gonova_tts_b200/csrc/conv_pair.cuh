@@ -13,9 +13,9 @@
 // so the halo recompute is (k-1)/(128*mh) of conv1 only (<= 4 % at mh = 2).
 //
 // Schedule (all roles walk the same static tile list t0, t1, ...):
-//   MMA issuer : M1(t0);  then per tile i:  wait E1(i) done -> M2(i) -> M1(i+1)
-//   epilogue   : per tile i:  E1(i) ; E2(i-1)          (so M2(i) and M1(i+1) run under E2(i-1))
-// TMEM: acc1 (one buffer, mh*C columns) + acc2 (two buffers): 3*mh*C <= 512 columns.
+//   MMA issuer : M1(0) M1(1);  then per tile i:  wait E1(i) done -> M2(i) -> M1(i+2)
+//   epilogue   : per tile i:  E1(i) ; E2(i-1)          (E1(i) never waits: M1(i) ran during tile i-2 / i-1)
+// TMEM: acc1 and acc2, two buffers each: 4*mh*C <= 512 columns (conv1 runs two tiles ahead of conv2).
 // Used for C <= 128 (stages 1 and 2, where the convs are memory / epilogue bound); C = 256 keeps the
 // two-launch path, which already runs at > 1 PFLOP/s.
 #pragma once
@@ -68,8 +68,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   const uint32_t bar0 = smem_base + p.off_bar;
   const uint32_t b_a_full = bar0, b_a_empty = b_a_full + 8u * p.sa;
   const uint32_t b_w_full = b_a_empty + 8u * p.sa, b_w_empty = b_w_full + 8u * p.sw;
-  const uint32_t b_acc1_full = b_w_empty + 8u * p.sw;
-  const uint32_t b_e1_done = b_acc1_full + 8u;        // epilogue 1 finished: h slab valid AND acc1 free
+  const uint32_t b_acc1_full = b_w_empty + 8u * p.sw; // two buffers
+  const uint32_t b_e1_done = b_acc1_full + 16u;       // epilogue 1 finished: h slab valid AND its acc1 buffer free
   const uint32_t b_h_empty = b_e1_done + 8u;          // conv2 MMAs retired: h slab may be overwritten
   const uint32_t b_acc2_full = b_h_empty + 8u, b_acc2_empty = b_acc2_full + 16u;
   const uint32_t b_in_full = b_acc2_empty + 16u, b_in_empty = b_in_full + 16u;
@@ -88,6 +88,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     for (int s = 0; s < p.sa; ++s) { mbar_init(b_a_full + 8u * s, 1); mbar_init(b_a_empty + 8u * s, 1); }
     for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
     mbar_init(b_acc1_full, 1);
+    mbar_init(b_acc1_full + 8u, 1);
     mbar_init(b_e1_done, 4 * p.n_epi_wg);
     mbar_init(b_h_empty, 1);
     for (int s = 0; s < 2; ++s) {
@@ -122,7 +123,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t acc1_col = 0, acc2_col0 = (uint32_t)(p.mh * p.C);   // acc2 buffer j at acc2_col0 + j*mh*C
+  // TMEM columns: acc1 buffers at 0 and mh*C, acc2 buffers at 2*mh*C and 3*mh*C
+  const uint32_t acc2_col0 = (uint32_t)(2 * p.mh * p.C);
 
   const int n_epi_chunks = p.C / kEpiCols;
   const int G = gridDim.x;
@@ -159,10 +161,12 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       auto load_m2 = [&]() {
         for (int ch = 0; ch < p.n_chunks; ++ch) load_w_groups(&maps.W2, ch);
       };
+      // the issuer runs conv1 two tiles ahead of conv2: M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...
       if ((int)blockIdx.x < p.total_tiles) load_m1(blockIdx.x);
+      if ((int)blockIdx.x + G < p.total_tiles) load_m1(blockIdx.x + G);
       for (int t = blockIdx.x; t < p.total_tiles; t += G) {
         load_m2();
-        if (t + G < p.total_tiles) load_m1(t + G);
+        if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G);
       }
     }
   } else if (warp == kWarpMma) {
@@ -192,15 +196,16 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           rw.advance(p.sw);
         }
       };
-      auto issue_m1 = [&]() {
+      auto issue_m1 = [&](int j) {                        // conv1 of this CTA's j-th tile into acc1 buffer j & 1
         uint32_t accum = 0u;
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
-          issue_taps(a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4), p.d1, tmem_base + acc1_col, accum);
+          issue_taps(a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4), p.d1,
+                     tmem_base + (uint32_t)((j & 1) * p.mh * p.C), accum);
           umma_commit(b_a_empty + 8u * ra.slot);
           ra.advance(p.sa);
         }
-        umma_commit(b_acc1_full);
+        umma_commit(b_acc1_full + 8u * (j & 1));
       };
       auto issue_m2 = [&](int i) {
         const int buf = i & 1;
@@ -212,13 +217,14 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         umma_commit(b_acc2_full + 8u * buf);
         umma_commit(b_h_empty);
       };
-      if ((int)blockIdx.x < p.total_tiles) issue_m1();
+      if ((int)blockIdx.x < p.total_tiles) issue_m1(0);
+      if ((int)blockIdx.x + G < p.total_tiles) issue_m1(1);
       int i = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += G, ++i) {
-        mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);          // h slab of tile i is valid, acc1 is free
+        mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);          // h slab of tile i is valid, acc1[i & 1] is free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_m2(i);
-        if (t + G < p.total_tiles) issue_m1();
+        if (t + 2 * G < p.total_tiles) issue_m1(i + 2);
       }
     }
   } else if (warp == kWarpLoader) {
@@ -273,7 +279,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
       const int g0 = m_tile * p.Mo - p.p2;                          // global row of h-slab row 0
       const int vr = valid_rows_of(b);
-      mbar_wait(b_acc1_full, (uint32_t)(i & 1), 4);
+      mbar_wait(b_acc1_full + 8u * (i & 1), (uint32_t)((i >> 1) & 1), 4);
       if (i > 0) mbar_wait(b_h_empty, (uint32_t)((i - 1) & 1), 4);  // conv2 of the previous tile has read the slab
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int item = (p.n_epi_wg == 2 ? wg : 0); item < n_items; item += p.n_epi_wg) {
@@ -282,7 +288,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         const int g = g0 + srow;
         const bool live1 = g >= 0 && g < vr;                        // conv2 sees zeros outside the utterance
         float v[32];
-        tmem_ld32(lane_base + acc1_col + (uint32_t)(h * p.C + cc * kEpiCols), v);
+        tmem_ld32(lane_base + (uint32_t)(((i & 1) * p.mh + h) * p.C + cc * kEpiCols), v);
         const int c0 = cc * kEpiCols;
         const float4* bt = reinterpret_cast<const float4*>(tab1 + c0);
         const float4* al = reinterpret_cast<const float4*>(tab1 + Cp + c0);
