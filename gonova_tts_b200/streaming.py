@@ -80,3 +80,48 @@ class StreamingDecoder:
             if f32 is not None:
                 f32s.append(f32)
         return (torch.cat(i16s, 1) if i16s else None), (torch.cat(f32s, 1) if f32s else None)
+
+
+class GraphedInference:
+    """inference() + PCM tail for one fixed (B, T), captured once in a CUDA graph and replayed.
+
+    The per-launch host cost of the ~70 kernels of a decode dominates the latency of a small chunk
+    (BASELINE config 2: batch 1, first chunk); a graph removes it.  All C-ABI decode calls are
+    capture-safe: they launch on the caller's current stream and neither allocate nor synchronise once
+    the (B, T) plan exists, which the warm-up below guarantees.  The NSF noise seed is baked into the
+    captured launch parameters, so every replay draws the same noise (use decode(x, s) with a host-side
+    source for per-call noise)."""
+
+    def __init__(self, hift: B200HiFT, B: int, T: int, emit_frames: Optional[int] = None, seed: int = 1,
+                 limit: float = 0.99, want_i16: bool = True, trim_fade: bool = False):
+        dev = hift.device
+        self.hift, self.B, self.T = hift, B, T
+        n_emit = (emit_frames if emit_frames is not None else T) * SAMPLES_PER_FRAME
+        self.mel = torch.zeros(B, 80, T, dtype=torch.float32, device=dev)
+        self.wav = torch.empty(B, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=dev)
+        self.src = torch.empty(B, 1, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=dev)
+        self.pcm = torch.empty(B, n_emit, dtype=torch.int16 if want_i16 else torch.float32, device=dev)
+        fw = trim_fade_window(dev) if trim_fade else None
+
+        def body():
+            hift.inference(self.mel, seed=seed, out=self.wav, source_out=self.src)
+            pcm_tail(self.wav[:, :n_emit], None, fw, limit, want_i16=want_i16, want_f32=not want_i16,
+                     out_i16=self.pcm if want_i16 else None, out_f32=None if want_i16 else self.pcm)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # builds the plan, warms the kernels
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    @torch.no_grad()
+    def __call__(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel [B,80,T] (device or pinned host) -> the graph's PCM buffer [B, n_emit] (overwritten by the next call)."""
+        self.mel.copy_(mel, non_blocking=True)
+        self.graph.replay()
+        return self.pcm
