@@ -19,7 +19,7 @@ ACT = {"none": 0, "snake": 1, "lrelu": 2, "elu": 3, "snake_fast": 4}
 SYMBOLS = [
     "gnv_create", "gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_workspace_bytes", "gnv_f0",
     "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_stft", "gnv_istft", "gnv_conv1d",
-    "gnv_debug_tap", "gnv_decode_launches", "gnv_inference_launches",
+    "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_float, f32p, f32p,
                                C.c_int, vp]
     lib.gnv_debug_tap.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, vp, f32p, C.c_size_t, C.POINTER(C.c_int64), vp]
+    lib.gnv_debug_cluster_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_decode_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_inference_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     for name in SYMBOLS:

@@ -231,6 +231,7 @@ ConvTc2Options tc2_options_from_env() {
   if (const char* v = getenv("GONOVA_TC2_MH")) o.mh = atoi(v);
   if (const char* v = getenv("GONOVA_TC2_CTAS")) o.max_ctas = atoi(v);
   if (const char* v = getenv("GONOVA_TC2_WGROUP")) o.w_group = atoi(v);
+  if (const char* v = getenv("GONOVA_TC2_CTA2")) o.cta2 = atoi(v);
   if (o.slab_mode < 0 || o.slab_mode > 2) o.slab_mode = 1;
   if (o.max_ctas < 1) o.max_ctas = 148;
   return o;
@@ -1118,6 +1119,15 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
   if ((size_t)B * L * C > out_capacity_elems) return fail(h, "tap output buffer too small");
   out_shape3[0] = B; out_shape3[1] = C; out_shape3[2] = L;
   GNV_CK(h, "tap", launch_nlc_to_nct(src, B, L, C, Cld ? Cld : C, 4, out_nct, (cudaStream_t)stream));
+  return 0;
+}
+
+int gnv_debug_cluster_probe(int smem_bytes, int grid, int* max_clusters) {
+  if (!max_clusters) return fail(nullptr, "NULL argument");
+  cudaError_t ce = conv_tc2_init();
+  if (ce != cudaSuccess) return fail_cuda(nullptr, "conv_tc2_init", ce);
+  const char* e = conv_tc2_cluster_probe(smem_bytes, grid, max_clusters);
+  if (*e) return fail(nullptr, std::string("cluster probe: ") + e);
   return 0;
 }
 

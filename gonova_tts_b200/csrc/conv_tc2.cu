@@ -15,10 +15,30 @@ cudaError_t conv_tc2_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kMaxDynSmem2);
+  e = cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_tc2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+  e = cudaFuncSetAttribute(conv_tc2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_tc2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+}
+
+// Diagnostics: how many 2-CTA clusters of conv_tc2_kernel<bf16> can be resident with `smem_bytes` of dynamic
+// shared memory per CTA (0 or an error text means cluster launches of that configuration are refused).
+const char* conv_tc2_cluster_probe(int smem_bytes, int grid, int* max_clusters) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  *max_clusters = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(max_clusters, conv_tc2_kernel<__nv_bfloat16, true>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
+  return "";
 }
 
 namespace {
@@ -82,23 +102,42 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   p.block_n = block_n;
   p.n_tiles_n = g.N_total / block_n;
 
+  // ---- CTA pairs (tcgen05.mma.cta_group::2): M = 256 across two SMs, each CTA stages half of every weight tile.
+  // Halves the weight traffic L2 -> SMEM and the B-operand shared-memory reads per MMA; worth it where the
+  // layer is tensor / operand-feed bound (N >= 128) and there are enough tiles to fill 74 pairs twice.
+  bool cta2 = false;
+  if (!transposed && block_n >= 128 && opt.cta2 != 0) {
+    const long pair_tiles = (long)g.B * ((g.M_rows + 255) / 256) * p.n_tiles_n;
+    // measured (B=64, T=500, bf16): pairs win on tensor-bound layers (N = 256: +13 %; N = 128 with K >= 896 and no
+    // residual traffic: +10 %) and lose 5-10 % on the HBM-bound ones (N = 128 conv2 / k = 3, source_downs)
+    const bool tensor_bound = block_n >= 256 || (g.n_taps * g.C_in >= 896 && !ep.res && !ep.raw_accum);
+    cta2 = opt.cta2 == 1 || (pair_tiles >= 2L * (opt.max_ctas / 2) && tensor_bound);
+  }
+  p.cta2 = cta2 ? 1 : 0;
+
   // ---- M tiling: two 128-row accumulators per tile when they fit TMEM twice and there is enough work ----
   int mh = opt.mh;
   if (mh != 1 && mh != 2) {
     mh = block_n <= 128 ? 2 : 1;
     const long tiles2 = (long)g.B * ((g.M_rows + 255) / 256) * p.n_tiles_n;
     if (tiles2 < 2L * opt.max_ctas) mh = 1;
+    if (cta2) {
+      const long tiles4 = (long)g.B * ((g.M_rows + 511) / 512) * p.n_tiles_n;
+      if (tiles4 < 2L * (opt.max_ctas / 2)) mh = 1;
+    }
   }
   if (mh * block_n > 512) mh = 1;
   p.mh = mh;
-  p.tiles_m = (g.M_rows + 128 * mh - 1) / (128 * mh);
+  const int rows_tile = 128 * mh * (cta2 ? 2 : 1);
+  p.tiles_m = (g.M_rows + rows_tile - 1) / rows_tile;
   p.total_tiles = g.B * p.tiles_m * p.n_tiles_n;
   p.acc_bufs = std::min(2, 512 / (mh * block_n));
   int cols = 32;
   while (cols < p.acc_bufs * mh * block_n) cols <<= 1;
   p.tmem_cols = cols;
   const uint32_t fmt = elem_bytes == 2 ? 1u : 2u;   // BF16 : TF32
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
+            (((cta2 ? 256u : 128u) >> 4) << 24);
 
   // ---- A slabs ----
   int tmin = 0, tmax = 0;
@@ -129,7 +168,7 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
     if (p.a_box_rows > 256) return "conv_tc2: A slab taller than two TMA boxes";
   }
   p.slab_bytes = (int)up1024((uint32_t)(p.a_n_boxes * p.a_box_rows) * 128u);
-  p.w_bytes = block_n * 128;
+  p.w_bytes = (cta2 ? block_n / 2 : block_n) * 128;      // CTA pair: this CTA's half of the weight tile
   p.w_group = std::max(1, std::min(4, 32768 / p.w_bytes));
   if (opt.w_group > 0) p.w_group = std::min(opt.w_group, 4);
   p.w_slot_bytes = p.w_group * p.w_bytes;
@@ -199,7 +238,7 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
     const int K = g.n_taps * g.C_in_ld;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)w_rows_alloc};
     cuuint64_t strides[1] = {(cuuint64_t)K * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)(cta2 ? block_n / 2 : block_n)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&out->maps.W, dt, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -231,6 +270,7 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
     }
   }
   out->grid = std::max(1, std::min(p.total_tiles, opt.max_ctas));
+  if (cta2) out->grid = 2 * std::max(1, std::min(p.total_tiles, opt.max_ctas / 2));
   out->elem_bytes = elem_bytes;
   return "";
 }
@@ -239,11 +279,29 @@ cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStre
   if (!L.d_maps) return cudaErrorInvalidValue;
   ConvTc2Params p = L.p;
   p.ep.lengths = lengths;
-  if (L.elem_bytes == 2)
-    conv_tc2_kernel<__nv_bfloat16><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-  else
-    conv_tc2_kernel<float><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-  return cudaGetLastError();
+  if (!p.cta2) {
+    if (L.elem_bytes == 2)
+      conv_tc2_kernel<__nv_bfloat16, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
+    else
+      conv_tc2_kernel<float, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
+    return cudaGetLastError();
+  }
+  // CTA pairs: cluster of two (an explicit 1x1x1 cluster attribute is refused for this kernel on driver 580)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = L.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const ConvTc2Maps* dm = L.d_maps;
+  if (L.elem_bytes == 2) return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__nv_bfloat16, true>, dm, p);
+  return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<float, true>, dm, p);
 }
 
 }  // namespace gnv

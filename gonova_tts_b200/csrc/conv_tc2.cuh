@@ -43,6 +43,8 @@ struct ConvTc2Params {
   int n_taps, n_chunks;
   int block_n, n_tiles_n, mh, tiles_m, total_tiles;
   int transposed;                  // epilogue tensor maps are per phase (= n tile), columns start at 0
+  int cta2;                        // 1: CTA pairs (cluster of 2): tcgen05.mma.cta_group::2, M = 256 across the pair,
+                                   // each CTA stages its own 128*mh rows of A and HALF of every weight tile
   int row_adj[kMaxPhase];          // transposed: TMA row coordinate = m - row_adj[phase]
   // A slabs: slab s of a channel block covers taps [slab_tap0[s], slab_tap0[s+1]) and holds
   // a_n_boxes * a_box_rows rows starting at tile row m0 + slab_row0[s]; tap j reads tile rows m0 + tap_row[j] ...
@@ -124,6 +126,57 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 }
 __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) helpers -------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <typename E>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  const uint32_t z = 0u;
+  if constexpr (sizeof(E) == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(z)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(z)
+        : "memory");
+  }
+}
+// commit of a CTA pair's MMAs: arrives on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
 }
 
 struct Ring {
@@ -290,7 +343,9 @@ __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab,
                                        bool live0);
 }  // namespace tc2
 
-template <typename E>
+// CTA2 = true: CTA pairs (cluster of two).  A separate instantiation, because a kernel image that contains
+// cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
+template <typename E, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ ConvTc2Params p) {
   using namespace tc2;
@@ -313,6 +368,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KBE = KBLK_BYTES / (int)sizeof(E);
+  const int crank = CTA2 ? (int)cluster_ctarank() : 0;     // rank inside the CTA pair; 0 = leader (issues the MMAs)
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first tile / tile stride of this CTA (pair)
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == kWarpProducer && lane == 0) {
     prefetch_tmap(&maps.A);
@@ -323,17 +381,24 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_acc_full + 8u * s, 1);
-      mbar_init(b_acc_empty + 8u * s, 4 * p.n_epi_wg);
+      mbar_init(b_acc_empty + 8u * s, 4 * p.n_epi_wg * (CTA2 ? 2 : 1));   // pair: both CTAs' epilogues arrive on the leader
       mbar_init(b_in_full + 8u * s, 1);
       mbar_init(b_in_empty + 8u * s, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpTmem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   // per-channel epilogue tables: bias, then (alpha, 1/(alpha + 1e-9)) per fused activation
   {
@@ -349,43 +414,59 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / TMA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int rows_per_tile = BLOCK_M * p.mh;
+  const int rows_per_cta = BLOCK_M * p.mh;
+  const int rows_per_tile = rows_per_cta * (CTA2 ? 2 : 1);   // a CTA pair's tile: the leader's rows, then the peer's
   const int n_epi_chunks = p.block_n / kEpiCols;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
       // ===== TMA producer: A slabs and W tile groups, in the order the MMA issuer consumes them =====
       Ring ra, rw;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step) {
         int q = t;
         const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
         const int m_tile = q % p.tiles_m;
         const int b = q / p.tiles_m;
         // polyphase tiles start at the phase's first valid GEMM row (row_adj), so that every TMA store
         // coordinate is non-negative
-        const int m0 = m_tile * rows_per_tile + (p.transposed ? p.row_adj[n_tile] : 0), n0 = n_tile * p.block_n;
+        const int m0 = m_tile * rows_per_tile + crank * rows_per_cta + (p.transposed ? p.row_adj[n_tile] : 0), n0 = n_tile * p.block_n;
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int s = 0; s < p.n_slabs; ++s) {
             mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
             const uint32_t dst = sA + ra.slot * p.slab_bytes;
             // a TMA box holds at most 256 rows: taller slabs arrive as two boxes of a_box_rows rows
-            mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES);
+            // CTA pair: both CTAs' loads complete on the LEADER's barrier, which expects both byte counts
+            const uint32_t a_bytes = (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES;
+            if (crank == 0) mbar_expect_tx(b_a_full + 8u * ra.slot, CTA2 ? 2u * a_bytes : a_bytes);
             const int r0 = m0 + p.slab_row0[s];
-            for (int bx = 0; bx < p.a_n_boxes; ++bx)
-              tma_load_3d(&maps.A, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
-                          r0 + bx * p.a_box_rows, b);
+            for (int bx = 0; bx < p.a_n_boxes; ++bx) {
+              if constexpr (CTA2)
+                tma_load_3d_2sm(&maps.A, (b_a_full + 8u * ra.slot) & kPeerBitMask,
+                                dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
+              else
+                tma_load_3d(&maps.A, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
+                            r0 + bx * p.a_box_rows, b);
+            }
             ra.advance(p.sa);
             // weight tiles travel in groups of up to w_group taps per barrier (fewer waits for small tiles)
             for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; tap += p.w_group) {
               const int ng = min(p.w_group, p.slab_tap0[s + 1] - tap);
               mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
-              mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes));
-              for (int g = 0; g < ng; ++g)
-                tma_load_2d(&maps.W, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
-                            ((tap + g) * p.n_chunks + ch) * KBE, n0);
+              // CTA pair: w_bytes is this CTA's HALF of the weight tile (rows n0 + crank*block_n/2 ...)
+              if (crank == 0) mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes) * (CTA2 ? 2u : 1u));
+              for (int g = 0; g < ng; ++g) {
+                if constexpr (CTA2)
+                  tma_load_2d_2sm(&maps.W, (b_w_full + 8u * rw.slot) & kPeerBitMask,
+                                  sW + rw.slot * p.w_slot_bytes + g * p.w_bytes, ((tap + g) * p.n_chunks + ch) * KBE,
+                                  n0 + crank * (p.block_n >> 1));
+                else
+                  tma_load_2d(&maps.W, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                              ((tap + g) * p.n_chunks + ch) * KBE, n0);
+              }
               rw.advance(p.sw);
             }
           }
@@ -393,12 +474,12 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (CTA pair: the leader issues for both CTAs) =====
       // Descriptors are built once; per MMA only the 14-bit start-address field moves (low word add).
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW);
       Ring ra, rw, racc;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step) {
         mbar_wait(b_acc_empty + 8u * racc.slot, racc.phase ^ 1u, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc0 = tmem_base + (uint32_t)(racc.slot * p.mh * p.block_n);
@@ -418,20 +499,26 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
                   uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
                   if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
                   const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
-                  umma<E>(acc, ad, bd, p.idesc, accum);
+                  if constexpr (CTA2) {
+                    umma_2sm<E>(acc, ad, bd, p.idesc, accum);
 #pragma unroll
-                  for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                    for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                  } else {
+                    umma<E>(acc, ad, bd, p.idesc, accum);
+#pragma unroll
+                    for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                  }
                 }
                 accum = 1u;
               }
-              umma_commit(b_w_empty + 8u * rw.slot);
+              if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
               rw.advance(p.sw);
             }
-            umma_commit(b_a_empty + 8u * ra.slot);
+            if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
             ra.advance(p.sa);
           }
         }
-        umma_commit(b_acc_full + 8u * racc.slot);
+        if constexpr (CTA2) umma_commit_2sm(b_acc_full + 8u * racc.slot); else umma_commit(b_acc_full + 8u * racc.slot);
         racc.advance(p.acc_bufs);
       }
     }
@@ -443,7 +530,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       uint32_t slot_phase[2] = {0u, 0u};
       int seq = 0;
       const int n_items = p.mh * n_epi_chunks;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step) {
         int q = t;
         const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
         const int m_tile = q % p.tiles_m;
@@ -453,7 +540,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int cbase = p.transposed ? 0 : n0;
         for (int item = 0; item < n_items; ++item, ++seq) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
-          const int mrow = m_tile * rows_per_tile + h * BLOCK_M;      // TMA row coordinate (GEMM row - row_adj)
+          const int mrow = m_tile * rows_per_tile + crank * rows_per_cta + h * BLOCK_M;   // TMA row coordinate (GEMM row - row_adj)
           const int slot = p.n_epi_wg == 2 ? (item & 1) : (seq & 1);
           mbar_wait(b_in_empty + 8u * slot, slot_phase[slot] ^ 1u, 3);
           mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
@@ -484,13 +571,13 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty;
     ectx.obase_wg = obase_wg; ectx.out_stride = out_stride; ectx.wg = wg; ectx.erow = erow; ectx.lane = lane;
     ectx.elected = elected;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = tile0; t < p.total_tiles; t += tile_step) {
       int qq = t;
       const int n_tile = qq % p.n_tiles_n; qq /= p.n_tiles_n;
       const int m_tile = qq % p.tiles_m;
       const int b = qq / p.tiles_m;
       const int ph = p.transposed ? n_tile : 0;
-      const int m0 = m_tile * rows_per_tile + (p.transposed ? p.row_adj[ph] : 0), n0 = n_tile * p.block_n;
+      const int m0 = m_tile * rows_per_tile + crank * rows_per_cta + (p.transposed ? p.row_adj[ph] : 0), n0 = n_tile * p.block_n;
       const int cbase = p.transposed ? 0 : n0;           // channel of the tile's first column
       int valid_rows = p.ep.L_out;
       if (p.ep.lengths) {
@@ -505,7 +592,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int p0 = m * p.ep.up + (p.transposed ? n_tile : 0) - p.ep.pad_out;
         const int row = p0 + p.ep.shift;
         const bool live = (m < p.M_rows) && (p0 >= 0) && (p0 < p.ep.L_store) && (row < valid_rows);
-        const int mrow = m_tile * rows_per_tile + h * BLOCK_M;
+        const int mrow = m_tile * rows_per_tile + crank * rows_per_cta + h * BLOCK_M;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                               (uint32_t)((racc.slot * p.mh + h) * p.block_n);
         float v[32];
@@ -534,16 +621,24 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       // accumulator drained: hand the TMEM buffer back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_acc_empty + 8u * racc.slot);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster((b_acc_empty + 8u * racc.slot) & kPeerBitMask);   // the leader's issuer waits for both CTAs
+        else mbar_arrive(b_acc_empty + 8u * racc.slot);
+      }
       racc.advance(p.acc_bufs);
     }
     if (elected) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();          // the peer may still be the target of multicast commits / remote arrives
   if (warp == kWarpTmem) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -586,6 +681,7 @@ struct ConvTc2Options {
   int slab_mode = 1;     // 0: one slab per tap; 1: one slab per channel block, taps by descriptor row offset (base_offset 0 — measured correct); 2: same with base_offset set (measured WRONG on B200, kept for the record)
   int mh = 0;            // 0 = choose
   int w_group = 0;       // 0 = choose (taps per weight barrier)
+  int cta2 = -1;         // CTA pairs: -1 = choose, 0 = never, 1 = whenever the layer allows it
   int max_ctas = 148;
 };
 
@@ -595,5 +691,6 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
                                  const ConvGeom& g, const EpiParams& ep, int c_pitch_out, const ConvTc2Options& opt);
 cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStream_t st);
 cudaError_t conv_tc2_init();
+const char* conv_tc2_cluster_probe(int smem_bytes, int grid, int* max_clusters);
 
 }  // namespace gnv

@@ -145,6 +145,9 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed,
 int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace, float* out_nct,
                   size_t out_capacity_elems, int64_t* out_shape3, void* stream);
 
+/* diagnostics: resident 2-CTA clusters of the persistent conv kernel for a dynamic shared-memory size */
+int gnv_debug_cluster_probe(int smem_bytes, int grid, int* max_clusters);
+
 /* number of kernel launches one gnv_decode / gnv_inference (B, T) issues (bench.py's gpu_launches) */
 int gnv_decode_launches(gnv_handle h, int B, int T, int* out);
 int gnv_inference_launches(gnv_handle h, int B, int T, int* out);
