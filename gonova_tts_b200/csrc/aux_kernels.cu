@@ -1,6 +1,9 @@
 // Bandwidth-bound kernels of the decoder: layout packers, f0 head, NSF source, STFT, iSTFT +
 // overlap-add, and the streaming PCM tail.  All are HBM-bound byte movers: coalesced, vectorised,
 // staged through shared memory where a thread's natural access would be strided.
+#include <cmath>
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -175,7 +178,10 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
     if (t >= T) break;
     const size_t n = (size_t)t * kSPF + j;
     const float f = f0_s[fi];
-    const double base = base_s[fi] + (double)(j + 1) * ((double)f / 24000.0);
+    // running phase of the fundamental in cycles, reduced mod 1 in fp64 once; each harmonic's phase is then
+    // (h+1) * frac in fp32 ((h+1)*frac <= 9: error <= 5e-7 cycles = 3e-6 rad, times the 0.1 sine amplitude)
+    const double based = base_s[fi] + (double)(j + 1) * ((double)f / 24000.0);
+    const float bfrac = (float)(based - floor(based));
     const float uv = f > 10.f ? 1.f : 0.f;
     const float namp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
     float nz[12];
@@ -187,17 +193,18 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
                       (uint32_t)(seed >> 32), r);
         const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
         float s0, c0, s1, c1;
-        __sincosf(6.2831853f * u01(r[1]), &s0, &c0);
-        __sincosf(6.2831853f * u01(r[3]), &s1, &c1);
+        __sincosf(6.2831853f * u01(r[1]) - 3.14159265f, &s0, &c0);     // argument in (-pi, pi]: MUFU accuracy range
+        __sincosf(6.2831853f * u01(r[3]) - 3.14159265f, &s1, &c1);
         nz[4 * g + 0] = r0 * c0; nz[4 * g + 1] = r0 * s0; nz[4 * g + 2] = r1 * c1; nz[4 * g + 3] = r1 * s1;
       }
     }
     float acc = lb;
 #pragma unroll
     for (int h = 0; h < 9; ++h) {
-      const double hp = (double)(h + 1) * base;
-      const float frac = (float)(hp - floor(hp));
-      const float sw = 0.1f * sinf(6.283185307179586f * frac + phi_s[h]);
+      const float x = (float)(h + 1) * bfrac;
+      float t = (x - floorf(x)) + phi_s[h] * 0.15915494309189535f;      // cycles; |phi| <= pi
+      t -= rintf(t);                                                    // (-0.5, 0.5]
+      const float sw = 0.1f * __sinf(6.283185307179586f * t);           // |arg| <= pi: abs error ~ 2^-21
       const float nv = noise ? noise[((size_t)b * 9 + h) * L + n] : nz[h];
       acc = fmaf(lw_s[h], sw * uv + namp * nv, acc);
     }
@@ -218,6 +225,43 @@ cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const fl
 // ------------------------------------------------------------------------------------------------
 constexpr int kStftFrames = 256;
 
+// Windowed DFT bases of the 16-point transforms, filled once per device by init_dft_tables():
+//   STFT : cw[k][n] = w[n] cos(2 pi k n / 16),  sw[k][n] = -w[n] sin(2 pi k n / 16)          (periodic Hann w)
+//   iSTFT: cb[k][n] = w[n] c_k cos(2 pi k n / 16) / 16,  sb[k][n] = -w[n] c_k sin(...) / 16 (c_k = 1 for DC/Nyquist, else 2;
+//          the imaginary parts of DC and Nyquist are ignored, as cuFFT C2R does),  w2[n] = w[n]^2
+__constant__ float c_stft_cw[9][16], c_stft_sw[9][16];
+__constant__ float c_istft_cb[9][16], c_istft_sb[9][16], c_istft_w2[16];
+
+static cudaError_t init_dft_tables() {
+  static std::mutex mu;
+  static unsigned long long done_mask = 0ull;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 64 && (done_mask >> dev) & 1ull) return cudaSuccess;
+  float cw[9][16], sw[9][16], cb[9][16], sb[9][16], w2[16];
+  const double pi = 3.14159265358979323846;
+  for (int k = 0; k < 9; ++k)
+    for (int n = 0; n < 16; ++n) {
+      const double win = 0.5 - 0.5 * cos(2.0 * pi * n / 16.0);
+      const double ang = 2.0 * pi * ((k * n) % 16) / 16.0;
+      const double ck = (k == 0 || k == 8) ? 1.0 : 2.0;
+      cw[k][n] = (float)(win * cos(ang));
+      sw[k][n] = (float)(-win * sin(ang));
+      cb[k][n] = (float)(win * ck * cos(ang) / 16.0);
+      sb[k][n] = (k == 0 || k == 8) ? 0.f : (float)(-win * ck * sin(ang) / 16.0);
+      if (k == 0) w2[n] = (float)(win * win);
+    }
+  if ((e = cudaMemcpyToSymbol(c_stft_cw, cw, sizeof(cw))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_stft_sw, sw, sizeof(sw))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_istft_cb, cb, sizeof(cb))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_istft_sb, sb, sizeof(sb))) != cudaSuccess) return e;
+  if ((e = cudaMemcpyToSymbol(c_istft_w2, w2, sizeof(w2))) != cudaSuccess) return e;
+  if (dev < 64) done_mask |= 1ull << dev;
+  return cudaSuccess;
+}
+
 // Output rows: [front zero rows | F frames | back zero rows] = total_rows rows of C_ld elements of E
 // (channels >= 18 are zero).  The padding rows are what lets the strided source_downs convs read their
 // conv padding (and the K padding of the GEMM view) as plain zeros.
@@ -225,21 +269,13 @@ template <typename E>
 __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restrict__ s, int L,
                                                            const int* __restrict__ lengths, E* __restrict__ spec,
                                                            int C_ld, int front, int total_rows, int round) {
-  __shared__ float x_s[kStftFrames * 4 + 12];
-  __shared__ float cw[9][16], sw[9][16];
-  __shared__ float out_s[kStftFrames * 24];
+  __shared__ __align__(16) float x_s[kStftFrames * 4 + 12];
+  __shared__ float out_s[kStftFrames * 25];                    // odd pitch (C_ld + 1): conflict-free staging
   const int b = blockIdx.y, rb = blockIdx.x * kStftFrames;     // first output row of this block
   const int fb = rb - front;                                   // its frame index (may be negative)
   const int Lb = lengths ? min(L, lengths[b] * kSPF) : L;      // this utterance's samples
   const int Fb = Lb / 4 + 1;
   const float* sb = s + (size_t)b * L;
-  for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
-    const int k = i / 16, n = i % 16;
-    const float win = 0.5f - 0.5f * cospif((float)n / 8.f);
-    const float ang = (float)((k * n) % 16) / 8.f;            // exact argument reduction
-    cw[k][n] = win * cospif(ang);
-    sw[k][n] = -win * sinpif(ang);
-  }
   for (int i = threadIdx.x; i < kStftFrames * 4 + 12; i += blockDim.x) {
     int idx = fb * 4 - 8 + i;
     if (idx < 0 && idx >= -8) idx = -idx;
@@ -250,25 +286,30 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
   const int f = fb + threadIdx.x;
   float x[16];
 #pragma unroll
-  for (int n = 0; n < 16; ++n) x[n] = x_s[threadIdx.x * 4 + n];
+  for (int q = 0; q < 4; ++q) {
+    const float4 v4 = *reinterpret_cast<const float4*>(&x_s[threadIdx.x * 4 + 4 * q]);
+    x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
+  }
   const bool live = f >= 0 && f < Fb;
+  const int SP = C_ld + 1;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     float re = 0.f, im = 0.f;
 #pragma unroll
     for (int n = 0; n < 16; ++n) {
-      re = fmaf(x[n], cw[k][n], re);
-      im = fmaf(x[n], sw[k][n], im);
+      re = fmaf(x[n], c_stft_cw[k][n], re);
+      im = fmaf(x[n], c_stft_sw[k][n], im);
     }
-    out_s[threadIdx.x * C_ld + k] = live ? re : 0.f;
-    out_s[threadIdx.x * C_ld + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
+    out_s[threadIdx.x * SP + k] = live ? re : 0.f;
+    out_s[threadIdx.x * SP + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
   }
-  for (int c = 18; c < C_ld; ++c) out_s[threadIdx.x * C_ld + c] = 0.f;
+  for (int c = 18; c < C_ld; ++c) out_s[threadIdx.x * SP + c] = 0.f;
   __syncthreads();
   const int nr = min(kStftFrames, total_rows - rb);
   E* ob = spec + ((size_t)b * total_rows + rb) * C_ld;
   for (int i = threadIdx.x; i < nr * C_ld; i += blockDim.x) {
-    float v = out_s[i];
+    const int ri = i / C_ld;
+    float v = out_s[ri * SP + (i - ri * C_ld)];
     if constexpr (sizeof(E) == 4) { if (round) v = round_tf32(v); }
     ElemIO<E>::store(ob + i, v);
   }
@@ -277,6 +318,7 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
 cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, void* spec_nlc, int elem_bytes, int round,
                         int C_ld, int front_rows, int total_rows, cudaStream_t st) {
   if (C_ld < 18 || C_ld > 24 || front_rows < 0 || total_rows < front_rows + L / 4 + 1) return cudaErrorInvalidValue;
+  if (cudaError_t e = init_dft_tables()) return e;
   dim3 grid((total_rows + kStftFrames - 1) / kStftFrames, B);
   if (elem_bytes == 2)
     stft_kernel<__nv_bfloat16><<<grid, kStftFrames, 0, st>>>(s, L, lengths, (__nv_bfloat16*)spec_nlc, C_ld, front_rows,
@@ -298,30 +340,25 @@ constexpr int kIstftNew = kIstftThreads - 3;
 __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __restrict__ x, int F, int C_ld,
                                                               const int* __restrict__ lengths, float limit,
                                                               float* __restrict__ wav) {
-  __shared__ float xin[kIstftThreads * 20];             // rows of C_ld (18 or 20) floats
+  __shared__ float xin[kIstftThreads * 19];             // 18 used floats per frame, odd pitch: no bank conflicts
   __shared__ float fr[kIstftThreads][17];
-  __shared__ float cb[9][16], sb[9][16], w2[16];
   const int b = blockIdx.y;
   const int L = 4 * (F - 1);
   const int Fb = lengths ? min(F, lengths[b] * (kSPF / 4) + 1) : F;
   const int Lb = 4 * (Fb - 1);
   const int m0 = blockIdx.x * (kIstftNew * 4);
   const int fbase = m0 / 4 - 1;
-  for (int i = threadIdx.x; i < 9 * 16; i += blockDim.x) {
-    const int k = i / 16, n = i % 16;
-    const float win = 0.5f - 0.5f * cospif((float)n / 8.f);
-    const float ck = (k == 0 || k == 8) ? 1.f : 2.f;
-    const float ang = (float)((k * n) % 16) / 8.f;
-    cb[k][n] = win * ck * cospif(ang) * (1.f / 16.f);
-    sb[k][n] = (k == 0 || k == 8) ? 0.f : -win * ck * sinpif(ang) * (1.f / 16.f);
-    if (k == 0) w2[n] = win * win;
-  }
   {
     const long long lo = (long long)fbase * C_ld, total = (long long)F * C_ld;
     const float* xb = x + (size_t)b * F * C_ld;
-    for (int i = threadIdx.x; i < kIstftThreads * C_ld; i += blockDim.x) {
+    // flat, coalesced copy of 256 frames x C_ld floats; (frame, channel) tracked incrementally (256 % C_ld steps)
+    int fr_i = threadIdx.x / C_ld, k = threadIdx.x - fr_i * C_ld;
+    const int dfr = kIstftThreads / C_ld, dk = kIstftThreads - dfr * C_ld;
+    for (int i = threadIdx.x; i < kIstftThreads * C_ld; i += kIstftThreads) {
       const long long g = lo + i;
-      xin[i] = (g >= 0 && g < total) ? xb[g] : 0.f;
+      if (k < 18) xin[fr_i * 19 + k] = (g >= 0 && g < total) ? xb[g] : 0.f;
+      fr_i += dfr; k += dk;
+      if (k >= C_ld) { k -= C_ld; ++fr_i; }
     }
   }
   __syncthreads();
@@ -331,10 +368,10 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
     const bool live = f >= 0 && f < Fb;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      const float mag = fminf(expf(xin[threadIdx.x * C_ld + k]), 100.f);
-      const float ph = sinf(xin[threadIdx.x * C_ld + 9 + k]);
+      const float mag = fminf(expf(xin[threadIdx.x * 19 + k]), 100.f);
+      const float ph = sinf(xin[threadIdx.x * 19 + 9 + k]);
       float sn, cs;
-      sincosf(ph, &sn, &cs);
+      __sincosf(ph, &sn, &cs);                               // |ph| <= 1: MUFU abs error ~ 2^-21
       re[k] = live ? mag * cs : 0.f;
       im[k] = live ? mag * sn : 0.f;
     }
@@ -343,8 +380,8 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        acc = fmaf(re[k], cb[k][n], acc);
-        acc = fmaf(im[k], sb[k][n], acc);
+        acc = fmaf(re[k], c_istft_cb[k][n], acc);
+        acc = fmaf(im[k], c_istft_sb[k][n], acc);
       }
       fr[threadIdx.x][n] = acc;
     }
@@ -363,7 +400,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
           const int f = fhi - j;
           if (f >= 0 && f < Fb) {
             acc += fr[threadIdx.x + 3 - j][e + 4 * j];
-            env += w2[e + 4 * j];
+            env += c_istft_w2[e + 4 * j];
           }
         }
         float v = (m + e < Lb) ? acc / env : 0.f;
@@ -379,6 +416,7 @@ cudaError_t launch_istft(const float* x_nlc, int B, int F, int C_ld, const int* 
   const int L = 4 * (F - 1);
   if (L <= 0) return cudaSuccess;
   if (C_ld < 18 || C_ld > 20) return cudaErrorInvalidValue;
+  if (cudaError_t e = init_dft_tables()) return e;
   dim3 grid((L + kIstftNew * 4 - 1) / (kIstftNew * 4), B);
   istft_kernel<<<grid, kIstftThreads, 0, st>>>(x_nlc, F, C_ld, lengths, limit, wav);
   return cudaGetLastError();
