@@ -197,6 +197,8 @@ struct gnv_decoder {
   bool use_tc = true;
   int tc_version = 2;
   bool fuse_pairs = true;   // conv1 + Snake + conv2 + residual of a ResBlock step in one kernel
+  int pair_cta2 = 0;        // CTA pairs in the fused kernel: -1 = choose, 0 = never, 1 = always.  Off: measured 0.15-0.2 ms
+                            // SLOWER per C=64 pair (the leader must wait for both CTAs' epilogue 1 before conv2)
   int fuse_max_c = 64;      // ... for stages with at most this many channels.  Measured (B=64, T=500, bf16): C=64
                             // pairs are 5-28 % faster fused; C=128 pairs must drop to 128-row tiles to fit TMEM
                             // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
@@ -607,7 +609,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
           if (me.empty()) {
             const char* pe = make_conv_pair_launch(&op.pairl, h->eb, cur, R.c1[d].w, R.c2[d].w, B, Ls, R.c1[d].C_in,
                                                    R.c1[d].C_in_ld, R.c1[d].k, R.c1[d].dil, R.c1[d].bias, R.a2[d], snake,
-                                                   tmp_op.ep, h->tc2opt.max_ctas, h->tc2opt.mh);
+                                                   tmp_op.ep, h->tc2opt.max_ctas, h->tc2opt.mh, h->pair_cta2);
             if (!*pe) {
               op.tc = true; op.tcv = 3;
               op.g = tmp_op.g; op.ep = tmp_op.ep;
@@ -812,6 +814,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   h->tc2opt = tc2_options_from_env();
   if (const char* v = getenv("GONOVA_FUSE_PAIRS")) h->fuse_pairs = atoi(v) != 0;
   if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
+  if (const char* v = getenv("GONOVA_PAIR_CTA2")) h->pair_cta2 = atoi(v);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
   std::string err;

@@ -14,10 +14,13 @@ cudaError_t conv_pair_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_pair_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kMaxDynSmemPair);
+  e = cudaFuncSetAttribute(conv_pair_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_pair_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
+  e = cudaFuncSetAttribute(conv_pair_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_pair_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_pair_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
 }
 
 namespace {
@@ -41,7 +44,8 @@ const char* encode_rows_map(PFN_encodeTiled enc, CUtensorMap* m, const void* bas
 
 const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const void* x, const void* w1, const void* w2,
                                   int B, int L, int C, int C_ld, int k, int d1, const float* bias1,
-                                  const float* alpha_mid, int mid_kind, const EpiParams& ep, int max_ctas, int mh_opt) {
+                                  const float* alpha_mid, int mid_kind, const EpiParams& ep, int max_ctas, int mh_opt,
+                                  int cta2_opt) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
   const int kbe = 128 / elem_bytes;
@@ -71,10 +75,14 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   if (4 * mh * C > 512) return "conv_pair: accumulators do not fit TMEM";
   p.mh = mh;
   p.Mo = 128 * mh - (k - 1);
-  p.tiles_m = (L + p.Mo - 1) / p.Mo;
+  const int cta_tiles = (L + p.Mo - 1) / p.Mo;
+  // CTA pairs share every weight tile and halve the B-operand reads; they need enough tiles to fill 74 pairs
+  const bool cta2 = cta2_opt == 1 || (cta2_opt != 0 && (long)B * ((cta_tiles + 1) / 2) >= 2L * (max_ctas / 2));
+  p.cta2 = cta2 ? 1 : 0;
+  p.tiles_m = cta2 ? (cta_tiles + 1) / 2 : cta_tiles;
   p.total_tiles = B * p.tiles_m;
   const uint32_t fmt = elem_bytes == 2 ? 1u : 2u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | (((cta2 ? 256u : 128u) >> 4) << 24);
 
   const int slab_rows = 128 * mh + (k - 1) * d1;
   if (slab_rows <= 256) {
@@ -84,7 +92,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
     if (p.a_box_rows > 256) return "conv_pair: x slab taller than two TMA boxes";
   }
   p.slab_bytes = (int)up1024((uint32_t)(p.a_n_boxes * p.a_box_rows) * 128u);
-  p.w_bytes = C * 128;
+  p.w_bytes = (cta2 ? C / 2 : C) * 128;
   p.w_group = std::max(1, std::min(4, 32768 / p.w_bytes));
   p.w_slot_bytes = p.w_group * p.w_bytes;
   p.h_kb_bytes = 128 * mh * 128;
@@ -154,7 +162,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
     const int K = k * C;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)C};
     cuuint64_t strides[1] = {(cuuint64_t)K * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)C};
+    cuuint32_t box[2] = {(cuuint32_t)kbe, (cuuint32_t)(cta2 ? C / 2 : C)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(i == 0 ? &out->maps.W1 : &out->maps.W2, dt, 2, const_cast<void*>(i == 0 ? w1 : w2), dims, strides, box,
                      es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -175,7 +183,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
       if (*e) return e;
     }
   }
-  out->grid = std::max(1, std::min(p.total_tiles, max_ctas));
+  out->grid = cta2 ? 2 * std::max(1, std::min(p.total_tiles, max_ctas / 2)) : std::max(1, std::min(p.total_tiles, max_ctas));
   out->elem_bytes = elem_bytes;
   return "";
 }
@@ -184,11 +192,26 @@ cudaError_t launch_conv_pair(const ConvPairLaunch& L, const int* lengths, cudaSt
   if (!L.d_maps) return cudaErrorInvalidValue;
   ConvPairParams p = L.p;
   p.ep.lengths = lengths;
-  if (L.elem_bytes == 2)
-    conv_pair_kernel<__nv_bfloat16><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-  else
-    conv_pair_kernel<float><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-  return cudaGetLastError();
+  if (!p.cta2) {
+    if (L.elem_bytes == 2)
+      conv_pair_kernel<__nv_bfloat16, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
+    else
+      conv_pair_kernel<float, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = L.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const ConvPairMaps* dm = L.d_maps;
+  if (L.elem_bytes == 2) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<__nv_bfloat16, true>, dm, p);
+  return cudaLaunchKernelEx(&cfg, conv_pair_kernel<float, true>, dm, p);
 }
 
 }  // namespace gnv

@@ -35,6 +35,7 @@ struct ConvPairParams {
   int w_bytes;                     // one weight tile: C rows x 128 B
   int w_group, w_slot_bytes;       // taps per weight barrier / ring slot
   int sa, sw, n_epi_wg, out_bufs;
+  int cta2;                        // CTA pairs: tiles_m / total_tiles then count PAIRS of CTA tiles
   uint32_t idesc;
   int n_in, has_raw, n_act, act_bytes, c_tab;
   int mid_kind;                    // activation between the two convs (ACT_SNAKE_FAST | ACT_SNAKE)
@@ -51,7 +52,10 @@ struct ConvPairMaps {
 
 #ifdef __CUDACC__
 
-template <typename E>
+// CTA2 = true: CTA pairs (cluster of two, tcgen05.mma.cta_group::2): the two CTAs work on ADJACENT tiles of the same
+// utterance, each with its own x slab, h slab, accumulators and epilogues; they share every weight tile (each stages
+// half of its rows), and the leader's MMA thread issues both CTAs' MMAs (M = 256 across the pair).
+template <typename E, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant__ ConvPairParams p) {
   using namespace tc2;
@@ -78,6 +82,9 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int KBE = KBLK_BYTES / (int)sizeof(E);
+  constexpr int kSub = CTA2 ? 2 : 1;                               // CTA tiles per scheduled tile
+  const int crank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
   if (warp == kWarpProducer && lane == 0) {
     prefetch_tmap(&maps.X);
@@ -89,20 +96,26 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     for (int s = 0; s < p.sw; ++s) { mbar_init(b_w_full + 8u * s, 1); mbar_init(b_w_empty + 8u * s, 1); }
     mbar_init(b_acc1_full, 1);
     mbar_init(b_acc1_full + 8u, 1);
-    mbar_init(b_e1_done, 4 * p.n_epi_wg);
+    mbar_init(b_e1_done, 4 * p.n_epi_wg * kSub);                 // pair: both CTAs' epilogues arrive on the leader
     mbar_init(b_h_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_acc2_full + 8u * s, 1);
-      mbar_init(b_acc2_empty + 8u * s, 4 * p.n_epi_wg);
+      mbar_init(b_acc2_empty + 8u * s, 4 * p.n_epi_wg * kSub);
       mbar_init(b_in_full + 8u * s, 1);
       mbar_init(b_in_empty + 8u * s, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kWarpTmem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   {
     const int C = p.C;
@@ -121,13 +134,14 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
   // TMEM columns: acc1 buffers at 0 and mh*C, acc2 buffers at 2*mh*C and 3*mh*C
   const uint32_t acc2_col0 = (uint32_t)(2 * p.mh * p.C);
 
   const int n_epi_chunks = p.C / kEpiCols;
-  const int G = gridDim.x;
+  const int G = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // tile stride of this CTA (pair)
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
@@ -137,23 +151,34 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int tap = 0; tap < p.k; tap += p.w_group) {
           const int ng = min(p.w_group, p.k - tap);
           mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
-          mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes));
-          for (int g = 0; g < ng; ++g)
-            tma_load_2d(wm, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
-                        ((tap + g) * p.n_chunks + ch) * KBE, 0);
+          if (crank == 0) mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes) * kSub);
+          for (int g = 0; g < ng; ++g) {
+            if constexpr (CTA2)   // this CTA's half of the weight rows, completing on the leader's barrier
+              tma_load_2d_2sm(wm, (b_w_full + 8u * rw.slot) & kPeerBitMask, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                              ((tap + g) * p.n_chunks + ch) * KBE, crank * (p.C >> 1));
+            else
+              tma_load_2d(wm, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                          ((tap + g) * p.n_chunks + ch) * KBE, 0);
+          }
           rw.advance(p.sw);
         }
       };
       auto load_m1 = [&](int t) {
-        const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
+        const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
         const int r0 = m_tile * p.Mo - p.p2 - p.p1;                 // first x row of the slab
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
           const uint32_t dst = sA + ra.slot * p.slab_bytes;
-          mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES);
-          for (int bx = 0; bx < p.a_n_boxes; ++bx)
-            tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
-                        r0 + bx * p.a_box_rows, b);
+          if (crank == 0)
+            mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES * kSub);
+          for (int bx = 0; bx < p.a_n_boxes; ++bx) {
+            if constexpr (CTA2)
+              tma_load_3d_2sm(&maps.X, (b_a_full + 8u * ra.slot) & kPeerBitMask,
+                              dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
+            else
+              tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
+                          r0 + bx * p.a_box_rows, b);
+          }
           ra.advance(p.sa);
           load_w_groups(&maps.W1, ch);
         }
@@ -162,16 +187,16 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch) load_w_groups(&maps.W2, ch);
       };
       // the issuer runs conv1 two tiles ahead of conv2: M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...
-      if ((int)blockIdx.x < p.total_tiles) load_m1(blockIdx.x);
-      if ((int)blockIdx.x + G < p.total_tiles) load_m1(blockIdx.x + G);
-      for (int t = blockIdx.x; t < p.total_tiles; t += G) {
+      if (tile0 < p.total_tiles) load_m1(tile0);
+      if (tile0 + G < p.total_tiles) load_m1(tile0 + G);
+      for (int t = tile0; t < p.total_tiles; t += G) {
         load_m2();
         if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G);
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && crank == 0) {
+      // ===== MMA issuer (pair: the leader issues both CTAs' MMAs) =====
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW), h_desc0 = umma_desc_sw128(sH);
       Ring ra, rw;
       // one K block (channel block ch) of a conv: every tap group's weights against row-shifted views of `a_base`
@@ -186,13 +211,19 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
             for (int h = 0; h < p.mh; ++h) {
               const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
               const uint32_t acc = acc0 + (uint32_t)(h * p.C);
-              umma<E>(acc, ad, bd, p.idesc, accum);
+              if constexpr (CTA2) {
+                umma_2sm<E>(acc, ad, bd, p.idesc, accum);
 #pragma unroll
-              for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+              } else {
+                umma<E>(acc, ad, bd, p.idesc, accum);
+#pragma unroll
+                for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+              }
             }
             accum = 1u;
           }
-          umma_commit(b_w_empty + 8u * rw.slot);
+          if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
           rw.advance(p.sw);
         }
       };
@@ -202,10 +233,10 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
           issue_taps(a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4), p.d1,
                      tmem_base + (uint32_t)((j & 1) * p.mh * p.C), accum);
-          umma_commit(b_a_empty + 8u * ra.slot);
+          if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
           ra.advance(p.sa);
         }
-        umma_commit(b_acc1_full + 8u * (j & 1));
+        if constexpr (CTA2) umma_commit_2sm(b_acc1_full + 8u * (j & 1)); else umma_commit(b_acc1_full + 8u * (j & 1));
       };
       auto issue_m2 = [&](int i) {
         const int buf = i & 1;
@@ -214,13 +245,13 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch)
           issue_taps(h_desc0 + (uint64_t)((uint32_t)(ch * p.h_kb_bytes) >> 4), 1,
                      tmem_base + acc2_col0 + (uint32_t)(buf * p.mh * p.C), accum);
-        umma_commit(b_acc2_full + 8u * buf);
-        umma_commit(b_h_empty);
+        if constexpr (CTA2) umma_commit_2sm(b_acc2_full + 8u * buf); else umma_commit(b_acc2_full + 8u * buf);
+        if constexpr (CTA2) umma_commit_2sm(b_h_empty); else umma_commit(b_h_empty);
       };
-      if ((int)blockIdx.x < p.total_tiles) issue_m1(0);
-      if ((int)blockIdx.x + G < p.total_tiles) issue_m1(1);
+      if (tile0 < p.total_tiles) issue_m1(0);
+      if (tile0 + G < p.total_tiles) issue_m1(1);
       int i = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += G, ++i) {
+      for (int t = tile0; t < p.total_tiles; t += G, ++i) {
         mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);          // h slab of tile i is valid, acc1[i & 1] is free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_m2(i);
@@ -233,8 +264,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       uint32_t slot_phase[2] = {0u, 0u};
       int seq = 0;
       const int n_items = p.mh * n_epi_chunks;
-      for (int t = blockIdx.x; t < p.total_tiles; t += G) {
-        const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
+      for (int t = tile0; t < p.total_tiles; t += G) {
+        const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
         for (int item = 0; item < n_items; ++item, ++seq) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
           const int mrow = m_tile * p.Mo + h * BLOCK_M;
@@ -276,7 +307,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     };
     // E1: acc1 -> bias1 -> Snake -> E -> h slab (K-major SWIZZLE_128B operand layout)
     auto epilogue1 = [&](int t, int i) {
-      const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
+      const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
       const int g0 = m_tile * p.Mo - p.p2;                          // global row of h-slab row 0
       const int vr = valid_rows_of(b);
       mbar_wait(b_acc1_full + 8u * (i & 1), (uint32_t)((i >> 1) & 1), 4);
@@ -343,11 +374,13 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       fence_async_smem();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_e1_done);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster(b_e1_done & kPeerBitMask); else mbar_arrive(b_e1_done);
+      }
     };
     // E2: acc2 -> bias2 -> shared epilogue (residual, running sum, outputs)
     auto epilogue2 = [&](int t, int i) {
-      const int m_tile = t % p.tiles_m, b = t / p.tiles_m;
+      const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
       const int m0 = m_tile * p.Mo;
       const int vr = valid_rows_of(b);
       const int buf = i & 1;
@@ -373,10 +406,13 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_acc2_empty + 8u * buf);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_cluster((b_acc2_empty + 8u * buf) & kPeerBitMask);
+        else mbar_arrive(b_acc2_empty + 8u * buf);
+      }
     };
     int i = 0, prev = -1;
-    for (int t = blockIdx.x; t < p.total_tiles; t += G, ++i) {
+    for (int t = tile0; t < p.total_tiles; t += G, ++i) {
       epilogue1(t, i);
       if (prev >= 0) epilogue2(prev, i - 1);
       prev = t;
@@ -386,8 +422,12 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();
   if (warp == kWarpTmem) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -406,7 +446,8 @@ struct ConvPairLaunch {
 // res / raw / act_out tensors are [B, L, C]).  Returns "" or the reason the pair cannot be fused.
 const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const void* x, const void* w1, const void* w2,
                                   int B, int L, int C, int C_ld, int k, int d1, const float* bias1,
-                                  const float* alpha_mid, int mid_kind, const EpiParams& ep, int max_ctas, int mh_opt);
+                                  const float* alpha_mid, int mid_kind, const EpiParams& ep, int max_ctas, int mh_opt,
+                                  int cta2_opt);
 cudaError_t launch_conv_pair(const ConvPairLaunch& L, const int* lengths, cudaStream_t st);
 cudaError_t conv_pair_init();
 
