@@ -2,6 +2,7 @@
 #include "conv_pair.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace gnv {
@@ -79,6 +80,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   // CTA pairs share every weight tile and halve the B-operand reads; they need enough tiles to fill 74 pairs
   const bool cta2 = cta2_opt == 1 || (cta2_opt != 0 && (long)B * ((cta_tiles + 1) / 2) >= 2L * (max_ctas / 2));
   p.cta2 = cta2 ? 1 : 0;
+  p.mma_order = getenv("GONOVA_MMA_ORDER") ? atoi(getenv("GONOVA_MMA_ORDER")) : 0;
   p.tiles_m = cta2 ? (cta_tiles + 1) / 2 : cta_tiles;
   p.total_tiles = B * p.tiles_m;
   const uint32_t fmt = elem_bytes == 2 ? 1u : 2u;

@@ -36,6 +36,7 @@ struct ConvPairParams {
   int w_group, w_slot_bytes;       // taps per weight barrier / ring slot
   int sa, sw, n_epi_wg, out_bufs;
   int cta2;                        // CTA pairs: tiles_m / total_tiles then count PAIRS of CTA tiles
+  int mma_order;                   // 0: alternate the two accumulators per MMA, 1: four k-steps per accumulator in a row
   uint32_t idesc;
   int n_in, has_raw, n_act, act_bytes, c_tab;
   int mid_kind;                    // activation between the two convs (ACT_SNAKE_FAST | ACT_SNAKE)
@@ -208,17 +209,35 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           for (int g = 0; g < ng; ++g) {
             const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
             const uint64_t ad0 = a_base + (uint64_t)((uint32_t)((tap + g) * row_step) * (KBLK_BYTES >> 4));
-            for (int h = 0; h < p.mh; ++h) {
-              const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
-              const uint32_t acc = acc0 + (uint32_t)(h * p.C);
-              if constexpr (CTA2) {
-                umma_2sm<E>(acc, ad, bd, p.idesc, accum);
+            // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA never
+            // waits for the previous one's accumulate into the same TMEM tile (p.mma_order == 1 keeps the old order)
+            if (p.mma_order == 0 && p.mh == 2) {
+              const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
+              const uint32_t acc1 = acc0 + (uint32_t)p.C;
 #pragma unroll
-                for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
-              } else {
-                umma<E>(acc, ad, bd, p.idesc, accum);
+              for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
+                const uint32_t ac = kk == 0 ? accum : 1u;
+                if constexpr (CTA2) {
+                  umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                  umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                } else {
+                  umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                  umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                }
+              }
+            } else {
+              for (int h = 0; h < p.mh; ++h) {
+                const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
+                const uint32_t acc = acc0 + (uint32_t)(h * p.C);
+                if constexpr (CTA2) {
+                  umma_2sm<E>(acc, ad, bd, p.idesc, accum);
 #pragma unroll
-                for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                  for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                } else {
+                  umma<E>(acc, ad, bd, p.idesc, accum);
+#pragma unroll
+                  for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                }
               }
             }
             accum = 1u;

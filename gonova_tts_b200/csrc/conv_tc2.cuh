@@ -495,18 +495,37 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
               for (int g = 0; g < ng; ++g) {
                 const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
                 const uint64_t ad0 = a_slab + (uint64_t)((uint32_t)(p.tap_row[tap + g] - p.slab_row0[s]) * (KBLK_BYTES >> 4));
-                for (int h = 0; h < p.mh; ++h) {
-                  uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
-                  if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
-                  const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
-                  if constexpr (CTA2) {
-                    umma_2sm<E>(acc, ad, bd, p.idesc, accum);
+                if (p.mh == 2 && !p.a_base_offset_mode) {
+                  // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA
+                  // never queues behind the previous one's accumulate into the same TMEM tile (measured +11 % on
+                  // the N = 64 layers)
+                  const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
+                  const uint32_t acc1 = acc0 + (uint32_t)p.block_n;
 #pragma unroll
-                    for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
-                  } else {
-                    umma<E>(acc, ad, bd, p.idesc, accum);
+                  for (int k = 0; k < KBLK_BYTES / 32; ++k) {
+                    const uint32_t ac = k == 0 ? accum : 1u;
+                    if constexpr (CTA2) {
+                      umma_2sm<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
+                      umma_2sm<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                    } else {
+                      umma<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
+                      umma<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                    }
+                  }
+                } else {
+                  for (int h = 0; h < p.mh; ++h) {
+                    uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
+                    if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
+                    const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
+                    if constexpr (CTA2) {
+                      umma_2sm<E>(acc, ad, bd, p.idesc, accum);
 #pragma unroll
-                    for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                      for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                    } else {
+                      umma<E>(acc, ad, bd, p.idesc, accum);
+#pragma unroll
+                      for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                    }
                   }
                 }
                 accum = 1u;
