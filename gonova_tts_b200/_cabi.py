@@ -18,7 +18,7 @@ ACT = {"none": 0, "snake": 1, "lrelu": 2, "elu": 3, "snake_fast": 4}
 # every symbol include/gonova_hift.h declares
 SYMBOLS = [
     "gnv_create", "gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_workspace_bytes", "gnv_f0",
-    "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_stft", "gnv_istft", "gnv_conv1d",
+    "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_pcm_mulaw", "gnv_stft", "gnv_istft", "gnv_conv1d",
     "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
 ]
 
@@ -62,6 +62,7 @@ def load():
                                           C.c_char_p, C.POINTER(C.c_int)]
     lib.gnv_pcm_tail.argtypes = [f32p, C.c_int64, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_float, i16p, f32p,
                                  C.c_int64, vp]
+    lib.gnv_pcm_mulaw.argtypes = [i16p, C.c_int64, vp, vp]
     lib.gnv_stft.argtypes = [f32p, C.c_int, C.c_int, f32p, vp]
     lib.gnv_istft.argtypes = [f32p, C.c_int, C.c_int, C.c_float, f32p, vp]
     lib.gnv_conv1d.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int, f32p, C.c_int, C.c_int, C.c_int, f32p, f32p,

@@ -1,0 +1,119 @@
+"""Micro-batching of decode requests from many connections.
+
+The reference service runs ONE synthesis at a time: a single `_tts_worker` coroutine takes one request
+off a bounded queue and blocks on it (services/tts/server.py:110-186; queue of 500 with drop-on-full,
+services/tts/core/queue_manager.py:54-79, :157-171).  The decoder is far faster batched (B=1: 5 k x
+real time, B=64: 21 k x), so this collects the requests that arrive within a short window, pads them to
+one ragged batch (`lengths`), runs the decoder once and hands every caller its own slice.
+
+Host-side only: `decode_fn(mel [B,80,Tmax] float32 host tensor, lengths list[int]) -> wav [B, 480*Tmax]`
+is the only thing that touches the GPU (see `for_decoder`)."""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+from concurrent.futures import Future
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+SAMPLES_PER_FRAME = 480
+
+
+class MicroBatcher:
+    def __init__(self, decode_fn: Callable[[torch.Tensor, List[int]], torch.Tensor], max_batch: int = 64,
+                 max_wait_ms: float = 2.0, max_queue: int = 500):
+        if max_batch < 1 or max_queue < 1:
+            raise ValueError("max_batch and max_queue must be positive")
+        self._decode = decode_fn
+        self.max_batch, self.max_wait = max_batch, max_wait_ms / 1e3
+        self._q: "queue.Queue[Optional[Tuple[torch.Tensor, Future]]]" = queue.Queue(maxsize=max_queue)
+        self.metrics = {"requests": 0, "dropped": 0, "batches": 0, "frames": 0, "padded_frames": 0}
+        self._closed = False
+        self._worker = threading.Thread(target=self._run, name="gonova-microbatcher", daemon=True)
+        self._worker.start()
+
+    # -- producer side ----------------------------------------------------------------------------
+    def submit(self, mel: torch.Tensor) -> Future:
+        """mel [80, T] (host).  Returns a Future of the fp32 waveform [480*T].  Like the reference queue,
+        a full queue drops the request: queue.Full is raised and counted."""
+        if self._closed:
+            raise RuntimeError("MicroBatcher is closed")
+        if mel.dim() != 2 or mel.shape[0] != 80 or mel.shape[1] < 1:
+            raise ValueError("mel must be [80, T] with T >= 1")
+        fut: Future = Future()
+        try:
+            self._q.put_nowait((mel.to(torch.float32), fut))
+        except queue.Full:
+            self.metrics["dropped"] += 1
+            raise
+        self.metrics["requests"] += 1
+        return fut
+
+    def close(self, timeout: Optional[float] = 30.0) -> None:
+        """Stop accepting work, decode what is queued, join the worker."""
+        if self._closed:
+            return
+        self._closed = True
+        self._q.put(None)
+        self._worker.join(timeout)
+
+    # -- worker -----------------------------------------------------------------------------------
+    def _gather(self) -> Optional[List[Tuple[torch.Tensor, Future]]]:
+        first = self._q.get()
+        if first is None:
+            return None
+        batch = [first]
+        deadline = time.monotonic() + self.max_wait
+        while len(batch) < self.max_batch:
+            left = deadline - time.monotonic()
+            try:
+                item = self._q.get(timeout=left) if left > 0 else self._q.get_nowait()
+            except queue.Empty:
+                break
+            if item is None:
+                self._q.put(None)               # leave the stop marker for the next round
+                break
+            batch.append(item)
+        return batch
+
+    def _run(self) -> None:
+        while True:
+            batch = self._gather()
+            if batch is None:
+                return
+            live = [(m, f) for m, f in batch if f.set_running_or_notify_cancel()]
+            if not live:
+                continue
+            lengths = [int(m.shape[1]) for m, _ in live]
+            tmax = max(lengths)
+            x = torch.zeros(len(live), 80, tmax, dtype=torch.float32)
+            for i, (m, _) in enumerate(live):
+                x[i, :, : m.shape[1]] = m
+            self.metrics["batches"] += 1
+            self.metrics["frames"] += sum(lengths)
+            self.metrics["padded_frames"] += tmax * len(live)
+            try:
+                wav = self._decode(x, lengths)
+                if wav.shape[0] != len(live) or wav.shape[1] < tmax * SAMPLES_PER_FRAME:
+                    raise RuntimeError(f"decode_fn returned {tuple(wav.shape)} for a batch of {len(live)} x {tmax} frames")
+                for i, (_, f) in enumerate(live):
+                    f.set_result(wav[i, : lengths[i] * SAMPLES_PER_FRAME].clone())
+            except BaseException as e:          # every caller of the batch sees the failure, the worker survives
+                for _, f in live:
+                    if not f.done():
+                        f.set_exception(e)
+
+
+def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: int = 500) -> MicroBatcher:
+    """MicroBatcher in front of a B200HiFT: pinned staging, ragged batch through `lengths`, fp32 result on the host."""
+    dev = hift.device
+
+    def decode(x: torch.Tensor, lengths: Sequence[int]) -> torch.Tensor:
+        with torch.cuda.device(dev):
+            xd = x.pin_memory().to(dev, non_blocking=True)
+            wav, _ = hift.inference(xd, lengths=list(lengths))
+            return wav.cpu()
+
+    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue)

@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -154,7 +155,8 @@ struct Plan {
     d_maps = o.d_maps; o.d_maps = nullptr;
     return *this;
   }
-  ~Plan() { if (d_maps) cudaFree(d_maps); }
+  // d_maps is owned by the decoder handle (freed in gnv_destroy), not by the plan: a CUDA graph captured from
+  // this plan keeps pointing at the tensor maps even after the plan cache evicts it.
 };
 
 // Uploads the tensor maps of every persistent-kernel op to one device buffer and points the ops at it.
@@ -211,7 +213,7 @@ struct gnv_decoder {
   int spec_cs = 20;      // channel pitch of the STFT buffer (18 -> 24 bf16 / 20 fp32: 16-byte multiples)
   ResBlockW rb[9], srb[3];
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr;
-  std::map<PlanKey, Plan> plans;
+  std::map<PlanKey, std::shared_ptr<Plan>> plans;   // shared: a call keeps its plan alive if another thread evicts the cache
   std::mutex mu;
 };
 
@@ -678,10 +680,12 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   for (ConvOp& op : plan->f0_ops) all.push_back(&op);
   for (ConvOp& op : plan->decode_ops) all.push_back(&op);
   h->launch_counts[{B, T}] = (int)plan->decode_ops.size();
-  return upload_maps(all, &plan->d_maps);
+  std::string ue = upload_maps(all, &plan->d_maps);
+  if (ue.empty() && plan->d_maps) h->allocs.push_back(plan->d_maps);
+  return ue;
 }
 
-int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, Plan** out) {
+int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, std::shared_ptr<Plan>* out) {
   if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
   if (!ws) return fail(h, "workspace is NULL");
   if (((uintptr_t)ws & 1023) != 0) return fail(h, "workspace must be 1024-byte aligned");
@@ -689,16 +693,14 @@ int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, Plan** out) 
   PlanKey key(B, T, ws);
   auto it = h->plans.find(key);
   if (it == h->plans.end()) {
-    Plan p;
-    std::string e = build_plan(h, B, T, ws, &p);
+    auto p = std::make_shared<Plan>();
+    std::string e = build_plan(h, B, T, ws, p.get());
     if (!e.empty()) return fail(h, e);
-    cudaError_t pe = cudaGetLastError();
-    (void)pe;
-    if (h->plans.size() > 24) h->plans.clear();
+    if (h->plans.size() > 24) h->plans.clear();          // plans still in use stay alive through their shared_ptr
     it = h->plans.emplace(key, std::move(p)).first;
   }
-  if (ws_bytes < it->second.lay.total) return fail(h, "workspace too small for (B, T)");
-  *out = &it->second;
+  if (ws_bytes < it->second->lay.total) return fail(h, "workspace too small for (B, T)");
+  *out = it->second;
   return 0;
 }
 
@@ -874,8 +876,9 @@ int gnv_f0(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T,
            size_t workspace_bytes, void* stream) {
   if (!h || !mel || !f0) return fail(h, "NULL argument");
   DeviceGuard dg(h->device);
-  Plan* plan = nullptr;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  std::shared_ptr<Plan> plan_ref;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  Plan* plan = plan_ref.get();
   return run_f0(h, plan, mel, lengths, B, T, f0, (char*)workspace, true, (cudaStream_t)stream);
 }
 
@@ -892,8 +895,9 @@ int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* le
                void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !mel || !s || !wav) return fail(h, "NULL argument");
   DeviceGuard dg(h->device);
-  Plan* plan = nullptr;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  std::shared_ptr<Plan> plan_ref;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  Plan* plan = plan_ref.get();
   return run_decode(h, plan, mel, s, lengths, B, T, wav, (char*)workspace, true, (cudaStream_t)stream);
 }
 
@@ -903,8 +907,9 @@ static int inference_impl(gnv_handle h, const float* mel, const float* cache_sou
   if (!h || !mel || !wav || !s_out) return fail(h, "NULL argument");
   if (cache_len < 0 || (cache_len > 0 && !cache_source)) return fail(h, "bad cache_source");
   DeviceGuard dg(h->device);
-  Plan* plan = nullptr;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan)) return rc;
+  std::shared_ptr<Plan> plan_ref;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  Plan* plan = plan_ref.get();
   char* ws = (char*)workspace;
   float* f0 = (float*)(ws + plan->lay.f0);
   if (prof) prof->begin(st);
@@ -962,6 +967,14 @@ int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, c
   cudaError_t e = launch_pcm_tail(cur, cur_stride, prev_tail, fade_w, rows, n, fade, limit, out_i16, out_f32,
                                   out_stride, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(nullptr, "pcm_tail", e);
+  return 0;
+}
+
+int gnv_pcm_mulaw(const int16_t* pcm, int64_t n, uint8_t* out, void* stream) {
+  if (!pcm || !out) return fail(nullptr, "NULL argument");
+  if (n < 0) return fail(nullptr, "negative size");
+  cudaError_t e = launch_mulaw(pcm, (long long)n, out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(nullptr, "pcm_mulaw", e);
   return 0;
 }
 

@@ -496,4 +496,49 @@ cudaError_t launch_pcm_tail(const float* cur, int64_t cur_stride, const float* p
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// G.711 mu-law companding of int16 PCM (wire format of telephony clients): 2 B in, 1 B out per sample.
+// Same arithmetic as CPython's audioop.lin2ulaw (14-bit magnitude, bias 33, clip 8159); bit-exact.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mulaw_one(int v16) {
+  int x = v16 >> 2;
+  const uint32_t mask = x < 0 ? 0x7Fu : 0xFFu;
+  x = x < 0 ? -x : x;
+  x = min(x, 8159) + 33;
+  // segment = index of the first end in {0x3F,0x7F,...,0x1FFF} that is >= x  ==  max(0, position of the MSB - 5)
+  const int seg = max(0, 26 - __clz(x));          // x in [33, 8192]: MSB position 5..13 -> seg 0..8
+  const uint32_t u = seg >= 8 ? 0x7Fu : (uint32_t)((seg << 4) | ((x >> (seg + 1)) & 0xF));
+  return (u ^ mask) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(256) mulaw_kernel(const int16_t* __restrict__ in, long long n, uint8_t* __restrict__ out) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + q);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = mulaw_one((int)(short)(w[i] & 0xFFFFu)), b = mulaw_one((int)(short)(w[i] >> 16));
+      const uint32_t pr = a | (b << 8);
+      if (i < 2) lo |= pr << (16 * i); else hi |= pr << (16 * (i - 2));
+    }
+    reinterpret_cast<uint2*>(out)[q] = make_uint2(lo, hi);
+  }
+  // tail (n not a multiple of 8)
+  const long long t0 = n8 << 3;
+  for (long long i = t0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (uint8_t)mulaw_one(in[i]);
+}
+
+cudaError_t launch_mulaw(const int16_t* in, long long n, uint8_t* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  if (((uintptr_t)in & 15) || ((uintptr_t)out & 7)) return cudaErrorInvalidValue;
+  long long blocks = ((n >> 3) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mulaw_kernel<<<(int)blocks, 256, 0, st>>>(in, n, out);
+  return cudaGetLastError();
+}
+
 }  // namespace gnv

@@ -29,4 +29,7 @@ cudaError_t launch_pcm_tail(const float* cur, int64_t cur_stride, const float* p
                             int rows, int n, int fade, float limit, int16_t* out_i16, float* out_f32,
                             int64_t out_stride, cudaStream_t st);
 
+// G.711 mu-law: int16 PCM [n] (16-byte aligned) -> uint8 [n] (8-byte aligned)
+cudaError_t launch_mulaw(const int16_t* in, long long n, uint8_t* out, cudaStream_t st);
+
 }  // namespace gnv

@@ -340,3 +340,22 @@ def pcm_tail(cur: torch.Tensor, prev_tail: Optional[torch.Tensor] = None, fade_w
                               fade, C.c_float(limit), _ptr(out_i16), _ptr(out_f32), n, _stream_ptr(cur.device))
     _cabi.check(rc, None, "gnv_pcm_tail")
     return out_i16, out_f32
+
+
+@torch.no_grad()
+def mulaw_encode(pcm_i16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int16 PCM (CUDA, contiguous) -> G.711 mu-law bytes (uint8), bit-identical to audioop.lin2ulaw."""
+    if pcm_i16.dtype != torch.int16 or pcm_i16.device.type != "cuda":
+        raise ValueError("pcm_i16 must be an int16 CUDA tensor")
+    pcm_i16 = pcm_i16.contiguous()
+    if out is None:
+        out = torch.empty(pcm_i16.shape, dtype=torch.uint8, device=pcm_i16.device)
+    if pcm_i16.numel() == 0:
+        return out
+    if pcm_i16.data_ptr() % 16 or out.data_ptr() % 8:
+        raise ValueError("mulaw_encode needs a 16-byte aligned input and an 8-byte aligned output")
+    lib = _cabi.load()
+    with torch.cuda.device(pcm_i16.device):
+        rc = lib.gnv_pcm_mulaw(_ptr(pcm_i16), pcm_i16.numel(), _ptr(out), _stream_ptr(pcm_i16.device))
+    _cabi.check(rc, None, "gnv_pcm_mulaw")
+    return out

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .decoder import B200HiFT, pcm_tail, trim_fade_window
+from .decoder import B200HiFT, mulaw_encode, pcm_tail, trim_fade_window
 
 
 def install(model, dtype: Optional[str] = None, device=None) -> B200HiFT:
@@ -29,14 +29,16 @@ def install(model, dtype: Optional[str] = None, device=None) -> B200HiFT:
 class PcmSink:
     """Device float32 wav -> host bytes for the WebSocket, through one pinned staging buffer.
     fmt 'f32' reproduces the reference's `audio.astype(np.float32).tobytes()` bytes exactly;
-    fmt 'i16' is the opt-in int16 pack (clamp + round-half-even, one kernel)."""
+    fmt 'i16' is the opt-in int16 pack (clamp + round-half-even, one kernel); fmt 'mulaw' adds G.711 companding
+    (8 bits per sample, the telephony clients of the reference's `phone` extra)."""
 
     def __init__(self, device, max_samples: int = 24000 * 60, fmt: str = "f32", limit: float = 0.99):
-        if fmt not in ("f32", "i16"):
-            raise ValueError("fmt must be 'f32' or 'i16'")
+        if fmt not in ("f32", "i16", "mulaw"):
+            raise ValueError("fmt must be 'f32', 'i16' or 'mulaw'")
         self.fmt, self.limit = fmt, limit
         self.device = torch.device(device)
-        self._host = torch.empty(max_samples, dtype=torch.float32 if fmt == "f32" else torch.int16).pin_memory()
+        host_dtype = {"f32": torch.float32, "i16": torch.int16, "mulaw": torch.uint8}[fmt]
+        self._host = torch.empty(max_samples, dtype=host_dtype).pin_memory()
 
     @torch.no_grad()
     def to_bytes(self, wav: torch.Tensor, trim_fade: bool = False) -> bytes:
@@ -45,8 +47,8 @@ class PcmSink:
         if n > self._host.numel():
             self._host = torch.empty(n, dtype=self._host.dtype).pin_memory()
         fw = trim_fade_window(self.device) if trim_fade else None
-        i16, f32 = pcm_tail(wav, None, fw, self.limit, want_i16=self.fmt == "i16", want_f32=self.fmt == "f32")
-        src = i16 if self.fmt == "i16" else f32
+        i16, f32 = pcm_tail(wav, None, fw, self.limit, want_i16=self.fmt != "f32", want_f32=self.fmt == "f32")
+        src = f32 if self.fmt == "f32" else (i16 if self.fmt == "i16" else mulaw_encode(i16))
         self._host[:n].copy_(src.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._host[:n].numpy().tobytes()

@@ -122,6 +122,11 @@ int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, c
                  int rows, int n, int fade, float limit,
                  int16_t* out_i16, float* out_f32, int64_t out_stride, void* stream);
 
+/* G.711 mu-law companding of int16 PCM (telephony wire format; the reference's `phone` extra, pyproject.toml:55-57):
+ * out[i] = audioop.lin2ulaw(pcm[i]) bit for bit.  pcm 16-byte aligned, out 8-byte aligned, device pointers.
+ * replaces nothing in the reference (it ships float32 only, server.py:152); SURVEY 8f-3. */
+int gnv_pcm_mulaw(const int16_t* pcm, int64_t n, uint8_t* out, void* stream);
+
 /* ---- unit-test hooks (one kernel each; used by tests/, not by the service) -------------------- */
 
 /* HiFTGenerator._stft + cat(real, imag): s [B, L] -> spec [B, 18, L/4+1] (fp32, NCT). */

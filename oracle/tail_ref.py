@@ -100,3 +100,20 @@ def stream_decode_ref(decode_fn, mel, s, chunk: int = 100, halo: int = 16, fade:
         if not last:
             prev_tail = wav[:, a + n_emit:a + n_emit + fade].copy()
     return out_f, out_i
+
+
+def mulaw_encode(pcm_i16: np.ndarray) -> np.ndarray:
+    """G.711 mu-law companding of int16 PCM -> uint8 (the wire format of the reference's `phone`
+    extra, /root/reference/pyproject.toml:55-57).  Restates CPython's audioop.lin2ulaw(width=2)
+    (Modules/audioop.c st_14linear2ulaw: 14-bit magnitude, bias 33, clip 8159, 8 segments); tests/test_tail_oracle.py
+    pins it against audioop itself on all 65536 inputs."""
+    x = np.asarray(pcm_i16, dtype=np.int16).astype(np.int32) >> 2          # arithmetic shift: 14-bit sample
+    neg = x < 0
+    mag = np.where(neg, -x, x)
+    mag = np.minimum(mag, 8159) + 33
+    ends = np.array([0x3F, 0x7F, 0xFF, 0x1FF, 0x3FF, 0x7FF, 0xFFF, 0x1FFF], dtype=np.int32)
+    seg = np.searchsorted(ends, mag, side="left").astype(np.int32)        # first segment whose end >= mag
+    uval = (seg << 4) | ((mag >> (seg + 1)) & 0xF)
+    uval = np.where(seg >= 8, 0x7F, uval)
+    mask = np.where(neg, 0x7F, 0xFF)
+    return (uval ^ mask).astype(np.uint8)

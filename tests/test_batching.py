@@ -1,0 +1,102 @@
+"""MicroBatcher (host logic of SURVEY 8f-4) with a fake decoder: no GPU needed."""
+import queue
+import threading
+import time
+
+import pytest
+import torch
+
+from gonova_tts_b200.batching import MicroBatcher
+
+
+class FakeDecoder:
+    """wav[b, n] = mean of the utterance's mel (so results identify their request); records every batch."""
+
+    def __init__(self, delay=0.0, fail_on=None):
+        self.batches, self.delay, self.fail_on = [], delay, fail_on
+
+    def __call__(self, x, lengths):
+        self.batches.append((tuple(x.shape), list(lengths)))
+        if self.fail_on is not None and len(self.batches) == self.fail_on:
+            raise RuntimeError("decoder exploded")
+        time.sleep(self.delay)
+        out = torch.zeros(x.shape[0], x.shape[2] * 480)
+        for i, n in enumerate(lengths):
+            out[i, : n * 480] = x[i, :, :n].mean()
+            assert float(x[i, :, n:].abs().sum()) == 0.0          # padding is zeros
+        return out
+
+
+def test_requests_are_batched_and_results_routed():
+    dec = FakeDecoder(delay=0.02)
+    mb = MicroBatcher(dec, max_batch=8, max_wait_ms=50.0)
+    mels = [torch.full((80, 3 + i), float(i)) for i in range(20)]
+    futs = [mb.submit(m) for m in mels]
+    for i, f in enumerate(futs):
+        wav = f.result(timeout=10)
+        assert wav.shape == ((3 + i) * 480,) and torch.all(wav == float(i))
+    mb.close()
+    assert sum(len(l) for _, l in dec.batches) == 20
+    assert max(len(l) for _, l in dec.batches) == 8              # never more than max_batch
+    assert len(dec.batches) <= 5                                  # ... and it really batched
+    for shape, lengths in dec.batches:
+        assert shape == (len(lengths), 80, max(lengths))
+    m = mb.metrics
+    assert m["requests"] == 20 and m["batches"] == len(dec.batches) and m["frames"] == sum(3 + i for i in range(20))
+    assert m["padded_frames"] >= m["frames"]
+
+
+def test_concurrent_producers_and_single_request_latency():
+    dec = FakeDecoder()
+    mb = MicroBatcher(dec, max_batch=64, max_wait_ms=1.0)
+    t0 = time.monotonic()
+    assert mb.submit(torch.ones(80, 5)).result(timeout=5).shape == (2400,)   # a lone request waits ~max_wait only
+    assert time.monotonic() - t0 < 1.0
+    results, errs = {}, []
+
+    def producer(k):
+        try:
+            results[k] = [mb.submit(torch.full((80, 4), float(k * 10 + j))).result(timeout=10) for j in range(5)]
+        except BaseException as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=producer, args=(k,)) for k in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    mb.close()
+    assert not errs
+    for k in range(6):
+        for j in range(5):
+            assert torch.all(results[k][j] == float(k * 10 + j))
+
+
+def test_full_queue_drops_like_the_reference_and_errors_reach_callers():
+    gate = threading.Event()
+
+    def slow(x, lengths):
+        gate.wait(5)
+        return torch.zeros(x.shape[0], x.shape[2] * 480)
+
+    mb = MicroBatcher(slow, max_batch=1, max_wait_ms=0.0, max_queue=2)
+    first = mb.submit(torch.zeros(80, 2))                # taken by the worker, blocks in decode
+    time.sleep(0.1)
+    mb.submit(torch.zeros(80, 2)); mb.submit(torch.zeros(80, 2))
+    with pytest.raises(queue.Full):
+        mb.submit(torch.zeros(80, 2))
+    assert mb.metrics["dropped"] == 1
+    gate.set()
+    first.result(timeout=5)
+    mb.close()
+
+    dec = FakeDecoder(fail_on=1)
+    mb = MicroBatcher(dec, max_batch=4, max_wait_ms=20.0)
+    futs = [mb.submit(torch.zeros(80, 2)) for _ in range(3)]
+    for f in futs:
+        with pytest.raises(RuntimeError, match="exploded"):
+            f.result(timeout=5)
+    assert mb.submit(torch.ones(80, 2)).result(timeout=5).shape == (960,)   # the worker survived
+    mb.close()
+    with pytest.raises(RuntimeError):
+        mb.submit(torch.zeros(80, 2))
+    with pytest.raises(ValueError):
+        MicroBatcher(dec).submit(torch.zeros(79, 2))

@@ -266,3 +266,17 @@ def test_conv_rejects_bad_geometry(lib, cuda_device):
     rc = lib.gnv_conv1d(0, 0, 0, 0, _vp(x), 1, 8, 16, C.c_void_p(w.data_ptr()), None, 8, 3, 1, 1, 1, 0, None,
                         C.c_float(0), None, _vp(out), 15, None)
     assert rc != 0 and "Lout" in _cabi.last_error(None)
+
+
+def test_mulaw_bit_exact(lib, cuda_device):
+    from gonova_tts_b200 import mulaw_encode
+
+    x = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)                  # every int16, 128-bit path
+    got = mulaw_encode(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+    np.testing.assert_array_equal(got, TR.mulaw_encode(x))
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 8, 9, 4803, 240000):                                           # ragged tails
+        y = rng.integers(-32768, 32768, size=n, dtype=np.int64).astype(np.int16)
+        got = mulaw_encode(torch.from_numpy(y).to(cuda_device)).cpu().numpy()
+        np.testing.assert_array_equal(got, TR.mulaw_encode(y))
+    assert mulaw_encode(torch.empty(0, dtype=torch.int16, device=cuda_device)).numel() == 0

@@ -79,3 +79,18 @@ def test_stream_decode_ref_with_a_local_decoder_is_exact():
     want = np.clip(s[:, 0, :] * np.float32(0.5), -0.99, 0.99)
     np.testing.assert_allclose(f, want, atol=1e-7)
     np.testing.assert_array_equal(i, TR.pack_i16(f))
+
+
+def test_mulaw_matches_audioop_on_every_int16():
+    """The mu-law oracle against a real reference implementation (CPython's audioop, G.711)."""
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        audioop = __import__("audioop")
+    x = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
+    want = np.frombuffer(audioop.lin2ulaw(x.tobytes(), 2), dtype=np.uint8)
+    np.testing.assert_array_equal(TR.mulaw_encode(x), want)
+    # known answers: silence is 0xFF, full scale saturates at 0x80 / 0x00
+    np.testing.assert_array_equal(TR.mulaw_encode(np.array([0, 32767, -32768, 4, -4], dtype=np.int16)),
+                                  [0xFF, 0x80, 0x00, 0xFE, 0x7E])
