@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
                                                            const int* __restrict__ lengths, E* __restrict__ spec,
                                                            int C_ld, int front, int total_rows, int round) {
   __shared__ __align__(16) float x_s[kStftFrames * 4 + 12];
-  __shared__ float out_s[kStftFrames * 25];                    // odd pitch (C_ld + 1): conflict-free staging
   const int b = blockIdx.y, rb = blockIdx.x * kStftFrames;     // first output row of this block
   const int fb = rb - front;                                   // its frame index (may be negative)
   const int Lb = lengths ? min(L, lengths[b] * kSPF) : L;      // this utterance's samples
@@ -291,7 +290,7 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
     x[4 * q] = v4.x; x[4 * q + 1] = v4.y; x[4 * q + 2] = v4.z; x[4 * q + 3] = v4.w;
   }
   const bool live = f >= 0 && f < Fb;
-  const int SP = C_ld + 1;
+  float o[24];                                   // the frame's output row: 9 re, 9 im, zero padding channels
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     float re = 0.f, im = 0.f;
@@ -300,19 +299,38 @@ __global__ void __launch_bounds__(kStftFrames) stft_kernel(const float* __restri
       re = fmaf(x[n], c_stft_cw[k][n], re);
       im = fmaf(x[n], c_stft_sw[k][n], im);
     }
-    out_s[threadIdx.x * SP + k] = live ? re : 0.f;
-    out_s[threadIdx.x * SP + 9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
+    o[k] = live ? re : 0.f;
+    o[9 + k] = (live && k != 0 && k != 8) ? im : 0.f;
   }
-  for (int c = 18; c < C_ld; ++c) out_s[threadIdx.x * SP + c] = 0.f;
-  __syncthreads();
-  const int nr = min(kStftFrames, total_rows - rb);
-  E* ob = spec + ((size_t)b * total_rows + rb) * C_ld;
-  for (int i = threadIdx.x; i < nr * C_ld; i += blockDim.x) {
-    const int ri = i / C_ld;
-    float v = out_s[ri * SP + (i - ri * C_ld)];
-    if constexpr (sizeof(E) == 4) { if (round) v = round_tf32(v); }
-    ElemIO<E>::store(ob + i, v);
+#pragma unroll
+  for (int c = 18; c < 24; ++c) o[c] = 0.f;
+  const int row = rb + threadIdx.x;
+  if (row >= total_rows) return;
+  E* orow = spec + ((size_t)b * total_rows + row) * C_ld;
+  // one thread = one row: 16-byte stores straight from registers when the row pitch allows it
+  if constexpr (sizeof(E) == 2) {
+    if (C_ld == 24) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        reinterpret_cast<uint4*>(orow)[q] = make_uint4(ElemIO<E>::pack2(o[8 * q], o[8 * q + 1]), ElemIO<E>::pack2(o[8 * q + 2], o[8 * q + 3]),
+                                                      ElemIO<E>::pack2(o[8 * q + 4], o[8 * q + 5]), ElemIO<E>::pack2(o[8 * q + 6], o[8 * q + 7]));
+      return;
+    }
+  } else {
+    if (round) {
+#pragma unroll
+      for (int c = 0; c < 18; ++c) o[c] = round_tf32(o[c]);
+    }
+    if (C_ld == 20) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q)
+        reinterpret_cast<float4*>(orow)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      return;
+    }
   }
+#pragma unroll
+  for (int c = 0; c < 24; ++c)
+    if (c < C_ld) ElemIO<E>::store(orow + c, o[c]);
 }
 
 cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, void* spec_nlc, int elem_bytes, int round,
