@@ -387,7 +387,9 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const float mag = fminf(expf(xin[threadIdx.x * 19 + k]), 100.f);
-      const float ph = sinf(xin[threadIdx.x * 19 + 9 + k]);
+      // sin of the raw phase channel: one explicit 2*pi reduction, then MUFU.SIN on |r| <= pi (abs error ~ 2^-21)
+      const float xr = xin[threadIdx.x * 19 + 9 + k];
+      const float ph = __sinf(fmaf(-6.283185307179586f, rintf(xr * 0.15915494309189535f), xr));
       float sn, cs;
       __sincosf(ph, &sn, &cs);                               // |ph| <= 1: MUFU abs error ~ 2^-21
       re[k] = live ? mag * cs : 0.f;

@@ -194,26 +194,13 @@ cudaError_t launch_conv_pair(const ConvPairLaunch& L, const int* lengths, cudaSt
   if (!L.d_maps) return cudaErrorInvalidValue;
   ConvPairParams p = L.p;
   p.ep.lengths = lengths;
-  if (!p.cta2) {
-    if (L.elem_bytes == 2)
-      conv_pair_kernel<__nv_bfloat16, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-    else
-      conv_pair_kernel<float, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-    return cudaGetLastError();
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = L.smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   const ConvPairMaps* dm = L.d_maps;
-  if (L.elem_bytes == 2) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<__nv_bfloat16, true>, dm, p);
-  return cudaLaunchKernelEx(&cfg, conv_pair_kernel<float, true>, dm, p);
+  if (!p.cta2) {
+    if (L.elem_bytes == 2) return launch_persistent(conv_pair_kernel<__nv_bfloat16, false>, L.grid, L.smem_bytes, st, false, dm, p);
+    return launch_persistent(conv_pair_kernel<float, false>, L.grid, L.smem_bytes, st, false, dm, p);
+  }
+  if (L.elem_bytes == 2) return launch_persistent(conv_pair_kernel<__nv_bfloat16, true>, L.grid, L.smem_bytes, st, true, dm, p);
+  return launch_persistent(conv_pair_kernel<float, true>, L.grid, L.smem_bytes, st, true, dm, p);
 }
 
 }  // namespace gnv

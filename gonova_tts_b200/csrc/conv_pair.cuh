@@ -138,6 +138,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   if constexpr (CTA2) cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait_then_release();                     // the prologue above may overlap the previous kernel's tail
   // TMEM columns: acc1 buffers at 0 and mh*C, acc2 buffers at 2*mh*C and 3*mh*C
   const uint32_t acc2_col0 = (uint32_t)(2 * p.mh * p.C);
 

@@ -3,11 +3,20 @@
 #include "conv_tc2.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace gnv {
 
 static constexpr size_t kMaxDynSmem2 = 227 * 1024;
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("GONOVA_PDL");
+    return !(v && atoi(v) == 0);
+  }();
+  return on;
+}
 
 cudaError_t conv_tc2_init() {
   uint32_t* dptr = nullptr;
@@ -279,29 +288,13 @@ cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStre
   if (!L.d_maps) return cudaErrorInvalidValue;
   ConvTc2Params p = L.p;
   p.ep.lengths = lengths;
-  if (!p.cta2) {
-    if (L.elem_bytes == 2)
-      conv_tc2_kernel<__nv_bfloat16, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-    else
-      conv_tc2_kernel<float, false><<<L.grid, 384, L.smem_bytes, st>>>(L.d_maps, p);
-    return cudaGetLastError();
-  }
-  // CTA pairs: cluster of two (an explicit 1x1x1 cluster attribute is refused for this kernel on driver 580)
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(L.grid);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = L.smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   const ConvTc2Maps* dm = L.d_maps;
-  if (L.elem_bytes == 2) return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__nv_bfloat16, true>, dm, p);
-  return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<float, true>, dm, p);
+  if (!p.cta2) {
+    if (L.elem_bytes == 2) return launch_persistent(conv_tc2_kernel<__nv_bfloat16, false>, L.grid, L.smem_bytes, st, false, dm, p);
+    return launch_persistent(conv_tc2_kernel<float, false>, L.grid, L.smem_bytes, st, false, dm, p);
+  }
+  if (L.elem_bytes == 2) return launch_persistent(conv_tc2_kernel<__nv_bfloat16, true>, L.grid, L.smem_bytes, st, true, dm, p);
+  return launch_persistent(conv_tc2_kernel<float, true>, L.grid, L.smem_bytes, st, true, dm, p);
 }
 
 }  // namespace gnv

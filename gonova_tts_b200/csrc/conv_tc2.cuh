@@ -179,6 +179,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                : "memory");
 }
 
+// griddepcontrol.wait returns when every prerequisite grid has completed and flushed its memory (immediately when
+// the kernel was not launched with the programmatic-serialization attribute); launch_dependents lets the NEXT
+// kernel in the stream begin its own prologue as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct Ring {
   int slot = 0;
   uint32_t phase = 0;
@@ -417,6 +425,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   if constexpr (CTA2) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / TMA
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, per-channel tables from the
+  // static weights) may overlap the previous kernel's tail; from here on we read what it produced.
+  pdl_wait_then_release();
 
   const int rows_per_cta = BLOCK_M * p.mh;
   const int rows_per_tile = rows_per_cta * (CTA2 ? 2 : 1);   // a CTA pair's tile: the leader's rows, then the peer's
@@ -687,6 +698,32 @@ __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab,
 #endif  // __CUDACC__
 
 // ---- host side --------------------------------------------------------------------------------
+// Launch of a persistent kernel: optional cluster of two (CTA pairs) and programmatic dependent launch.
+bool pdl_enabled();      // GONOVA_PDL=0 switches programmatic dependent launch off
+template <typename Kern, typename... Args>
+inline cudaError_t launch_persistent(Kern kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster2) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = n ? attr : nullptr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 struct ConvTc2Launch {
   ConvTc2Maps maps;                 // host copy; the caller uploads it and sets d_maps before launching
   const ConvTc2Maps* d_maps = nullptr;
