@@ -172,7 +172,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for a weight tensor";
   }
   for (int v = 0; v < 2; ++v) {
-    const int box_rows = v == 0 ? 128 : 128 - (k - 1);
+    const int box_rows = v == 0 ? 32 : 32 - (k - 1);      // stores are per warp (32 rows); loads stay 128 rows
     const char* e = "";
     if (ep.res) e = encode_rows_map(enc, &out->maps.epi[v][EPI_IN0], ep.res, 4, C, L, B, 128);
     if (*e) return e;

@@ -48,7 +48,7 @@ struct ConvPairParams {
 
 struct ConvPairMaps {
   CUtensorMap X, W1, W2;
-  CUtensorMap epi[2][6];           // [0]: 128-row boxes, [1]: (128 - (k-1))-row boxes for a tile's last half
+  CUtensorMap epi[2][6];           // stores: [0] 32-row boxes, [1] (32 - (k-1))-row boxes (last warp of a tile's last half); loads: 128 rows
 };
 
 #ifdef __CUDACC__
@@ -420,8 +420,9 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           const float4 b4 = bt[j];
           v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
         }
-        // the tile's last half stores only its first 128 - (k-1) rows (the rest belongs to the next tile)
-        const CUtensorMap* m6 = &maps.epi[h == p.mh - 1 ? 1 : 0][0];
+        // the tile's last half stores only its first 128 - (k-1) rows (the rest belongs to the next tile): every warp
+        // stores its own 32 rows, the last warp of the last half a (32 - (k-1))-row box
+        const CUtensorMap* m6 = &maps.epi[(h == p.mh - 1 && q == 3) ? 1 : 0][0];
         epi_finish_item<E>(ectx, v, live, c0, m6, c0, m0 + h * BLOCK_M, b, rin, ob);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -438,7 +439,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       prev = t;
     }
     if (prev >= 0) epilogue2(prev, i - 1);
-    if (elected) bulk_wait_read<0>();
+    if (lane == 0) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -57,7 +57,7 @@ inline uint32_t up1024(uint32_t x) { return (x + 1023u) & ~1023u; }
 // [B, rows, C] view of an epilogue tensor for one polyphase `phase` (or the whole tensor when up == 1):
 // coordinate j of dim 1 is output row  base_row + j * up.
 const char* encode_epi_map(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int elem_bytes, int C_valid,
-                           int C_pitch, int L_out, int B, int up, int base_row, int n_rows) {
+                           int C_pitch, int L_out, int B, int up, int base_row, int n_rows, int box_rows) {
   if (!base) return "conv_tc2: epilogue tensor is NULL";
   if (n_rows <= 0) n_rows = 1;   // degenerate phase: every box is clipped (coordinates never reach it)
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -65,7 +65,7 @@ const char* encode_epi_map(PFN_encodeTiled enc, CUtensorMap* m, const void* base
   if (((uintptr_t)p & 15) || ((size_t)C_pitch * elem_bytes) % 16) return "conv_tc2: epilogue tensor is not 16-byte aligned";
   cuuint64_t dims[3] = {(cuuint64_t)C_valid, (cuuint64_t)n_rows, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)up * C_pitch * elem_bytes, (cuuint64_t)L_out * C_pitch * elem_bytes};
-  cuuint32_t box[3] = {(cuuint32_t)kEpiCols, 128u, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)kEpiCols, (cuuint32_t)box_rows, 1u};
   cuuint32_t es[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = (kEpiCols * elem_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(m, dt, 3, const_cast<char*>(p), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -267,14 +267,14 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
       n_rows = first_p0 <= ep.L_store - 1 ? (ep.L_store - 1 - first_p0) / ep.up + 1 : 0;
     }
     const char* e = "";
-    if (ep.res) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_IN0], ep.res, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows);
+    if (ep.res) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_IN0], ep.res, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows, 128);
     if (*e) return e;
-    if (ep.raw_accum) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_IN0 + (ep.res ? 1 : 0)], ep.raw, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows);
+    if (ep.raw_accum) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_IN0 + (ep.res ? 1 : 0)], ep.raw, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows, 128);
     if (*e) return e;
-    if (ep.raw) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_RAW], ep.raw, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows);
+    if (ep.raw) e = encode_epi_map(enc, &out->maps.epi[ph][EPI_RAW], ep.raw, 4, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows, 32);
     if (*e) return e;
     for (int a = 0; a < ep.n_act; ++a) {
-      e = encode_epi_map(enc, &out->maps.epi[ph][EPI_ACT0 + a], ep.act_out[a], elem_bytes, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows);
+      e = encode_epi_map(enc, &out->maps.epi[ph][EPI_ACT0 + a], ep.act_out[a], elem_bytes, ep.C_out, c_pitch_out, ep.L_out, g.B, up, base_row, n_rows, 32);
       if (*e) return e;
     }
   }

@@ -263,10 +263,12 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
     }
     // ---- stage the outputs (the store that last used this staging buffer must have drained) ----
     const uint32_t obase = c.obase_wg + ob * c.out_stride;
-    if (c.elected) {
+    // Each WARP stages and stores its own 32 rows of the chunk (its lane 0 owns the bulk-store groups), so the four
+    // warps of a warpgroup never wait for each other.
+    if (c.lane == 0) {
       if (c.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
     }
-    epi_bar_sync(c.wg);
+    __syncwarp();
     uint32_t o = obase;
     if (c.has_raw) {
 #pragma unroll
@@ -330,15 +332,16 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
       o += c.act_bytes;
     }
     fence_async_smem();
-    epi_bar_sync(c.wg);
-    if (c.elected) {
+    __syncwarp();
+    if (c.lane == 0) {
+      const int wq = c.erow >> 5;                          // this warp's 32-row quarter of the 128-row chunk
       uint32_t src = obase;
-                if (c.has_raw) {
-        tma_store_3d(maps6 + EPI_RAW, src, cs, mrow, b);
+      if (c.has_raw) {
+        tma_store_3d(maps6 + EPI_RAW, src + wq * (32 * kEpiCols * 4), cs, mrow + 32 * wq, b);
         src += BLOCK_M * kEpiCols * 4;
       }
       for (int a = 0; a < c.n_act; ++a) {
-        tma_store_3d(maps6 + EPI_ACT0 + a, src, cs, mrow, b);
+        tma_store_3d(maps6 + EPI_ACT0 + a, src + wq * (c.act_bytes >> 2), cs, mrow + 32 * wq, b);
         src += c.act_bytes;
       }
       bulk_commit();
@@ -657,7 +660,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       }
       racc.advance(p.acc_bufs);
     }
-    if (elected) bulk_wait_read<0>();
+    if (lane == 0) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
