@@ -34,7 +34,7 @@ struct ConvPairParams {
   int h_kb_bytes;                  // one K block of the h slab: 128*mh rows x 128 B
   int w_bytes;                     // one weight tile: C rows x 128 B
   int w_group, w_slot_bytes;       // taps per weight barrier / ring slot
-  int sa, sw, n_epi_wg, out_bufs;
+  int sa, sw, n_epi_wg, out_bufs, in_ring;
   int cta2;                        // CTA pairs: tiles_m / total_tiles then count PAIRS of CTA tiles
   int mma_order;                   // 0: alternate the two accumulators per MMA, 1: four k-steps per accumulator in a row
   uint32_t idesc;
@@ -77,8 +77,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   const uint32_t b_e1_done = b_acc1_full + 16u;       // epilogue 1 finished: h slab valid AND its acc1 buffer free
   const uint32_t b_h_empty = b_e1_done + 8u;          // conv2 MMAs retired: h slab may be overwritten
   const uint32_t b_acc2_full = b_h_empty + 8u, b_acc2_empty = b_acc2_full + 16u;
-  const uint32_t b_in_full = b_acc2_empty + 16u, b_in_empty = b_in_full + 16u;
-  const uint32_t tmem_slot = b_in_empty + 16u;
+  const uint32_t b_in_full = b_acc2_empty + 16u, b_in_empty = b_in_full + 8u * kMaxInSlots;
+  const uint32_t tmem_slot = b_in_empty + 8u * kMaxInSlots;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +102,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_acc2_full + 8u * s, 1);
       mbar_init(b_acc2_empty + 8u * s, 4 * p.n_epi_wg * kSub);
+    }
+    for (int s = 0; s < kMaxInSlots; ++s) {
       mbar_init(b_in_full + 8u * s, 1);
       mbar_init(b_in_empty + 8u * s, 4);
     }
@@ -281,21 +283,21 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   } else if (warp == kWarpLoader) {
     if (lane == 0 && p.n_in > 0) {
       // ===== epilogue-2 input loader (same ring protocol as conv_tc2) =====
-      uint32_t slot_phase[2] = {0u, 0u};
-      int seq = 0;
+      int cnt[2] = {0, 0};
       const int n_items = p.mh * n_epi_chunks;
       for (int t = tile0; t < p.total_tiles; t += G) {
         const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
-        for (int item = 0; item < n_items; ++item, ++seq) {
+        for (int item = 0; item < n_items; ++item) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
           const int mrow = m_tile * p.Mo + h * BLOCK_M;
-          const int slot = p.n_epi_wg == 2 ? (item & 1) : (seq & 1);
-          mbar_wait(b_in_empty + 8u * slot, slot_phase[slot] ^ 1u, 3);
+          const int wgi = p.n_epi_wg == 2 ? (item & 1) : 0;
+          const int k = cnt[wgi]++;
+          const int slot = wgi * p.in_ring + k % p.in_ring;
+          mbar_wait(b_in_empty + 8u * slot, (uint32_t)((k / p.in_ring) & 1) ^ 1u, 3);
           mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
           for (int j = 0; j < p.n_in; ++j)
             tma_load_3d(&maps.epi[0][EPI_IN0 + j], b_in_full + 8u * slot,
                         sIn + (slot * p.n_in + j) * (BLOCK_M * kEpiCols * 4), cc * kEpiCols, mrow, b);
-          slot_phase[slot] ^= 1u;
         }
       }
     }
@@ -312,7 +314,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     EpiCtx ectx;
     ectx.ep = &p.ep; ectx.tab = tab; ectx.c_tab = Cp; ectx.n_in = p.n_in; ectx.has_raw = p.has_raw;
     ectx.n_act = p.n_act; ectx.act_bytes = p.act_bytes; ectx.n_epi_wg = p.n_epi_wg; ectx.out_bufs = p.out_bufs;
-    ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty;
+    ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty; ectx.in_ring = p.in_ring;
     ectx.obase_wg = sOut + wg * p.out_bufs * out_stride; ectx.out_stride = out_stride;
     ectx.wg = wg; ectx.erow = erow; ectx.lane = lane; ectx.elected = elected;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);

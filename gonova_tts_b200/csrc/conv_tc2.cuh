@@ -31,6 +31,7 @@ namespace gnv {
 constexpr int kMaxPhase = 8;
 constexpr int kMaxSlab = 12;
 constexpr int kEpiCols = 32;    // columns per epilogue chunk (one 128-byte fp32 row)
+constexpr int kMaxInSlots = 8;  // epilogue-input slots (residual / running-sum tiles prefetched by the loader warp)
 // Warp roles of the persistent kernels (384 threads).  The single-lane control warps get the HIGHEST
 // warp ids: the SM's warp arbiter favours higher ids, and the MMA issuer / TMA producer must never
 // queue behind the (issue-bound) epilogue warps that share their scheduler.
@@ -56,6 +57,7 @@ struct ConvTc2Params {
   int a_base_offset_mode;          // 1: descriptor base_offset = (start address >> 7) & 7
   int sa, sw, n_epi_wg, acc_bufs;   // n_epi_wg: epilogue warpgroups in use (1 or 2)
   int out_bufs;                     // output staging buffers per warpgroup (1 or 2)
+  int in_ring;                      // epilogue-input slots per warpgroup (prefetch depth of the loader warp)
   int slab_bytes, w_bytes;
   int w_group, w_slot_bytes;       // taps per weight barrier; bytes of one weight ring slot (w_group * w_bytes)
   int tmem_cols;
@@ -214,7 +216,8 @@ struct EpiCtx {
   const EpiParams* ep;
   const float* tab;            // bias[c_tab], then (alpha[c_tab], 1/(alpha+1e-9)[c_tab]) per activation
   int c_tab, n_in, has_raw, n_act, act_bytes, n_epi_wg, out_bufs;
-  uint8_t* smem_in;            // the loader's ring of two input slots
+  int in_ring;                 // input slots per warpgroup (the loader runs that many chunks ahead of it)
+  uint8_t* smem_in;            // the loader's input slots: warpgroup g owns slots [g*in_ring, (g+1)*in_ring)
   uint32_t b_in_full, b_in_empty;
   uint32_t obase_wg;           // this warpgroup's staging buffers
   int out_stride;
@@ -227,8 +230,7 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
                                                 const CUtensorMap* maps6, int cs, int mrow, int b, Ring& rin, int& ob) {
     // ---- residual, scale, running sum ----
     if (c.n_in > 0) {
-      // two warpgroups: this one owns slot `wg` of the loader's ring of two; one: it uses both in turn
-      const int in_slot = c.n_epi_wg == 2 ? c.wg : rin.slot;
+      const int in_slot = c.wg * c.in_ring + rin.slot;
       const uint8_t* in_tile = c.smem_in + (size_t)in_slot * c.n_in * (BLOCK_M * kEpiCols * 4);
       mbar_wait(c.b_in_full + 8u * in_slot, rin.phase, 5);
       if (c.ep->res) {
@@ -252,7 +254,7 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
       }
       __syncwarp();
       if (c.lane == 0) mbar_arrive(c.b_in_empty + 8u * in_slot);
-      if (c.n_epi_wg == 2) rin.phase ^= 1u; else rin.advance(2);
+      rin.advance(c.in_ring);
     } else if (c.ep->raw_scale != 1.0f) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] *= c.ep->raw_scale;
@@ -373,8 +375,8 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   const uint32_t b_a_full = bar0, b_a_empty = b_a_full + 8u * p.sa;
   const uint32_t b_w_full = b_a_empty + 8u * p.sa, b_w_empty = b_w_full + 8u * p.sw;
   const uint32_t b_acc_full = b_w_empty + 8u * p.sw, b_acc_empty = b_acc_full + 16u;
-  const uint32_t b_in_full = b_acc_empty + 16u, b_in_empty = b_in_full + 16u;
-  const uint32_t tmem_slot = b_in_empty + 16u;
+  const uint32_t b_in_full = b_acc_empty + 16u, b_in_empty = b_in_full + 8u * kMaxInSlots;
+  const uint32_t tmem_slot = b_in_empty + 8u * kMaxInSlots;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -393,6 +395,8 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_acc_full + 8u * s, 1);
       mbar_init(b_acc_empty + 8u * s, 4 * p.n_epi_wg * (CTA2 ? 2 : 1));   // pair: both CTAs' epilogues arrive on the leader
+    }
+    for (int s = 0; s < kMaxInSlots; ++s) {
       mbar_init(b_in_full + 8u * s, 1);
       mbar_init(b_in_empty + 8u * s, 4);
     }
@@ -558,10 +562,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   } else if (warp == kWarpLoader) {
     if (lane == 0 && p.n_in > 0) {
       // ===== epilogue-input loader: residual / running-sum tiles -> shared memory =====
-      // Ring of two slots.  With two epilogue warpgroups item i of a tile goes to slot i % 2 (the
-      // warpgroup that will consume it); with one, slots simply alternate.  Phases are per slot.
-      uint32_t slot_phase[2] = {0u, 0u};
-      int seq = 0;
+      // Each warpgroup owns a ring of in_ring slots; chunk i of a tile goes to warpgroup i % 2 (the one that will
+      // consume it), so the loader runs in_ring chunks ahead of every warpgroup.
+      int cnt[2] = {0, 0};                               // chunks handed to each warpgroup so far
       const int n_items = p.mh * n_epi_chunks;
       for (int t = tile0; t < p.total_tiles; t += tile_step) {
         int q = t;
@@ -571,16 +574,17 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
         const int n0 = n_tile * p.block_n;
         const int ph = p.transposed ? n_tile : 0;
         const int cbase = p.transposed ? 0 : n0;
-        for (int item = 0; item < n_items; ++item, ++seq) {
+        for (int item = 0; item < n_items; ++item) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
           const int mrow = m_tile * rows_per_tile + crank * rows_per_cta + h * BLOCK_M;   // TMA row coordinate (GEMM row - row_adj)
-          const int slot = p.n_epi_wg == 2 ? (item & 1) : (seq & 1);
-          mbar_wait(b_in_empty + 8u * slot, slot_phase[slot] ^ 1u, 3);
+          const int wgi = p.n_epi_wg == 2 ? (item & 1) : 0;                               // the warpgroup that will consume it
+          const int k = cnt[wgi]++;
+          const int slot = wgi * p.in_ring + k % p.in_ring;
+          mbar_wait(b_in_empty + 8u * slot, (uint32_t)((k / p.in_ring) & 1) ^ 1u, 3);
           mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
           for (int i = 0; i < p.n_in; ++i)
             tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * slot,
                         sIn + (slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
-          slot_phase[slot] ^= 1u;
         }
       }
     }
@@ -601,7 +605,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     EpiCtx ectx;
     ectx.ep = &p.ep; ectx.tab = tab; ectx.c_tab = p.c_tab; ectx.n_in = p.n_in; ectx.has_raw = p.has_raw;
     ectx.n_act = p.n_act; ectx.act_bytes = p.act_bytes; ectx.n_epi_wg = p.n_epi_wg; ectx.out_bufs = p.out_bufs;
-    ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty;
+    ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty; ectx.in_ring = p.in_ring;
     ectx.obase_wg = obase_wg; ectx.out_stride = out_stride; ectx.wg = wg; ectx.erow = erow; ectx.lane = lane;
     ectx.elected = elected;
     for (int t = tile0; t < p.total_tiles; t += tile_step) {
@@ -703,6 +707,7 @@ __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab,
 // ---- host side --------------------------------------------------------------------------------
 // Launch of a persistent kernel: optional cluster of two (CTA pairs) and programmatic dependent launch.
 bool pdl_enabled();      // GONOVA_PDL=0 switches programmatic dependent launch off
+int in_slots_cap();      // GONOVA_IN_SLOTS caps the epilogue-input prefetch slots
 template <typename Kern, typename... Args>
 inline cudaError_t launch_persistent(Kern kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, Args... args) {
   cudaLaunchConfig_t cfg{};
