@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -141,50 +142,75 @@ struct WsLayout {
   size_t total = 0;
 };
 
+// Device home of one plan's tensor maps.  Slots belong to the decoder handle and are recycled when the plan cache
+// evicts a plan (a service sees a new sentence length on almost every call: no cudaMalloc / cudaFree per call and
+// no growth).  `last_use` is recorded after every launch sequence that reads the slot.
+struct MapsSlot {
+  void* d = nullptr;           // device buffer
+  char* staging = nullptr;     // pinned host mirror the upload is issued from
+  size_t bytes = 0;
+  cudaEvent_t last_use = nullptr;
+  bool used = false;
+};
+
 struct Plan {
   std::vector<ConvOp> decode_ops;
   std::vector<ConvOp> f0_ops;
   WsLayout lay;
-  void* d_maps = nullptr;          // device copy of every op's tensor maps (conv_tc2)
+  MapsSlot slot;                   // tensor maps of every persistent-kernel op
+  unsigned long long last_tick = 0;
+  bool pinned = false;             // used inside a stream capture: a CUDA graph points at `slot` for good, never evicted
   Plan() = default;
   Plan(const Plan&) = delete;
   Plan& operator=(const Plan&) = delete;
-  Plan(Plan&& o) noexcept { *this = std::move(o); }
-  Plan& operator=(Plan&& o) noexcept {
-    decode_ops = std::move(o.decode_ops); f0_ops = std::move(o.f0_ops); lay = o.lay;
-    d_maps = o.d_maps; o.d_maps = nullptr;
-    return *this;
-  }
-  // d_maps is owned by the decoder handle (freed in gnv_destroy), not by the plan: a CUDA graph captured from
-  // this plan keeps pointing at the tensor maps even after the plan cache evicts it.
 };
 
-// Uploads the tensor maps of every persistent-kernel op to one device buffer and points the ops at it.
-std::string upload_maps(std::vector<ConvOp*>& ops, void** d_out) {
-  *d_out = nullptr;
+void free_slot(MapsSlot& sl) {
+  if (sl.last_use) cudaEventDestroy(sl.last_use);
+  if (sl.staging) cudaFreeHost(sl.staging);
+  if (sl.d) cudaFree(sl.d);
+  sl = MapsSlot();
+}
+
+// Uploads the tensor maps of every persistent-kernel op to the plan's slot (taken from `free_slots` when one is large
+// enough) and points the ops at it.  The copy is stream-ordered on `st`, from pinned memory.
+std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_slots, MapsSlot* slot, cudaStream_t st) {
   size_t bytes = 0;
   for (ConvOp* op : ops) {
     if (op->tc && op->tcv == 2) bytes += sizeof(ConvTc2Maps);
     if (op->tc && op->tcv == 3) bytes += sizeof(ConvPairMaps);
   }
   if (!bytes) return "";
-  std::vector<char> host(bytes);
+  MapsSlot sl;
+  for (size_t i = 0; i < free_slots.size(); ++i)
+    if (free_slots[i].bytes >= bytes) { sl = free_slots[i]; free_slots.erase(free_slots.begin() + i); break; }
+  if (!sl.d) {
+    cudaError_t e = cudaMalloc(&sl.d, bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&sl.staging, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.last_use, cudaEventDisableTiming);
+    if (e != cudaSuccess) { free_slot(sl); return std::string("tensor-map slot: ") + cudaGetErrorString(e); }
+    sl.bytes = bytes;
+  } else if (sl.used) {
+    // the evicted plan's launches (and its own upload) must be done before the mirror is rewritten; it was the least
+    // recently used plan, so this returns at once in practice
+    cudaError_t e = cudaEventSynchronize(sl.last_use);
+    if (e != cudaSuccess) { free_slots.push_back(sl); return std::string("tensor-map slot wait: ") + cudaGetErrorString(e); }
+  }
   size_t off = 0;
   for (ConvOp* op : ops) {
-    if (op->tc && op->tcv == 2) { memcpy(host.data() + off, &op->tc2l.maps, sizeof(ConvTc2Maps)); off += sizeof(ConvTc2Maps); }
-    if (op->tc && op->tcv == 3) { memcpy(host.data() + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
+    if (op->tc && op->tcv == 2) { memcpy(sl.staging + off, &op->tc2l.maps, sizeof(ConvTc2Maps)); off += sizeof(ConvTc2Maps); }
+    if (op->tc && op->tcv == 3) { memcpy(sl.staging + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
   }
-  void* d = nullptr;
-  cudaError_t e = cudaMalloc(&d, bytes);
-  if (e != cudaSuccess) return std::string("cudaMalloc(tensor maps): ") + cudaGetErrorString(e);
-  e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(d); return std::string("cudaMemcpy(tensor maps): ") + cudaGetErrorString(e); }
+  cudaError_t e = cudaMemcpyAsync(sl.d, sl.staging, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventRecord(sl.last_use, st);
+  if (e != cudaSuccess) { free_slots.push_back(sl); return std::string("cudaMemcpyAsync(tensor maps): ") + cudaGetErrorString(e); }
+  sl.used = true;
   off = 0;
   for (ConvOp* op : ops) {
-    if (op->tc && op->tcv == 2) { op->tc2l.d_maps = reinterpret_cast<const ConvTc2Maps*>((char*)d + off); off += sizeof(ConvTc2Maps); }
-    if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)d + off); off += sizeof(ConvPairMaps); }
+    if (op->tc && op->tcv == 2) { op->tc2l.d_maps = reinterpret_cast<const ConvTc2Maps*>((char*)sl.d + off); off += sizeof(ConvTc2Maps); }
+    if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)sl.d + off); off += sizeof(ConvPairMaps); }
   }
-  *d_out = d;
+  *slot = sl;
   return "";
 }
 
@@ -214,6 +240,10 @@ struct gnv_decoder {
   ResBlockW rb[9], srb[3];
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr;
   std::map<PlanKey, std::shared_ptr<Plan>> plans;   // shared: a call keeps its plan alive if another thread evicts the cache
+  std::vector<MapsSlot> free_slots;                 // tensor-map slots of evicted plans, reused by the next plan built
+  size_t max_plans = 64;                            // LRU bound of `plans` (GONOVA_MAX_PLANS); pinned plans do not count out
+  unsigned long long tick = 0;
+  unsigned long long plans_built = 0, slots_allocated = 0;
   std::mutex mu;
 };
 
@@ -529,7 +559,7 @@ cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   }
 }
 
-std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
+std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaStream_t st) {
   plan->lay = make_layout(h, B, T);
   const WsLayout& w = plan->lay;
   char* base = (char*)ws;
@@ -679,29 +709,67 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan) {
   std::vector<ConvOp*> all;
   for (ConvOp& op : plan->f0_ops) all.push_back(&op);
   for (ConvOp& op : plan->decode_ops) all.push_back(&op);
+  if (h->launch_counts.size() > 4096) h->launch_counts.clear();
   h->launch_counts[{B, T}] = (int)plan->decode_ops.size();
-  std::string ue = upload_maps(all, &plan->d_maps);
-  if (ue.empty() && plan->d_maps) h->allocs.push_back(plan->d_maps);
+  const size_t free_before = h->free_slots.size();
+  std::string ue = upload_maps(all, h->free_slots, &plan->slot, st);
+  if (ue.empty() && plan->slot.d && h->free_slots.size() == free_before) ++h->slots_allocated;
   return ue;
 }
 
-int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, std::shared_ptr<Plan>* out) {
+// Plan cache: LRU over (B, T, workspace), bounded by h->max_plans.  The reference service decodes one sentence at a
+// time (services/tts/server.py:118-182), so nearly every call brings a new T: a miss must be cheap and must not grow
+// the process.  An evicted plan hands its tensor-map slot to the next plan built.
+int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, cudaStream_t st, std::shared_ptr<Plan>* out) {
   if (B <= 0 || T <= 0) return fail(h, "B and T must be positive");
   if (!ws) return fail(h, "workspace is NULL");
   if (((uintptr_t)ws & 1023) != 0) return fail(h, "workspace must be 1024-byte aligned");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   std::lock_guard<std::mutex> lk(h->mu);
   PlanKey key(B, T, ws);
   auto it = h->plans.find(key);
   if (it == h->plans.end()) {
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(h, "the first call for a new (B, T, workspace) builds its launch plan and cannot run inside a stream "
+                     "capture: call once outside the capture first");
+    while (h->plans.size() >= h->max_plans) {
+      auto victim = h->plans.end();
+      for (auto j = h->plans.begin(); j != h->plans.end(); ++j)
+        if (!j->second->pinned && j->second.use_count() == 1 &&
+            (victim == h->plans.end() || j->second->last_tick < victim->second->last_tick))
+          victim = j;
+      if (victim == h->plans.end()) break;             // everything is pinned or in use: let the cache grow
+      if (victim->second->slot.d) h->free_slots.push_back(victim->second->slot);
+      h->plans.erase(victim);
+    }
     auto p = std::make_shared<Plan>();
-    std::string e = build_plan(h, B, T, ws, p.get());
-    if (!e.empty()) return fail(h, e);
-    if (h->plans.size() > 24) h->plans.clear();          // plans still in use stay alive through their shared_ptr
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string e = build_plan(h, B, T, ws, p.get(), st);
+    if (!e.empty()) {
+      if (p->slot.d) h->free_slots.push_back(p->slot);
+      return fail(h, e);
+    }
+    ++h->plans_built;
+    if (getenv("GONOVA_PLAN_TIMING"))
+      fprintf(stderr, "[gonova] plan B=%d T=%d built in %.0f us (%zu cached, %llu slots)\n", B, T,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(),
+              h->plans.size() + 1, h->slots_allocated);
     it = h->plans.emplace(key, std::move(p)).first;
   }
   if (ws_bytes < it->second->lay.total) return fail(h, "workspace too small for (B, T)");
+  it->second->last_tick = ++h->tick;
+  if (cap != cudaStreamCaptureStatusNone) it->second->pinned = true;
   *out = it->second;
   return 0;
+}
+
+// After the launches of one call: marks the plan's tensor-map slot as in use up to this point of the stream.
+void plan_used(Plan* plan, cudaStream_t st) {
+  if (!plan->slot.last_use || plan->pinned) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+  cudaEventRecord(plan->slot.last_use, st);
 }
 
 struct DeviceGuard {
@@ -774,6 +842,8 @@ void gnv_destroy(gnv_handle h) {
   if (!h) return;
   {
     DeviceGuard dg(h->device);
+    for (auto& kv : h->plans) free_slot(kv.second->slot);
+    for (MapsSlot& sl : h->free_slots) free_slot(sl);
     for (void* p : h->allocs) cudaFree(p);
   }
   delete h;
@@ -817,6 +887,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   if (const char* v = getenv("GONOVA_FUSE_PAIRS")) h->fuse_pairs = atoi(v) != 0;
   if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_PAIR_CTA2")) h->pair_cta2 = atoi(v);
+  if (const char* v = getenv("GONOVA_MAX_PLANS")) h->max_plans = (size_t)(atoi(v) > 0 ? atoi(v) : 1);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
   std::string err;
@@ -877,9 +948,11 @@ int gnv_f0(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T,
   if (!h || !mel || !f0) return fail(h, "NULL argument");
   DeviceGuard dg(h->device);
   std::shared_ptr<Plan> plan_ref;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, (cudaStream_t)stream, &plan_ref)) return rc;
   Plan* plan = plan_ref.get();
-  return run_f0(h, plan, mel, lengths, B, T, f0, (char*)workspace, true, (cudaStream_t)stream);
+  const int rc = run_f0(h, plan, mel, lengths, B, T, f0, (char*)workspace, true, (cudaStream_t)stream);
+  plan_used(plan, (cudaStream_t)stream);
+  return rc;
 }
 
 int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
@@ -896,9 +969,11 @@ int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* le
   if (!h || !mel || !s || !wav) return fail(h, "NULL argument");
   DeviceGuard dg(h->device);
   std::shared_ptr<Plan> plan_ref;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, (cudaStream_t)stream, &plan_ref)) return rc;
   Plan* plan = plan_ref.get();
-  return run_decode(h, plan, mel, s, lengths, B, T, wav, (char*)workspace, true, (cudaStream_t)stream);
+  const int rc = run_decode(h, plan, mel, s, lengths, B, T, wav, (char*)workspace, true, (cudaStream_t)stream);
+  plan_used(plan, (cudaStream_t)stream);
+  return rc;
 }
 
 static int inference_impl(gnv_handle h, const float* mel, const float* cache_source, int cache_len,
@@ -908,8 +983,9 @@ static int inference_impl(gnv_handle h, const float* mel, const float* cache_sou
   if (cache_len < 0 || (cache_len > 0 && !cache_source)) return fail(h, "bad cache_source");
   DeviceGuard dg(h->device);
   std::shared_ptr<Plan> plan_ref;
-  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, &plan_ref)) return rc;
+  if (int rc = get_plan(h, B, T, workspace, workspace_bytes, st, &plan_ref)) return rc;
   Plan* plan = plan_ref.get();
+  struct Used { Plan* p; cudaStream_t s; ~Used() { plan_used(p, s); } } used{plan, st};
   char* ws = (char*)workspace;
   float* f0 = (float*)(ws + plan->lay.f0);
   if (prof) prof->begin(st);
@@ -1091,10 +1167,11 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed, const floa
   std::string me = make_op(&tmp, L, A, B, Lin, es, &op);
   if (!me.empty()) return fail(nullptr, "gnv_conv1d: " + me);
   std::vector<ConvOp*> one{&op};
-  void* d_maps = nullptr;
-  me = upload_maps(one, &d_maps);
+  std::vector<MapsSlot> no_free;
+  MapsSlot slot;
+  struct SlotGuard { MapsSlot* s; ~SlotGuard() { free_slot(*s); } } slot_guard{&slot};   // the hook syncs before returning
+  me = upload_maps(one, no_free, &slot, st);
   if (!me.empty()) return fail(nullptr, "gnv_conv1d: " + me);
-  if (d_maps) sc.p.push_back(d_maps);
   GNV_CK(nullptr, "conv", run_op(op, nullptr, st));
   if (act != GNV_ACT_NONE)
     GNV_CK(nullptr, "unpack", launch_nlc_to_nct(actb, B, Lout, Cout, Cp, tmp.eb, y_nct, st));
@@ -1159,6 +1236,17 @@ int gnv_decode_launches(gnv_handle h, int B, int T, int* out) {
     else if (h->use_tc && h->tc_version == 2 && h->fuse_pairs) convs -= 4 * 3 * (h->fuse_max_c >= 128 ? 2 : 1);
   }
   *out = 3 + convs;
+  return 0;
+}
+
+int gnv_plan_stats(gnv_handle h, uint64_t out[4]) {
+  if (!h || !out) return fail(h, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  out[0] = h->plans.size();
+  out[1] = h->plans_built;
+  out[2] = h->slots_allocated;
+  out[3] = 0;
+  for (auto& kv : h->plans) out[3] += kv.second->pinned ? 1 : 0;
   return 0;
 }
 

@@ -56,7 +56,11 @@ class B200HiFT:
     audio_limit = 0.99
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dtype: str = "bf16",
-                 simt_conv: bool = False, precise_act: bool = False, tc_v1: bool = False, prefix: str = ""):
+                 simt_conv: bool = False, precise_act: bool = False, tc_v1: bool = False, prefix: str = "",
+                 bucket_frames: int = 0):
+        """bucket_frames > 1: `inference()` rounds T up to a multiple of it and masks the tail through `lengths`, so a
+        service that sees a new sentence length on every call (services/tts/server.py:118-182) keeps hitting the
+        handle's launch-plan cache (gnv_plan_stats).  Results for the first T frames do not change."""
         if dtype not in _cabi.DTYPE:
             raise ValueError(f"dtype must be one of {sorted(_cabi.DTYPE)}")
         self.device = torch.device(device)
@@ -87,6 +91,7 @@ class B200HiFT:
         _cabi.check(rc, None, "gnv_create")
         self._h = h
         self._ws: Optional[torch.Tensor] = None
+        self.bucket_frames = int(bucket_frames)
         self._lock = threading.Lock()
         self._seed = 0
         self.f0_predictor = _F0Predictor(self)
@@ -134,10 +139,18 @@ class B200HiFT:
 
     def _workspace(self, B: int, T: int) -> torch.Tensor:
         need = self.workspace_bytes(B, T)
-        if self._ws is None or self._ws.numel() < need:
+        if self._ws is None or self._ws.numel() < need + 1024:
+            # every launch plan is tied to the workspace address: grow by at least half so that a run of slightly
+            # longer sentences does not rebuild the plans each time
+            grow = 0 if self._ws is None else self._ws.numel() + self._ws.numel() // 2
             self._ws = None
-            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(max(need + 1024, grow), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def reserve(self, B: int, T: int) -> None:
+        """Allocate the workspace for the largest (B, T) the caller will send, once (e.g. at service start-up)."""
+        with self._lock:
+            self._workspace(B, T)
 
     @staticmethod
     def _aligned(ws: torch.Tensor) -> Tuple[int, int]:
@@ -229,10 +242,16 @@ class B200HiFT:
             cache_len = cache_source.shape[1]
         else:
             cache_source = None
-        lengths = self._lengths(lengths, B)
         if seed is None:
             self._seed += 1
             seed = self._seed
+        T_true = T
+        if self.bucket_frames > 1 and out is None and source_out is None and T % self.bucket_frames:
+            T = -(-T // self.bucket_frames) * self.bucket_frames
+            mel = torch.nn.functional.pad(mel, (0, T - T_true))
+            if lengths is None:
+                lengths = [T_true] * B
+        lengths = self._lengths(lengths, B)
         L = T * SAMPLES_PER_FRAME
         wav = out if out is not None else torch.empty(B, L, dtype=torch.float32, device=self.device)
         src = source_out if source_out is not None else torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
@@ -243,6 +262,11 @@ class B200HiFT:
                                          C.c_uint64(seed), _ptr(wav), _ptr(src), C.c_void_p(p), n,
                                          _stream_ptr(self.device))
             _cabi.check(rc, self._h, "gnv_inference")
+        if T != T_true:                                   # bucketed: hand back exactly the caller's frames
+            Lt = T_true * SAMPLES_PER_FRAME
+            wav, src = wav[:, :Lt], src[:, :, :Lt]
+            if B > 1:
+                wav, src = wav.contiguous(), src.contiguous()
         return wav, src
 
     # -- extras -----------------------------------------------------------------------------------
@@ -293,6 +317,12 @@ class B200HiFT:
         fn = self._lib.gnv_inference_launches if inference else self._lib.gnv_decode_launches
         _cabi.check(fn(self._h, B, T, C.byref(n)), self._h, "launch count")
         return n.value
+
+    def plan_stats(self) -> dict:
+        """Launch-plan cache of the handle (gnv_plan_stats): plans cached / built so far, device slots, pinned plans."""
+        out = (C.c_uint64 * 4)()
+        _cabi.check(self._lib.gnv_plan_stats(self._h, out), self._h, "gnv_plan_stats")
+        return {"cached": int(out[0]), "built": int(out[1]), "slots": int(out[2]), "pinned": int(out[3])}
 
 
 # -------------------------------------------------------------------------------------------------

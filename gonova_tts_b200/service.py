@@ -16,12 +16,19 @@ import torch
 from .decoder import B200HiFT, mulaw_encode, pcm_tail, trim_fade_window
 
 
-def install(model, dtype: Optional[str] = None, device=None) -> B200HiFT:
+def install(model, dtype: Optional[str] = None, device=None, bucket_frames: int = 8,
+            max_frames: int = 3000) -> B200HiFT:
     """Swap `model.s3gen.mel2wav` for a B200HiFT built from its weights.  Returns the new decoder.
-    Raises (never falls back) if the CUDA library is missing or the device is not a B200."""
+    Raises (never falls back) if the CUDA library is missing or the device is not a B200.
+
+    The service decodes one sentence per call, each with its own length: `bucket_frames` rounds T up to a multiple
+    (masked, results unchanged) so the launch-plan cache keeps hitting, and the workspace for `max_frames` (60 s) is
+    reserved once so plans never move."""
     dtype = dtype or os.environ.get("GONOVA_DECODER_DTYPE", "bf16")
     old = model.s3gen.mel2wav
-    new = B200HiFT.from_module(old, device=device, dtype=dtype)
+    new = B200HiFT.from_module(old, device=device, dtype=dtype, bucket_frames=bucket_frames)
+    if max_frames > 0:
+        new.reserve(1, max_frames)
     model.s3gen.mel2wav = new
     return new
 

@@ -1,0 +1,96 @@
+"""The launch-plan cache behind the C ABI under the reference service's traffic shape.
+
+The reference decodes ONE sentence per call (services/tts/server.py:118-182; synthesizer.py:327-359), so the
+decoder sees a new T on almost every call.  A plan (tensor maps + tile lists) is per (B, T, workspace); these tests
+pin down that a long run of distinct lengths neither grows device memory nor changes results, that the Python
+shim's length bucketing is invisible in the output, and that a CUDA graph keeps its plan."""
+import pytest
+import torch
+
+from oracle import hift_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    from gonova_tts_b200 import random_state_dict
+
+    return random_state_dict(0, False)
+
+
+def test_many_sentence_lengths_reuse_slots_and_results_survive_eviction(lib, cuda_device, sd):
+    from gonova_tts_b200 import B200HiFT
+
+    dec = B200HiFT(sd, device=cuda_device, dtype="bf16")
+    dec.reserve(1, 120)                                   # one workspace address for the whole run
+    mel = R.synthetic_mel(1, 120, seed=11).to(cuda_device)
+    g = torch.Generator().manual_seed(12)
+    s = (torch.rand(1, 1, 120 * 480, generator=g) * 0.2 - 0.1).to(cuda_device)
+
+    def decode(T):
+        return dec.decode(mel[:, :, :T].contiguous(), s[:, :, : T * 480].contiguous())
+
+    first = {T: decode(T).clone() for T in (3, 5, 40)}
+    for T in range(1, 121):                               # 120 distinct lengths through an LRU of 64
+        decode(T)
+    st = dec.plan_stats()
+    assert st["cached"] <= 64, st
+    assert st["built"] >= 120, st
+    assert st["slots"] <= 65, st                          # evicted plans hand their device slot on: no growth
+    for T, want in first.items():                         # rebuilt after eviction: bit-identical
+        assert torch.equal(decode(T), want), T
+    before = dec.plan_stats()["slots"]
+    for T in range(1, 121):
+        decode(T)
+    assert dec.plan_stats()["slots"] == before
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_bucketed_inference_is_invisible(lib, cuda_device, sd, dtype):
+    """bucket_frames rounds T up and masks through `lengths`: waveform and source of the caller's T frames are
+    exactly those of the un-bucketed call, and the plan cache sees one shape per bucket."""
+    from gonova_tts_b200 import B200HiFT
+
+    exact = B200HiFT(sd, device=cuda_device, dtype=dtype)
+    bucketed = B200HiFT(sd, device=cuda_device, dtype=dtype, bucket_frames=8)
+    worst = 0.0
+    for T in (1, 7, 8, 9, 33, 117, 233):
+        mel = R.synthetic_mel(2, T, seed=T).to(cuda_device)
+        wav_e, src_e = exact.inference(mel, seed=5)
+        wav_b, src_b = bucketed.inference(mel, seed=5)
+        assert wav_b.shape == wav_e.shape == (2, T * 480) and src_b.shape == src_e.shape
+        assert wav_b.is_contiguous() and src_b.is_contiguous()
+        assert torch.equal(src_b, src_e), T
+        worst = max(worst, float((wav_b - wav_e).abs().max()))
+    print(f"[bucket] {dtype}: max |bucketed - exact| = {worst:.3e}")
+    assert worst == 0.0
+    assert bucketed.plan_stats()["built"] == 5            # buckets 8, 16, 40, 120, 240
+
+
+def test_graph_pins_its_plan_and_first_call_in_capture_is_refused(lib, cuda_device, sd):
+    from gonova_tts_b200 import B200HiFT, GraphedInference
+
+    dec = B200HiFT(sd, device=cuda_device, dtype="bf16")
+    dec.reserve(1, 100)
+    gi = GraphedInference(dec, 1, 24, seed=3)
+    mel = R.synthetic_mel(1, 24, seed=1).to(cuda_device)
+    want = gi(mel).clone()
+    assert dec.plan_stats()["pinned"] == 1
+    for T in range(25, 101):                              # 76 other shapes: enough to evict anything evictable
+        dec.inference(R.synthetic_mel(1, T, seed=T).to(cuda_device), seed=3)
+    assert dec.plan_stats()["pinned"] == 1
+    assert torch.equal(gi(mel), want)                     # the graph's tensor maps were not recycled
+
+    fresh = B200HiFT(sd, device=cuda_device, dtype="bf16")
+    fresh.reserve(1, 16)
+    m16 = R.synthetic_mel(1, 16, seed=2).to(cuda_device)
+    wav = torch.empty(1, 16 * 480, device=cuda_device)
+    src = torch.empty(1, 1, 16 * 480, device=cuda_device)
+    graph = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="capture"):
+        with torch.cuda.graph(graph):
+            fresh.inference(m16, seed=1, out=wav, source_out=src)
+    torch.cuda.synchronize()
+    w2, _ = fresh.inference(m16, seed=1)                  # and the handle still works afterwards
+    assert torch.isfinite(w2).all()
