@@ -804,7 +804,7 @@ int run_f0(gnv_handle h, Plan* plan, const float* mel, const int* lengths, int B
     prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
   }
   const void* hl = ws + (plan->f0_ops.size() % 2 ? w.H0 : w.H1);
-  GNV_CK(h, "f0 head", launch_f0_head(hl, h->eb, B * T, 512, h->f0_w, h->f0_b, f0, st));
+  GNV_CK(h, "f0 head", launch_f0_head(hl, h->eb, B * T, T, lengths, 512, h->f0_w, h->f0_b, f0, st));
   prof_mark(prof, "f0_predictor.classifier", GNV_LAUNCH_AUX, 2.0 * B * T * 512);
   return 0;
 }

@@ -76,27 +76,30 @@ cudaError_t launch_nlc_to_nct(const void* in, int B, int L, int C, int C_ld, int
 // f0 head: |Linear(512 -> 1)|, one warp per (b, t) row
 // ------------------------------------------------------------------------------------------------
 template <typename E>
-__global__ void f0_head_kernel(const E* __restrict__ h, int rows, int C, const float* __restrict__ w,
-                               const float* __restrict__ bias, float* __restrict__ f0) {
+__global__ void f0_head_kernel(const E* __restrict__ h, int rows, int T, const int* __restrict__ lengths, int C,
+                               const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ f0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const E* p = h + (size_t)row * C;
   float acc = 0.f;
-  for (int c = lane; c < C; c += 32) acc = fmaf(ElemIO<E>::load(p + c), w[c], acc);
+  // frames past the utterance's length hold zero rows by definition (a ragged batch may leave them unwritten)
+  const bool live = !lengths || (row % T) < lengths[row / T];
+  if (live)
+    for (int c = lane; c < C; c += 32) acc = fmaf(ElemIO<E>::load(p + c), w[c], acc);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) f0[row] = fabsf(acc + bias[0]);
 }
 
-cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int C, const float* w, const float* bias,
-                           float* f0, cudaStream_t st) {
+cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int T, const int* lengths, int C, const float* w,
+                           const float* bias, float* f0, cudaStream_t st) {
   const int wpb = 8;
   dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
   if (elem_bytes == 2)
-    f0_head_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)h, rows, C, w, bias, f0);
+    f0_head_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)h, rows, T, lengths, C, w, bias, f0);
   else
-    f0_head_kernel<float><<<grid, block, 0, st>>>((const float*)h, rows, C, w, bias, f0);
+    f0_head_kernel<float><<<grid, block, 0, st>>>((const float*)h, rows, T, lengths, C, w, bias, f0);
   return cudaGetLastError();
 }
 

@@ -146,6 +146,20 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
 
   const int n_epi_chunks = p.C / kEpiCols;
   const int G = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // tile stride of this CTA (pair)
+  // Ragged batches: tiles wholly kDeadMargin rows or more past their utterance's valid length are skipped by every role
+  // (see conv_tc2_kernel); `next_tile` walks this CTA's live tiles.
+  auto tile_live = [&](int t) -> bool {
+    if (!p.ep.lengths) return true;
+    const int b = t / p.tiles_m;
+    const long valid = (long)p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
+    return (long)(t % p.tiles_m) * kSub * p.Mo < valid + kDeadMargin;
+  };
+  auto next_tile = [&](int t) -> int {
+    do { t += G; } while (t < p.total_tiles && !tile_live(t));
+    return t;
+  };
+  const int tile_first = (tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
+  const int tile_second = tile_first < p.total_tiles ? next_tile(tile_first) : tile_first;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
@@ -191,11 +205,13 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch) load_w_groups(&maps.W2, ch);
       };
       // the issuer runs conv1 two tiles ahead of conv2: M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...
-      if (tile0 < p.total_tiles) load_m1(tile0);
-      if (tile0 + G < p.total_tiles) load_m1(tile0 + G);
-      for (int t = tile0; t < p.total_tiles; t += G) {
+      if (tile_first < p.total_tiles) load_m1(tile_first);
+      if (tile_second < p.total_tiles) load_m1(tile_second);
+      for (int t = tile_first, t1 = tile_second; t < p.total_tiles;) {
         load_m2();
-        if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G);
+        const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
+        if (t2 < p.total_tiles) load_m1(t2);
+        t = t1; t1 = t2;
       }
     }
   } else if (warp == kWarpMma) {
@@ -270,14 +286,16 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         if constexpr (CTA2) umma_commit_2sm(b_acc2_full + 8u * buf); else umma_commit(b_acc2_full + 8u * buf);
         if constexpr (CTA2) umma_commit_2sm(b_h_empty); else umma_commit(b_h_empty);
       };
-      if (tile0 < p.total_tiles) issue_m1(0);
-      if (tile0 + G < p.total_tiles) issue_m1(1);
+      if (tile_first < p.total_tiles) issue_m1(0);
+      if (tile_second < p.total_tiles) issue_m1(1);
       int i = 0;
-      for (int t = tile0; t < p.total_tiles; t += G, ++i) {
+      for (int t = tile_first, t1 = tile_second; t < p.total_tiles; ++i) {
         mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);          // h slab of tile i is valid, acc1[i & 1] is free
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         issue_m2(i);
-        if (t + 2 * G < p.total_tiles) issue_m1(i + 2);
+        const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
+        if (t2 < p.total_tiles) issue_m1(i + 2);
+        t = t1; t1 = t2;
       }
     }
   } else if (warp == kWarpLoader) {
@@ -285,7 +303,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       // ===== epilogue-2 input loader (same ring protocol as conv_tc2) =====
       int cnt[2] = {0, 0};
       const int n_items = p.mh * n_epi_chunks;
-      for (int t = tile0; t < p.total_tiles; t += G) {
+      for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
         for (int item = 0; item < n_items; ++item) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
@@ -435,7 +453,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       }
     };
     int i = 0, prev = -1;
-    for (int t = tile0; t < p.total_tiles; t += G, ++i) {
+    for (int t = tile_first; t < p.total_tiles; t = next_tile(t), ++i) {
       epilogue1(t, i);
       if (prev >= 0) epilogue2(prev, i - 1);
       prev = t;

@@ -31,6 +31,9 @@ namespace gnv {
 constexpr int kMaxPhase = 8;
 constexpr int kMaxSlab = 12;
 constexpr int kEpiCols = 32;    // columns per epilogue chunk (one 128-byte fp32 row)
+// rows past an utterance's valid length that are still written (as zeros) in a ragged batch: covers the halo any
+// consumer reads ((k - 1) * dilation / 2 <= 25 rows) with room to spare
+constexpr int kDeadMargin = 64;
 constexpr int kMaxInSlots = 8;  // epilogue-input slots (residual / running-sum tiles prefetched by the loader warp)
 // Warp roles of the persistent kernels (384 threads).  The single-lane control warps get the HIGHEST
 // warp ids: the SM's warp arbiter favours higher ids, and the MMA issuer / TMA producer must never
@@ -439,12 +442,28 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   const int rows_per_cta = BLOCK_M * p.mh;
   const int rows_per_tile = rows_per_cta * (CTA2 ? 2 : 1);   // a CTA pair's tile: the leader's rows, then the peer's
   const int n_epi_chunks = p.block_n / kEpiCols;
+  // Ragged batches: a tile whose every output row lies kDeadMargin or more rows past its utterance's valid length is
+  // skipped by ALL roles (same predicate, so the barrier sequences stay in step).  Rows in [valid, valid + margin)
+  // are still written (as zeros): that is the zero padding the next layer's last valid rows read.
+  auto tile_live = [&](int t) -> bool {
+    if (!p.ep.lengths) return true;
+    const int qt = t / p.n_tiles_n;
+    const int m_tile = qt % p.tiles_m, b = qt / p.tiles_m;
+    const long valid = (long)p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
+    const long first_row = (long)m_tile * rows_per_tile * p.ep.up - p.ep.pad_out + p.ep.shift;
+    return first_row < valid + kDeadMargin;
+  };
+  auto next_tile = [&](int t) -> int {
+    do { t += tile_step; } while (t < p.total_tiles && !tile_live(t));
+    return t;
+  };
+  const int tile_first = (tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
       // ===== TMA producer: A slabs and W tile groups, in the order the MMA issuer consumes them =====
       Ring ra, rw;
-      for (int t = tile0; t < p.total_tiles; t += tile_step) {
+      for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         int q = t;
         const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
         const int m_tile = q % p.tiles_m;
@@ -497,7 +516,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       // Descriptors are built once; per MMA only the 14-bit start-address field moves (low word add).
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW);
       Ring ra, rw, racc;
-      for (int t = tile0; t < p.total_tiles; t += tile_step) {
+      for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         mbar_wait(b_acc_empty + 8u * racc.slot, racc.phase ^ 1u, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc0 = tmem_base + (uint32_t)(racc.slot * p.mh * p.block_n);
@@ -566,7 +585,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       // consume it), so the loader runs in_ring chunks ahead of every warpgroup.
       int cnt[2] = {0, 0};                               // chunks handed to each warpgroup so far
       const int n_items = p.mh * n_epi_chunks;
-      for (int t = tile0; t < p.total_tiles; t += tile_step) {
+      for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         int q = t;
         const int n_tile = q % p.n_tiles_n; q /= p.n_tiles_n;
         const int m_tile = q % p.tiles_m;
@@ -608,7 +627,7 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     ectx.smem_in = smem_gen + p.off_in; ectx.b_in_full = b_in_full; ectx.b_in_empty = b_in_empty; ectx.in_ring = p.in_ring;
     ectx.obase_wg = obase_wg; ectx.out_stride = out_stride; ectx.wg = wg; ectx.erow = erow; ectx.lane = lane;
     ectx.elected = elected;
-    for (int t = tile0; t < p.total_tiles; t += tile_step) {
+    for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
       int qq = t;
       const int n_tile = qq % p.n_tiles_n; qq /= p.n_tiles_n;
       const int m_tile = qq % p.tiles_m;

@@ -12,8 +12,8 @@ cudaError_t launch_nct_to_nlc(const float* in, int B, int C, int L, const int* l
 cudaError_t launch_nlc_to_nct(const void* in, int B, int L, int C, int C_ld, int elem_bytes, float* out,
                               cudaStream_t st, long long in_batch_stride = 0);
 // f0[b,t] = | dot(h[b,t,:C], w) + bias |   (ConvRNNF0Predictor.classifier + abs)
-cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int C, const float* w, const float* bias,
-                           float* f0, cudaStream_t st);
+cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int T, const int* lengths, int C, const float* w,
+                           const float* bias, float* f0, cudaStream_t st);
 // SineGen + SourceModuleHnNSF: f0 [B,T] -> s [B, 480T]
 cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
                           const float* lin_w /*[9]*/, const float* lin_b /*[1]*/, float* s, cudaStream_t st);

@@ -121,3 +121,11 @@ def test_result_does_not_depend_on_workspace_contents(lib, cuda_device, sd, dtyp
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
     for b, n in enumerate(lens):
         assert not outs[0][0][b, n * 480:].any()
+        # ... and every row of the ragged batch is bit-identical to that utterance decoded alone at its own length
+        # (tiles wholly past an utterance's end are skipped, not computed and discarded)
+        alone, src1 = dec.inference(mel[b:b + 1, :, :n].contiguous(), seed=9)
+        if b == 0:                                        # the noise stream is keyed by the row index: row 0 matches
+            assert torch.equal(src1[0, 0], outs[0][1][0, 0, : n * 480])
+            assert torch.equal(alone[0], outs[0][0][0, : n * 480])
+        one = dec.decode(mel[b:b + 1, :, :n].contiguous(), outs[0][1][b:b + 1, :, : n * 480].contiguous())
+        assert torch.equal(one[0], outs[0][0][b, : n * 480]), (b, n)
