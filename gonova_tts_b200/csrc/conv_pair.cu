@@ -15,13 +15,17 @@ cudaError_t conv_pair_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_pair_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_pair_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_pair_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_pair_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
+  const auto set = [](auto kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemPair);
+  };
+  if ((e = set(conv_pair_kernel<__nv_bfloat16, false, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<__nv_bfloat16, false, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<float, false, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<float, false, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<__nv_bfloat16, true, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<__nv_bfloat16, true, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_pair_kernel<float, true, false>)) != cudaSuccess) return e;
+  return set(conv_pair_kernel<float, true, true>);
 }
 
 namespace {
@@ -203,12 +207,17 @@ cudaError_t launch_conv_pair(const ConvPairLaunch& L, const int* lengths, cudaSt
   ConvPairParams p = L.p;
   p.ep.lengths = lengths;
   const ConvPairMaps* dm = L.d_maps;
+  // the RAGGED instantiation (dead tiles skipped) only when the batch carries lengths: the dense walk stays as it was
+  const auto go = [&](auto dense, auto ragged, bool pair) {
+    return lengths ? launch_persistent(ragged, L.grid, L.smem_bytes, st, pair, dm, p)
+                   : launch_persistent(dense, L.grid, L.smem_bytes, st, pair, dm, p);
+  };
   if (!p.cta2) {
-    if (L.elem_bytes == 2) return launch_persistent(conv_pair_kernel<__nv_bfloat16, false>, L.grid, L.smem_bytes, st, false, dm, p);
-    return launch_persistent(conv_pair_kernel<float, false>, L.grid, L.smem_bytes, st, false, dm, p);
+    if (L.elem_bytes == 2) return go(conv_pair_kernel<__nv_bfloat16, false, false>, conv_pair_kernel<__nv_bfloat16, false, true>, false);
+    return go(conv_pair_kernel<float, false, false>, conv_pair_kernel<float, false, true>, false);
   }
-  if (L.elem_bytes == 2) return launch_persistent(conv_pair_kernel<__nv_bfloat16, true>, L.grid, L.smem_bytes, st, true, dm, p);
-  return launch_persistent(conv_pair_kernel<float, true>, L.grid, L.smem_bytes, st, true, dm, p);
+  if (L.elem_bytes == 2) return go(conv_pair_kernel<__nv_bfloat16, true, false>, conv_pair_kernel<__nv_bfloat16, true, true>, true);
+  return go(conv_pair_kernel<float, true, false>, conv_pair_kernel<float, true, true>, true);
 }
 
 }  // namespace gnv

@@ -56,7 +56,7 @@ struct ConvPairMaps {
 // CTA2 = true: CTA pairs (cluster of two, tcgen05.mma.cta_group::2): the two CTAs work on ADJACENT tiles of the same
 // utterance, each with its own x slab, h slab, accumulators and epilogues; they share every weight tile (each stages
 // half of its rows), and the leader's MMA thread issues both CTAs' MMAs (M = 256 across the pair).
-template <typename E, bool CTA2>
+template <typename E, bool CTA2, bool RAGGED>
 __global__ void __launch_bounds__(384, 1)
 conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant__ ConvPairParams p) {
   using namespace tc2;
@@ -146,20 +146,25 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
 
   const int n_epi_chunks = p.C / kEpiCols;
   const int G = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // tile stride of this CTA (pair)
-  // Ragged batches: tiles wholly kDeadMargin rows or more past their utterance's valid length are skipped by every role
-  // (see conv_tc2_kernel); `next_tile` walks this CTA's live tiles.
+  // Ragged batches (RAGGED instantiation, launched when `lengths` is given): tiles wholly kDeadMargin rows or more past
+  // their utterance's valid length are skipped by every role (see conv_tc2_kernel); `next_tile` walks this CTA's live
+  // tiles.  The dense instantiation compiles to the plain strided walk.
   auto tile_live = [&](int t) -> bool {
-    if (!p.ep.lengths) return true;
+    if constexpr (!RAGGED) return true;
     const int b = t / p.tiles_m;
     const long valid = (long)p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
     return (long)(t % p.tiles_m) * kSub * p.Mo < valid + kDeadMargin;
   };
   auto next_tile = [&](int t) -> int {
+    if constexpr (!RAGGED) return t + G;
     do { t += G; } while (t < p.total_tiles && !tile_live(t));
     return t;
   };
-  const int tile_first = (tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
-  const int tile_second = tile_first < p.total_tiles ? next_tile(tile_first) : tile_first;
+  int tile_first = tile0, tile_second = tile0;
+  if constexpr (RAGGED) {
+    if (tile0 < p.total_tiles && !tile_live(tile0)) tile_first = next_tile(tile0);
+    tile_second = tile_first < p.total_tiles ? next_tile(tile_first) : tile_first;
+  }
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
@@ -205,18 +210,30 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch) load_w_groups(&maps.W2, ch);
       };
       // the issuer runs conv1 two tiles ahead of conv2: M1(0) M1(1) | M2(0) M1(2) | M2(1) M1(3) | ...
-      if (tile_first < p.total_tiles) load_m1(tile_first);
-      if (tile_second < p.total_tiles) load_m1(tile_second);
-      for (int t = tile_first, t1 = tile_second; t < p.total_tiles;) {
-        load_m2();
-        const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
-        if (t2 < p.total_tiles) load_m1(t2);
-        t = t1; t1 = t2;
+      // (the dense walk is kept in its plain strided form: ptxas keeps the issuer's descriptors in uniform registers
+      // for it, and loses that — R2UR before every MMA, 16 % slower k = 11 pairs — with the rotating live-tile walk)
+      if constexpr (RAGGED) {
+        if (tile_first < p.total_tiles) load_m1(tile_first);
+        if (tile_second < p.total_tiles) load_m1(tile_second);
+        for (int t = tile_first, t1 = tile_second; t < p.total_tiles;) {
+          load_m2();
+          const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
+          if (t2 < p.total_tiles) load_m1(t2);
+          t = t1; t1 = t2;
+        }
+      } else {
+        if (tile0 < p.total_tiles) load_m1(tile0);
+        if (tile0 + G < p.total_tiles) load_m1(tile0 + G);
+        for (int t = tile0; t < p.total_tiles; t += G) {
+          load_m2();
+          if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G);
+        }
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0) {
       // ===== MMA issuer (pair: the leader issues both CTAs' MMAs) =====
+      // whole warp in the loops, one elected lane issues (see conv_tc2_kernel): uniform registers, UTCHMMAs back to back
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW), h_desc0 = umma_desc_sw128(sH);
       Ring ra, rw;
       // one K block (channel block ch) of a conv: every tap group's weights against row-shifted views of `a_base`
@@ -225,43 +242,47 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           const int ng = min(p.w_group, p.k - tap);
           mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int g = 0; g < ng; ++g) {
-            const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
-            const uint64_t ad0 = a_base + (uint64_t)((uint32_t)((tap + g) * row_step) * (KBLK_BYTES >> 4));
-            // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA never
-            // waits for the previous one's accumulate into the same TMEM tile (p.mma_order == 1 keeps the old order)
-            if (p.mma_order == 0 && p.mh == 2) {
-              const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
-              const uint32_t acc1 = acc0 + (uint32_t)p.C;
+          if (elect_one()) {
+            for (int g = 0; g < ng; ++g) {
+              const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
+              const uint64_t ad0 = a_base + (uint64_t)((uint32_t)((tap + g) * row_step) * (KBLK_BYTES >> 4));
+              const uint32_t ac0 = g == 0 ? accum : 1u;
+              // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA never
+              // waits for the previous one's accumulate into the same TMEM tile (p.mma_order == 1 keeps the old order)
+              if (p.mma_order == 0 && p.mh == 2) {
+                const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
+                const uint32_t acc1 = acc0 + (uint32_t)p.C;
 #pragma unroll
-              for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
-                const uint32_t ac = kk == 0 ? accum : 1u;
-                if constexpr (CTA2) {
-                  umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
-                  umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
-                } else {
-                  umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
-                  umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
+                  const uint32_t ac = kk == 0 ? ac0 : 1u;
+                  if constexpr (CTA2) {
+                    umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                    umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                  } else {
+                    umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                    umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                  }
                 }
-              }
-            } else {
-              for (int h = 0; h < p.mh; ++h) {
-                const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
-                const uint32_t acc = acc0 + (uint32_t)(h * p.C);
-                if constexpr (CTA2) {
-                  umma_2sm<E>(acc, ad, bd, p.idesc, accum);
+              } else {
+                for (int h = 0; h < p.mh; ++h) {
+                  const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
+                  const uint32_t acc = acc0 + (uint32_t)(h * p.C);
+                  if constexpr (CTA2) {
+                    umma_2sm<E>(acc, ad, bd, p.idesc, ac0);
 #pragma unroll
-                  for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
-                } else {
-                  umma<E>(acc, ad, bd, p.idesc, accum);
+                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                  } else {
+                    umma<E>(acc, ad, bd, p.idesc, ac0);
 #pragma unroll
-                  for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                  }
                 }
               }
             }
-            accum = 1u;
+            if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
           }
-          if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
+          __syncwarp();
+          accum = 1u;
           rw.advance(p.sw);
         }
       };
@@ -271,10 +292,16 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
           issue_taps(a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4), p.d1,
                      tmem_base + (uint32_t)((j & 1) * p.mh * p.C), accum);
-          if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
+          if (elect_one()) {
+            if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
+          }
+          __syncwarp();
           ra.advance(p.sa);
         }
-        if constexpr (CTA2) umma_commit_2sm(b_acc1_full + 8u * (j & 1)); else umma_commit(b_acc1_full + 8u * (j & 1));
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_2sm(b_acc1_full + 8u * (j & 1)); else umma_commit(b_acc1_full + 8u * (j & 1));
+        }
+        __syncwarp();
       };
       auto issue_m2 = [&](int i) {
         const int buf = i & 1;
@@ -283,19 +310,33 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch)
           issue_taps(h_desc0 + (uint64_t)((uint32_t)(ch * p.h_kb_bytes) >> 4), 1,
                      tmem_base + acc2_col0 + (uint32_t)(buf * p.mh * p.C), accum);
-        if constexpr (CTA2) umma_commit_2sm(b_acc2_full + 8u * buf); else umma_commit(b_acc2_full + 8u * buf);
-        if constexpr (CTA2) umma_commit_2sm(b_h_empty); else umma_commit(b_h_empty);
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_2sm(b_acc2_full + 8u * buf); else umma_commit(b_acc2_full + 8u * buf);
+          if constexpr (CTA2) umma_commit_2sm(b_h_empty); else umma_commit(b_h_empty);
+        }
+        __syncwarp();
       };
-      if (tile_first < p.total_tiles) issue_m1(0);
-      if (tile_second < p.total_tiles) issue_m1(1);
       int i = 0;
-      for (int t = tile_first, t1 = tile_second; t < p.total_tiles; ++i) {
-        mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);          // h slab of tile i is valid, acc1[i & 1] is free
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_m2(i);
-        const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
-        if (t2 < p.total_tiles) issue_m1(i + 2);
-        t = t1; t1 = t2;
+      if constexpr (RAGGED) {
+        if (tile_first < p.total_tiles) issue_m1(0);
+        if (tile_second < p.total_tiles) issue_m1(1);
+        for (int t = tile_first, t1 = tile_second; t < p.total_tiles; ++i) {
+          mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);        // h slab of tile i is valid, acc1[i & 1] is free
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_m2(i);
+          const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
+          if (t2 < p.total_tiles) issue_m1(i + 2);
+          t = t1; t1 = t2;
+        }
+      } else {
+        if (tile0 < p.total_tiles) issue_m1(0);
+        if (tile0 + G < p.total_tiles) issue_m1(1);
+        for (int t = tile0; t < p.total_tiles; t += G, ++i) {
+          mbar_wait(b_e1_done, (uint32_t)(i & 1), 2);        // h slab of tile i is valid, acc1[i & 1] is free
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          issue_m2(i);
+          if (t + 2 * G < p.total_tiles) issue_m1(i + 2);
+        }
       }
     }
   } else if (warp == kWarpLoader) {
@@ -303,7 +344,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       // ===== epilogue-2 input loader (same ring protocol as conv_tc2) =====
       int cnt[2] = {0, 0};
       const int n_items = p.mh * n_epi_chunks;
-      for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
+      for (int t = RAGGED ? tile_first : tile0; t < p.total_tiles; t = RAGGED ? next_tile(t) : t + G) {
         const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
         for (int item = 0; item < n_items; ++item) {
           const int h = item / n_epi_chunks, cc = item - h * n_epi_chunks;
@@ -453,7 +494,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       }
     };
     int i = 0, prev = -1;
-    for (int t = tile_first; t < p.total_tiles; t = next_tile(t), ++i) {
+    for (int t = RAGGED ? tile_first : tile0; t < p.total_tiles; t = RAGGED ? next_tile(t) : t + G, ++i) {
       epilogue1(t, i);
       if (prev >= 0) epilogue2(prev, i - 1);
       prev = t;

@@ -33,13 +33,17 @@ cudaError_t conv_tc2_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_tc2_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_tc2_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+  const auto set = [](auto kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
+  };
+  if ((e = set(conv_tc2_kernel<__nv_bfloat16, false, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<__nv_bfloat16, false, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<float, false, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<float, false, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<__nv_bfloat16, true, false>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<__nv_bfloat16, true, true>)) != cudaSuccess) return e;
+  if ((e = set(conv_tc2_kernel<float, true, false>)) != cudaSuccess) return e;
+  return set(conv_tc2_kernel<float, true, true>);
 }
 
 // Diagnostics: how many 2-CTA clusters of conv_tc2_kernel<bf16> can be resident with `smem_bytes` of dynamic
@@ -54,7 +58,7 @@ const char* conv_tc2_cluster_probe(int smem_bytes, int grid, int* max_clusters) 
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   *max_clusters = -1;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(max_clusters, conv_tc2_kernel<__nv_bfloat16, true>, &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(max_clusters, conv_tc2_kernel<__nv_bfloat16, true, false>, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); return cudaGetErrorString(e); }
   return "";
 }
@@ -306,12 +310,17 @@ cudaError_t launch_conv_tc2(const ConvTc2Launch& L, const int* lengths, cudaStre
   ConvTc2Params p = L.p;
   p.ep.lengths = lengths;
   const ConvTc2Maps* dm = L.d_maps;
+  // the RAGGED instantiation (dead tiles skipped) only when the batch carries lengths: the dense walk stays as it was
+  const auto go = [&](auto dense, auto ragged, bool pair) {
+    return lengths ? launch_persistent(ragged, L.grid, L.smem_bytes, st, pair, dm, p)
+                   : launch_persistent(dense, L.grid, L.smem_bytes, st, pair, dm, p);
+  };
   if (!p.cta2) {
-    if (L.elem_bytes == 2) return launch_persistent(conv_tc2_kernel<__nv_bfloat16, false>, L.grid, L.smem_bytes, st, false, dm, p);
-    return launch_persistent(conv_tc2_kernel<float, false>, L.grid, L.smem_bytes, st, false, dm, p);
+    if (L.elem_bytes == 2) return go(conv_tc2_kernel<__nv_bfloat16, false, false>, conv_tc2_kernel<__nv_bfloat16, false, true>, false);
+    return go(conv_tc2_kernel<float, false, false>, conv_tc2_kernel<float, false, true>, false);
   }
-  if (L.elem_bytes == 2) return launch_persistent(conv_tc2_kernel<__nv_bfloat16, true>, L.grid, L.smem_bytes, st, true, dm, p);
-  return launch_persistent(conv_tc2_kernel<float, true>, L.grid, L.smem_bytes, st, true, dm, p);
+  if (L.elem_bytes == 2) return go(conv_tc2_kernel<__nv_bfloat16, true, false>, conv_tc2_kernel<__nv_bfloat16, true, true>, true);
+  return go(conv_tc2_kernel<float, true, false>, conv_tc2_kernel<float, true, true>, true);
 }
 
 }  // namespace gnv

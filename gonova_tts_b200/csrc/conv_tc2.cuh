@@ -192,6 +192,13 @@ __device__ __forceinline__ void pdl_wait_then_release() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// elect.sync: one lane of a converged warp; ptxas knows the guarded block runs in a single thread
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct Ring {
   int slot = 0;
   uint32_t phase = 0;
@@ -361,7 +368,7 @@ __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab,
 
 // CTA2 = true: CTA pairs (cluster of two).  A separate instantiation, because a kernel image that contains
 // cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
-template <typename E, bool CTA2>
+template <typename E, bool CTA2, bool RAGGED>
 __global__ void __launch_bounds__(384, 1)
 conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ ConvTc2Params p) {
   using namespace tc2;
@@ -442,11 +449,12 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   const int rows_per_cta = BLOCK_M * p.mh;
   const int rows_per_tile = rows_per_cta * (CTA2 ? 2 : 1);   // a CTA pair's tile: the leader's rows, then the peer's
   const int n_epi_chunks = p.block_n / kEpiCols;
-  // Ragged batches: a tile whose every output row lies kDeadMargin or more rows past its utterance's valid length is
-  // skipped by ALL roles (same predicate, so the barrier sequences stay in step).  Rows in [valid, valid + margin)
-  // are still written (as zeros): that is the zero padding the next layer's last valid rows read.
+  // Ragged batches (RAGGED instantiation, launched when `lengths` is given): a tile whose every output row lies
+  // kDeadMargin or more rows past its utterance's valid length is skipped by ALL roles (same predicate, so the barrier
+  // sequences stay in step).  Rows in [valid, valid + margin) are still written (as zeros): that is the zero padding the
+  // next layer's last valid rows read.  The dense instantiation compiles to the plain strided walk.
   auto tile_live = [&](int t) -> bool {
-    if (!p.ep.lengths) return true;
+    if constexpr (!RAGGED) return true;
     const int qt = t / p.n_tiles_n;
     const int m_tile = qt % p.tiles_m, b = qt / p.tiles_m;
     const long valid = (long)p.ep.lengths[b] * p.ep.len_mul + p.ep.len_add;
@@ -454,10 +462,11 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     return first_row < valid + kDeadMargin;
   };
   auto next_tile = [&](int t) -> int {
+    if constexpr (!RAGGED) return t + tile_step;
     do { t += tile_step; } while (t < p.total_tiles && !tile_live(t));
     return t;
   };
-  const int tile_first = (tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
+  const int tile_first = (RAGGED && tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
 
   if (warp == kWarpProducer) {
     if (lane == 0) {
@@ -511,8 +520,12 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       }
     }
   } else if (warp == kWarpMma) {
-    if (lane == 0 && crank == 0) {
+    if (crank == 0) {
       // ===== MMA issuer (CTA pair: the leader issues for both CTAs) =====
+      // The WHOLE warp walks the loops (warp-uniform control flow, waits included) and one elected lane issues:
+      // ptxas then keeps descriptors and loop state in uniform registers and emits the UTCHMMAs back to back.  Under
+      // `if (lane == 0)` every MMA was wrapped in an ELECT / BRA.U.ANY loop of its own — and the issue path is on
+      // the critical path of the N <= 128 layers (one extra R2UR per MMA measured 16 % on the k = 11 pairs).
       // Descriptors are built once; per MMA only the 14-bit start-address field moves (low word add).
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW);
       Ring ra, rw, racc;
@@ -529,52 +542,62 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
               const int ng = min(p.w_group, p.slab_tap0[s + 1] - tap);
               mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              for (int g = 0; g < ng; ++g) {
-                const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
-                const uint64_t ad0 = a_slab + (uint64_t)((uint32_t)(p.tap_row[tap + g] - p.slab_row0[s]) * (KBLK_BYTES >> 4));
-                if (p.mh == 2 && !p.a_base_offset_mode) {
-                  // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA
-                  // never queues behind the previous one's accumulate into the same TMEM tile (measured +11 % on
-                  // the N = 64 layers)
-                  const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
-                  const uint32_t acc1 = acc0 + (uint32_t)p.block_n;
+              if (elect_one()) {
+                for (int g = 0; g < ng; ++g) {
+                  const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
+                  const uint64_t ad0 = a_slab + (uint64_t)((uint32_t)(p.tap_row[tap + g] - p.slab_row0[s]) * (KBLK_BYTES >> 4));
+                  const uint32_t ac0 = g == 0 ? accum : 1u;
+                  if (p.mh == 2 && !p.a_base_offset_mode) {
+                    // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA
+                    // never queues behind the previous one's accumulate into the same TMEM tile (measured +11 % on
+                    // the N = 64 layers)
+                    const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
+                    const uint32_t acc1 = acc0 + (uint32_t)p.block_n;
 #pragma unroll
-                  for (int k = 0; k < KBLK_BYTES / 32; ++k) {
-                    const uint32_t ac = k == 0 ? accum : 1u;
-                    if constexpr (CTA2) {
-                      umma_2sm<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
-                      umma_2sm<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
-                    } else {
-                      umma<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
-                      umma<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                    for (int k = 0; k < KBLK_BYTES / 32; ++k) {
+                      const uint32_t ac = k == 0 ? ac0 : 1u;
+                      if constexpr (CTA2) {
+                        umma_2sm<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
+                        umma_2sm<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                      } else {
+                        umma<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
+                        umma<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                      }
                     }
-                  }
-                } else {
-                  for (int h = 0; h < p.mh; ++h) {
-                    uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
-                    if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
-                    const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
-                    if constexpr (CTA2) {
-                      umma_2sm<E>(acc, ad, bd, p.idesc, accum);
+                  } else {
+                    for (int h = 0; h < p.mh; ++h) {
+                      uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
+                      if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
+                      const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
+                      if constexpr (CTA2) {
+                        umma_2sm<E>(acc, ad, bd, p.idesc, ac0);
 #pragma unroll
-                      for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
-                    } else {
-                      umma<E>(acc, ad, bd, p.idesc, accum);
+                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                      } else {
+                        umma<E>(acc, ad, bd, p.idesc, ac0);
 #pragma unroll
-                      for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                      }
                     }
                   }
                 }
-                accum = 1u;
+                if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
               }
-              if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
+              __syncwarp();
+              accum = 1u;
               rw.advance(p.sw);
             }
-            if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
+            if (elect_one()) {
+              if constexpr (CTA2) umma_commit_2sm(b_a_empty + 8u * ra.slot); else umma_commit(b_a_empty + 8u * ra.slot);
+            }
+            __syncwarp();
             ra.advance(p.sa);
           }
         }
-        if constexpr (CTA2) umma_commit_2sm(b_acc_full + 8u * racc.slot); else umma_commit(b_acc_full + 8u * racc.slot);
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_2sm(b_acc_full + 8u * racc.slot); else umma_commit(b_acc_full + 8u * racc.slot);
+        }
+        __syncwarp();
         racc.advance(p.acc_bufs);
       }
     }
