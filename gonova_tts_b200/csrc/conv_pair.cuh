@@ -167,22 +167,26 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
   }
 
   if (warp == kWarpProducer) {
-    if (lane == 0) {
+    {
       // ===== TMA producer: x slabs + W1 tile groups for M1, W2 tile groups for M2, in the issuer's order =====
+      // (whole warp in the loops, one elected lane issues)
       Ring ra, rw;
       auto load_w_groups = [&](const CUtensorMap* wm, int ch) {
         for (int tap = 0; tap < p.k; tap += p.w_group) {
           const int ng = min(p.w_group, p.k - tap);
           mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
-          if (crank == 0) mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes) * kSub);
-          for (int g = 0; g < ng; ++g) {
-            if constexpr (CTA2)   // this CTA's half of the weight rows, completing on the leader's barrier
-              tma_load_2d_2sm(wm, (b_w_full + 8u * rw.slot) & kPeerBitMask, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
-                              ((tap + g) * p.n_chunks + ch) * KBE, crank * (p.C >> 1));
-            else
-              tma_load_2d(wm, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
-                          ((tap + g) * p.n_chunks + ch) * KBE, 0);
+          if (elect_one()) {
+            if (crank == 0) mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes) * kSub);
+            for (int g = 0; g < ng; ++g) {
+              if constexpr (CTA2)   // this CTA's half of the weight rows, completing on the leader's barrier
+                tma_load_2d_2sm(wm, (b_w_full + 8u * rw.slot) & kPeerBitMask, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                                ((tap + g) * p.n_chunks + ch) * KBE, crank * (p.C >> 1));
+              else
+                tma_load_2d(wm, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
+                            ((tap + g) * p.n_chunks + ch) * KBE, 0);
+            }
           }
+          __syncwarp();
           rw.advance(p.sw);
         }
       };
@@ -192,16 +196,19 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
           const uint32_t dst = sA + ra.slot * p.slab_bytes;
-          if (crank == 0)
-            mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES * kSub);
-          for (int bx = 0; bx < p.a_n_boxes; ++bx) {
-            if constexpr (CTA2)
-              tma_load_3d_2sm(&maps.X, (b_a_full + 8u * ra.slot) & kPeerBitMask,
-                              dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
-            else
-              tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
-                          r0 + bx * p.a_box_rows, b);
+          if (elect_one()) {
+            if (crank == 0)
+              mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES * kSub);
+            for (int bx = 0; bx < p.a_n_boxes; ++bx) {
+              if constexpr (CTA2)
+                tma_load_3d_2sm(&maps.X, (b_a_full + 8u * ra.slot) & kPeerBitMask,
+                                dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
+              else
+                tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
+                            r0 + bx * p.a_box_rows, b);
+            }
           }
+          __syncwarp();
           ra.advance(p.sa);
           load_w_groups(&maps.W1, ch);
         }
@@ -340,8 +347,8 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       }
     }
   } else if (warp == kWarpLoader) {
-    if (lane == 0 && p.n_in > 0) {
-      // ===== epilogue-2 input loader (same ring protocol as conv_tc2) =====
+    if (p.n_in > 0) {
+      // ===== epilogue-2 input loader (same ring protocol as conv_tc2; whole warp, elected lane issues) =====
       int cnt[2] = {0, 0};
       const int n_items = p.mh * n_epi_chunks;
       for (int t = RAGGED ? tile_first : tile0; t < p.total_tiles; t = RAGGED ? next_tile(t) : t + G) {
@@ -353,10 +360,13 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           const int k = cnt[wgi]++;
           const int slot = wgi * p.in_ring + k % p.in_ring;
           mbar_wait(b_in_empty + 8u * slot, (uint32_t)((k / p.in_ring) & 1) ^ 1u, 3);
-          mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
-          for (int j = 0; j < p.n_in; ++j)
-            tma_load_3d(&maps.epi[0][EPI_IN0 + j], b_in_full + 8u * slot,
-                        sIn + (slot * p.n_in + j) * (BLOCK_M * kEpiCols * 4), cc * kEpiCols, mrow, b);
+          if (elect_one()) {
+            mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
+            for (int j = 0; j < p.n_in; ++j)
+              tma_load_3d(&maps.epi[0][EPI_IN0 + j], b_in_full + 8u * slot,
+                          sIn + (slot * p.n_in + j) * (BLOCK_M * kEpiCols * 4), cc * kEpiCols, mrow, b);
+          }
+          __syncwarp();
         }
       }
     }
@@ -455,7 +465,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       fence_async_smem();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if constexpr (CTA2) mbar_arrive_cluster(b_e1_done & kPeerBitMask); else mbar_arrive(b_e1_done);
       }
     };
@@ -488,7 +498,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if constexpr (CTA2) mbar_arrive_cluster((b_acc2_empty + 8u * buf) & kPeerBitMask);
         else mbar_arrive(b_acc2_empty + 8u * buf);
       }
@@ -500,7 +510,7 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       prev = t;
     }
     if (prev >= 0) epilogue2(prev, i - 1);
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

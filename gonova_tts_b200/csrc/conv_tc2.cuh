@@ -263,7 +263,7 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
         }
       }
       __syncwarp();
-      if (c.lane == 0) mbar_arrive(c.b_in_empty + 8u * in_slot);
+      if (elect_one()) mbar_arrive(c.b_in_empty + 8u * in_slot);
       rin.advance(c.in_ring);
     } else if (c.ep->raw_scale != 1.0f) {
 #pragma unroll
@@ -277,7 +277,7 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
     const uint32_t obase = c.obase_wg + ob * c.out_stride;
     // Each WARP stages and stores its own 32 rows of the chunk (its lane 0 owns the bulk-store groups), so the four
     // warps of a warpgroup never wait for each other.
-    if (c.lane == 0) {
+    if (elect_one()) {                                     // (always the same lane: it owns this warp's bulk groups)
       if (c.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
     }
     __syncwarp();
@@ -345,7 +345,7 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
     }
     fence_async_smem();
     __syncwarp();
-    if (c.lane == 0) {
+    if (elect_one()) {
       const int wq = c.erow >> 5;                          // this warp's 32-row quarter of the 128-row chunk
       uint32_t src = obase;
       if (c.has_raw) {
@@ -469,8 +469,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
   const int tile_first = (RAGGED && tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
 
   if (warp == kWarpProducer) {
-    if (lane == 0) {
+    {
       // ===== TMA producer: A slabs and W tile groups, in the order the MMA issuer consumes them =====
+      // (whole warp in the loops, one elected lane issues: see the MMA issuer)
       Ring ra, rw;
       for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         int q = t;
@@ -487,8 +488,9 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
             // a TMA box holds at most 256 rows: taller slabs arrive as two boxes of a_box_rows rows
             // CTA pair: both CTAs' loads complete on the LEADER's barrier, which expects both byte counts
             const uint32_t a_bytes = (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES;
-            if (crank == 0) mbar_expect_tx(b_a_full + 8u * ra.slot, CTA2 ? 2u * a_bytes : a_bytes);
             const int r0 = m0 + p.slab_row0[s];
+            if (elect_one()) {
+            if (crank == 0) mbar_expect_tx(b_a_full + 8u * ra.slot, CTA2 ? 2u * a_bytes : a_bytes);
             for (int bx = 0; bx < p.a_n_boxes; ++bx) {
               if constexpr (CTA2)
                 tma_load_3d_2sm(&maps.A, (b_a_full + 8u * ra.slot) & kPeerBitMask,
@@ -497,12 +499,15 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
                 tma_load_3d(&maps.A, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
                             r0 + bx * p.a_box_rows, b);
             }
+            }
+            __syncwarp();
             ra.advance(p.sa);
             // weight tiles travel in groups of up to w_group taps per barrier (fewer waits for small tiles)
             for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; tap += p.w_group) {
               const int ng = min(p.w_group, p.slab_tap0[s + 1] - tap);
               mbar_wait(b_w_empty + 8u * rw.slot, rw.phase ^ 1u, 1);
               // CTA pair: w_bytes is this CTA's HALF of the weight tile (rows n0 + crank*block_n/2 ...)
+              if (elect_one()) {
               if (crank == 0) mbar_expect_tx(b_w_full + 8u * rw.slot, (uint32_t)(ng * p.w_bytes) * (CTA2 ? 2u : 1u));
               for (int g = 0; g < ng; ++g) {
                 if constexpr (CTA2)
@@ -513,6 +518,8 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
                   tma_load_2d(&maps.W, b_w_full + 8u * rw.slot, sW + rw.slot * p.w_slot_bytes + g * p.w_bytes,
                               ((tap + g) * p.n_chunks + ch) * KBE, n0);
               }
+              }
+              __syncwarp();
               rw.advance(p.sw);
             }
           }
@@ -602,8 +609,8 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       }
     }
   } else if (warp == kWarpLoader) {
-    if (lane == 0 && p.n_in > 0) {
-      // ===== epilogue-input loader: residual / running-sum tiles -> shared memory =====
+    if (p.n_in > 0) {
+      // ===== epilogue-input loader: residual / running-sum tiles -> shared memory (whole warp, elected lane issues) =====
       // Each warpgroup owns a ring of in_ring slots; chunk i of a tile goes to warpgroup i % 2 (the one that will
       // consume it), so the loader runs in_ring chunks ahead of every warpgroup.
       int cnt[2] = {0, 0};                               // chunks handed to each warpgroup so far
@@ -623,10 +630,13 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
           const int k = cnt[wgi]++;
           const int slot = wgi * p.in_ring + k % p.in_ring;
           mbar_wait(b_in_empty + 8u * slot, (uint32_t)((k / p.in_ring) & 1) ^ 1u, 3);
-          mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
-          for (int i = 0; i < p.n_in; ++i)
-            tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * slot,
-                        sIn + (slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
+          if (elect_one()) {
+            mbar_expect_tx(b_in_full + 8u * slot, (uint32_t)p.n_in * (BLOCK_M * kEpiCols * 4));
+            for (int i = 0; i < p.n_in; ++i)
+              tma_load_3d(&maps.epi[ph][EPI_IN0 + i], b_in_full + 8u * slot,
+                          sIn + (slot * p.n_in + i) * (BLOCK_M * kEpiCols * 4), cbase + cc * kEpiCols, mrow, b);
+          }
+          __syncwarp();
         }
       }
     }
@@ -700,13 +710,13 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       // accumulator drained: hand the TMEM buffer back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         if constexpr (CTA2) mbar_arrive_cluster((b_acc_empty + 8u * racc.slot) & kPeerBitMask);   // the leader's issuer waits for both CTAs
         else mbar_arrive(b_acc_empty + 8u * racc.slot);
       }
       racc.advance(p.acc_bufs);
     }
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
