@@ -243,53 +243,66 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       // whole warp in the loops, one elected lane issues (see conv_tc2_kernel): uniform registers, UTCHMMAs back to back
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW), h_desc0 = umma_desc_sw128(sH);
       Ring ra, rw;
-      // one K block (channel block ch) of a conv: every tap group's weights against row-shifted views of `a_base`
+      // one K block (channel block ch) of a conv: every tap group's weights against row-shifted views of `a_base`.
+      // The issue path is the critical path (tools/mma_issue_bench.cu: an N = 64 MMA retires every 48 cycles when the
+      // issuer keeps up), so descriptors advance by loop-invariant strides — no multiplies, no parameter loads per tap.
+      const uint32_t k_taps = (uint32_t)p.k, w_group = (uint32_t)p.w_group;
+      const uint64_t w_slot_units = (uint64_t)((uint32_t)p.w_slot_bytes >> 4), w_units = (uint64_t)((uint32_t)p.w_bytes >> 4);
+      const uint32_t idesc = p.idesc, colsC = (uint32_t)p.C;
+      const bool alt = p.mma_order == 0 && p.mh == 2;
+      const int mh = p.mh;
       auto issue_taps = [&](uint64_t a_base, int row_step, uint32_t acc0, uint32_t& accum) {
-        for (int tap = 0; tap < p.k; tap += p.w_group) {
-          const int ng = min(p.w_group, p.k - tap);
+        const uint64_t a_step = (uint64_t)((uint32_t)row_step * (KBLK_BYTES >> 4));   // descriptor units per tap
+        uint64_t ad_tap = a_base;
+        for (uint32_t tap = 0; tap < k_taps; tap += w_group) {
+          const uint32_t ng = min(w_group, k_taps - tap);
           mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            for (int g = 0; g < ng; ++g) {
-              const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
-              const uint64_t ad0 = a_base + (uint64_t)((uint32_t)((tap + g) * row_step) * (KBLK_BYTES >> 4));
-              const uint32_t ac0 = g == 0 ? accum : 1u;
+            uint64_t bd = w_desc0 + (uint64_t)rw.slot * w_slot_units;
+            uint64_t ad0 = ad_tap;
+            uint32_t ac0 = accum;
+            for (uint32_t g = 0; g < ng; ++g) {
               // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA never
               // waits for the previous one's accumulate into the same TMEM tile (p.mma_order == 1 keeps the old order)
-              if (p.mma_order == 0 && p.mh == 2) {
+              if (alt) {
                 const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
-                const uint32_t acc1 = acc0 + (uint32_t)p.C;
+                const uint32_t acc1 = acc0 + colsC;
 #pragma unroll
                 for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
                   const uint32_t ac = kk == 0 ? ac0 : 1u;
                   if constexpr (CTA2) {
-                    umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
-                    umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                    umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
+                    umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
                   } else {
-                    umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, p.idesc, ac);
-                    umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, p.idesc, ac);
+                    umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
+                    umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
                   }
                 }
               } else {
-                for (int h = 0; h < p.mh; ++h) {
+                for (int h = 0; h < mh; ++h) {
                   const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
-                  const uint32_t acc = acc0 + (uint32_t)(h * p.C);
+                  const uint32_t acc = acc0 + (uint32_t)h * colsC;
                   if constexpr (CTA2) {
-                    umma_2sm<E>(acc, ad, bd, p.idesc, ac0);
+                    umma_2sm<E>(acc, ad, bd, idesc, ac0);
 #pragma unroll
-                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
                   } else {
-                    umma<E>(acc, ad, bd, p.idesc, ac0);
+                    umma<E>(acc, ad, bd, idesc, ac0);
 #pragma unroll
-                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc, 1u);
+                    for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
                   }
                 }
               }
+              ac0 = 1u;
+              bd += w_units;
+              ad0 += a_step;
             }
             if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
           }
           __syncwarp();
           accum = 1u;
+          ad_tap += (uint64_t)ng * a_step;
           rw.advance(p.sw);
         }
       };

@@ -535,58 +535,67 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
       // the critical path of the N <= 128 layers (one extra R2UR per MMA measured 16 % on the k = 11 pairs).
       // Descriptors are built once; per MMA only the 14-bit start-address field moves (low word add).
       const uint64_t a_desc0 = umma_desc_sw128(sA), w_desc0 = umma_desc_sw128(sW);
+      // loop-invariant strides in descriptor units (16 B): the issue path is the critical path of the N <= 128 layers
+      const uint64_t w_slot_units = (uint64_t)((uint32_t)p.w_slot_bytes >> 4), w_units = (uint64_t)((uint32_t)p.w_bytes >> 4);
+      const uint64_t slab_units = (uint64_t)((uint32_t)p.slab_bytes >> 4);
+      const uint32_t idesc = p.idesc, cols_n = (uint32_t)p.block_n;
+      const bool alt = p.mh == 2 && !p.a_base_offset_mode;
+      const int mh = p.mh, w_group = p.w_group;
       Ring ra, rw, racc;
       for (int t = tile_first; t < p.total_tiles; t = next_tile(t)) {
         mbar_wait(b_acc_empty + 8u * racc.slot, racc.phase ^ 1u, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc0 = tmem_base + (uint32_t)(racc.slot * p.mh * p.block_n);
+        const uint32_t acc0 = tmem_base + (uint32_t)(racc.slot * mh) * cols_n;
         uint32_t accum = 0u;                                   // 0 for the tile's first MMA of each half
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int s = 0; s < p.n_slabs; ++s) {
             mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
-            const uint64_t a_slab = a_desc0 + (uint64_t)((uint32_t)(ra.slot * p.slab_bytes) >> 4);
-            for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; tap += p.w_group) {
-              const int ng = min(p.w_group, p.slab_tap0[s + 1] - tap);
+            const uint64_t a_slab = a_desc0 + (uint64_t)ra.slot * slab_units;
+            const int row0 = p.slab_row0[s];
+            for (int tap = p.slab_tap0[s]; tap < p.slab_tap0[s + 1]; tap += w_group) {
+              const int ng = min(w_group, p.slab_tap0[s + 1] - tap);
               mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               if (elect_one()) {
+                uint64_t bd = w_desc0 + (uint64_t)rw.slot * w_slot_units;
+                uint32_t ac0 = accum;
                 for (int g = 0; g < ng; ++g) {
-                  const uint64_t bd = w_desc0 + (uint64_t)((uint32_t)(rw.slot * p.w_slot_bytes + g * p.w_bytes) >> 4);
-                  const uint64_t ad0 = a_slab + (uint64_t)((uint32_t)(p.tap_row[tap + g] - p.slab_row0[s]) * (KBLK_BYTES >> 4));
-                  const uint32_t ac0 = g == 0 ? accum : 1u;
-                  if (p.mh == 2 && !p.a_base_offset_mode) {
+                  const uint64_t ad0 = a_slab + (uint64_t)((uint32_t)(p.tap_row[tap + g] - row0) * (KBLK_BYTES >> 4));
+                  if (alt) {
                     // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA
                     // never queues behind the previous one's accumulate into the same TMEM tile (measured +11 % on
                     // the N = 64 layers)
                     const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
-                    const uint32_t acc1 = acc0 + (uint32_t)p.block_n;
+                    const uint32_t acc1 = acc0 + cols_n;
 #pragma unroll
                     for (int k = 0; k < KBLK_BYTES / 32; ++k) {
                       const uint32_t ac = k == 0 ? ac0 : 1u;
                       if constexpr (CTA2) {
-                        umma_2sm<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
-                        umma_2sm<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                        umma_2sm<E>(acc0, ad0 + 2u * k, bd + 2u * k, idesc, ac);
+                        umma_2sm<E>(acc1, ad1 + 2u * k, bd + 2u * k, idesc, ac);
                       } else {
-                        umma<E>(acc0, ad0 + 2u * k, bd + 2u * k, p.idesc, ac);
-                        umma<E>(acc1, ad1 + 2u * k, bd + 2u * k, p.idesc, ac);
+                        umma<E>(acc0, ad0 + 2u * k, bd + 2u * k, idesc, ac);
+                        umma<E>(acc1, ad1 + 2u * k, bd + 2u * k, idesc, ac);
                       }
                     }
                   } else {
-                    for (int h = 0; h < p.mh; ++h) {
+                    for (int h = 0; h < mh; ++h) {
                       uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
                       if (p.a_base_offset_mode) ad |= (uint64_t)((((uint32_t)ad & 0x3FFFu) >> 3) & 7u) << 49;
-                      const uint32_t acc = acc0 + (uint32_t)(h * p.block_n);
+                      const uint32_t acc = acc0 + (uint32_t)h * cols_n;
                       if constexpr (CTA2) {
-                        umma_2sm<E>(acc, ad, bd, p.idesc, ac0);
+                        umma_2sm<E>(acc, ad, bd, idesc, ac0);
 #pragma unroll
-                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma_2sm<E>(acc, ad + 2u * k, bd + 2u * k, idesc, 1u);
                       } else {
-                        umma<E>(acc, ad, bd, p.idesc, ac0);
+                        umma<E>(acc, ad, bd, idesc, ac0);
 #pragma unroll
-                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, p.idesc, 1u);
+                        for (int k = 1; k < KBLK_BYTES / 32; ++k) umma<E>(acc, ad + 2u * k, bd + 2u * k, idesc, 1u);
                       }
                     }
                   }
+                  ac0 = 1u;
+                  bd += w_units;
                 }
                 if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
               }

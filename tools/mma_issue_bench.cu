@@ -37,10 +37,12 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 }
 
 // style 0: whole role under `if (lane == 0)`;  style 1: warp-uniform loop, elect_one around the MMAs
-template <int STYLE>
-__global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int groups, int per_group, long long* cycles) {
+template <int STYLE, int NACC>
+__global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cycles) {
+  constexpr int per_group = 8;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t full[4], empty[4];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* base = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -48,6 +50,10 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int groups, in
   for (int i = threadIdx.x; i < (4 * 16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(base)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[i])));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&empty[i])));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -68,24 +74,30 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int groups, in
       if (lane == 0) {
         t0 = clock64();
         for (int g = 0; g < groups; ++g) {
-          for (int i = 0; i < per_group; ++i) {
-            const int acc = i % n_acc;
-            umma(tmem + (uint32_t)(acc * N), a0 + (uint64_t)((g & 3) * 1024 + 2 * (i & 3)), b0 + (uint64_t)(2 * (i & 3)), idesc, (g | (i >= n_acc)) ? 1u : 0u);
-          }
+          const uint64_t ag = a0 + (uint64_t)((g & 3) * 1024);
+#pragma unroll
+          for (int i = 0; i < per_group; ++i)
+            umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | (i >= NACC)) ? 1u : 0u);
         }
         umma_commit(smem_u32(&bar));
         mbar_wait(smem_u32(&bar), 0);
         t1 = clock64();
         cycles[blockIdx.x] = t1 - t0;
       }
-    } else {
+    } else if (STYLE == 2) {
+      // the conv kernels' protocol: per group wait on a "full" barrier (armed by a producer warp that itself waits for
+      // the MMAs' commit on "empty"), fence, elected lane issues 8 MMAs and commits to "empty"
       t0 = clock64();
       for (int g = 0; g < groups; ++g) {
+        const int sl = g & 3;
+        mbar_wait(smem_u32(&full[sl]), (uint32_t)((g >> 2) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          for (int i = 0; i < per_group; ++i) {
-            const int acc = i % n_acc;
-            umma(tmem + (uint32_t)(acc * N), a0 + (uint64_t)((g & 3) * 1024 + 2 * (i & 3)), b0 + (uint64_t)(2 * (i & 3)), idesc, (g | (i >= n_acc)) ? 1u : 0u);
-          }
+          const uint64_t ag = a0 + (uint64_t)((g & 3) * 1024);
+#pragma unroll
+          for (int i = 0; i < per_group; ++i)
+            umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | (i >= NACC)) ? 1u : 0u);
+          umma_commit(smem_u32(&empty[sl]));
         }
         __syncwarp();
       }
@@ -94,6 +106,30 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int n_acc, int groups, in
       mbar_wait(smem_u32(&bar), 0);
       t1 = clock64();
       if (lane == 0) cycles[blockIdx.x] = t1 - t0;
+    } else {
+      t0 = clock64();
+      for (int g = 0; g < groups; ++g) {
+        if (elect_one()) {
+          const uint64_t ag = a0 + (uint64_t)((g & 3) * 1024);
+#pragma unroll
+          for (int i = 0; i < per_group; ++i)
+            umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | (i >= NACC)) ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(smem_u32(&bar));
+      __syncwarp();
+      mbar_wait(smem_u32(&bar), 0);
+      t1 = clock64();
+      if (lane == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+  }
+  if (STYLE == 2 && warp == 2) {
+    for (int g = 0; g < groups; ++g) {
+      const int sl = g & 3;
+      mbar_wait(smem_u32(&empty[sl]), (uint32_t)((g >> 2) & 1) ^ 1u);
+      if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[sl])) : "memory");
+      __syncwarp();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -106,22 +142,30 @@ int main() {
   cudaSetDevice(dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = 4 * 16384 + 32768 + 1024;
-  cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bench<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   long long* d = nullptr;
   cudaMalloc(&d, sms * sizeof(long long));
   std::vector<long long> h(sms);
   const int groups = 512, per_group = 8;
   printf("tcgen05.mma kind::f16 M=128 K=16 SS, %d CTAs, %d MMAs each; cycles per MMA (median over CTAs)\n", sms, groups * per_group);
-  printf("%6s %6s %22s %22s %10s\n", "N", "accs", "lane0-if (ELECT loops)", "elected lane, uniform", "floor");
+  printf("%6s %6s %22s %22s %22s %10s\n", "N", "accs", "lane0-if (ELECT loops)", "elected lane, uniform", "elected + ring protocol", "floor");
   for (int N : {32, 64, 128, 256}) {
     for (int n_acc : {1, 2}) {
       if (n_acc * N > 512) continue;
-      double res[2];
-      for (int style = 0; style < 2; ++style) {
+      double res[3];
+      for (int style = 0; style < 3; ++style) {
         for (int rep = 0; rep < 2; ++rep) {
-          if (style == 0) bench<0><<<sms, 128, smem>>>(N, n_acc, groups, per_group, d);
-          else bench<1><<<sms, 128, smem>>>(N, n_acc, groups, per_group, d);
+          if (style == 0 && n_acc == 1) bench<0, 1><<<sms, 128, smem>>>(N, groups, d);
+          if (style == 0 && n_acc == 2) bench<0, 2><<<sms, 128, smem>>>(N, groups, d);
+          if (style == 1 && n_acc == 1) bench<1, 1><<<sms, 128, smem>>>(N, groups, d);
+          if (style == 1 && n_acc == 2) bench<1, 2><<<sms, 128, smem>>>(N, groups, d);
+          if (style == 2 && n_acc == 1) bench<2, 1><<<sms, 128, smem>>>(N, groups, d);
+          if (style == 2 && n_acc == 2) bench<2, 2><<<sms, 128, smem>>>(N, groups, d);
           cudaError_t e = cudaDeviceSynchronize();
           if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
         }
@@ -130,7 +174,7 @@ int main() {
         std::sort(v.begin(), v.end());
         res[style] = (double)v[sms / 2] / (groups * per_group);
       }
-      printf("%6d %6d %22.1f %22.1f %10d\n", N, n_acc, res[0], res[1], 128 * N / 256);
+      printf("%6d %6d %22.1f %22.1f %22.1f %10d\n", N, n_acc, res[0], res[1], res[2], 128 * N / 256);
     }
   }
   cudaFree(d);
