@@ -100,6 +100,7 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   p.slab_bytes = (int)up1024((uint32_t)(p.a_n_boxes * p.a_box_rows) * 128u);
   p.w_bytes = (cta2 ? C / 2 : C) * 128;
   p.w_group = std::max(1, std::min(4, 32768 / p.w_bytes));
+  if (const char* v = getenv("GONOVA_PAIR_WGROUP")) p.w_group = std::max(1, std::min(4, atoi(v)));
   p.w_slot_bytes = p.w_group * p.w_bytes;
   p.h_kb_bytes = 128 * mh * 128;
   // conv2's taps read up to k-1 rows past the slab's last K block: keep that inside the allocation

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,7 +39,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
 
 // style 0: whole role under `if (lane == 0)`;  style 1: warp-uniform loop, elect_one around the MMAs
 template <int STYLE, int NACC>
-__global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cycles, int flags = 0) {
   constexpr int per_group = 8;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -91,12 +92,15 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cy
       for (int g = 0; g < groups; ++g) {
         const int sl = g & 3;
         mbar_wait(smem_u32(&full[sl]), (uint32_t)((g >> 2) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!(flags & 1)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint64_t ag = a0 + (uint64_t)((g & 3) * 1024);
+          const int reps = (flags & 2) ? 4 : 1;           // 8 or 32 MMAs per barrier round
+          for (int r = 0; r < reps; ++r) {
 #pragma unroll
-          for (int i = 0; i < per_group; ++i)
-            umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | (i >= NACC)) ? 1u : 0u);
+            for (int i = 0; i < per_group; ++i)
+              umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | r | (i >= NACC)) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&empty[sl]));
         }
         __syncwarp();
@@ -152,31 +156,33 @@ int main() {
   cudaMalloc(&d, sms * sizeof(long long));
   std::vector<long long> h(sms);
   const int groups = 512, per_group = 8;
+  (void)per_group;
   printf("tcgen05.mma kind::f16 M=128 K=16 SS, %d CTAs, %d MMAs each; cycles per MMA (median over CTAs)\n", sms, groups * per_group);
   printf("%6s %6s %22s %22s %22s %10s\n", "N", "accs", "lane0-if (ELECT loops)", "elected lane, uniform", "elected + ring protocol", "floor");
-  for (int N : {32, 64, 128, 256}) {
+  auto run = [&](int style, int n_acc, int N, int flags) -> double {
+    for (int rep = 0; rep < 2; ++rep) {
+      if (style == 0 && n_acc == 1) bench<0, 1><<<sms, 128, smem>>>(N, groups, d);
+      if (style == 0 && n_acc == 2) bench<0, 2><<<sms, 128, smem>>>(N, groups, d);
+      if (style == 1 && n_acc == 1) bench<1, 1><<<sms, 128, smem>>>(N, groups, d);
+      if (style == 1 && n_acc == 2) bench<1, 2><<<sms, 128, smem>>>(N, groups, d);
+      if (style == 2 && n_acc == 1) bench<2, 1><<<sms, 128, smem>>>(N, groups, d, flags);
+      if (style == 2 && n_acc == 2) bench<2, 2><<<sms, 128, smem>>>(N, groups, d, flags);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
+    }
+    cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    std::vector<long long> v(h);
+    std::sort(v.begin(), v.end());
+    return (double)v[sms / 2] / (groups * per_group * ((style == 2 && (flags & 2)) ? 4 : 1));
+  };
+  for (int N : {32, 64, 128, 256})
     for (int n_acc : {1, 2}) {
       if (n_acc * N > 512) continue;
-      double res[3];
-      for (int style = 0; style < 3; ++style) {
-        for (int rep = 0; rep < 2; ++rep) {
-          if (style == 0 && n_acc == 1) bench<0, 1><<<sms, 128, smem>>>(N, groups, d);
-          if (style == 0 && n_acc == 2) bench<0, 2><<<sms, 128, smem>>>(N, groups, d);
-          if (style == 1 && n_acc == 1) bench<1, 1><<<sms, 128, smem>>>(N, groups, d);
-          if (style == 1 && n_acc == 2) bench<1, 2><<<sms, 128, smem>>>(N, groups, d);
-          if (style == 2 && n_acc == 1) bench<2, 1><<<sms, 128, smem>>>(N, groups, d);
-          if (style == 2 && n_acc == 2) bench<2, 2><<<sms, 128, smem>>>(N, groups, d);
-          cudaError_t e = cudaDeviceSynchronize();
-          if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
-        }
-        cudaMemcpy(h.data(), d, sms * sizeof(long long), cudaMemcpyDeviceToHost);
-        std::vector<long long> v(h);
-        std::sort(v.begin(), v.end());
-        res[style] = (double)v[sms / 2] / (groups * per_group);
-      }
-      printf("%6d %6d %22.1f %22.1f %22.1f %10d\n", N, n_acc, res[0], res[1], res[2], 128 * N / 256);
+      printf("%6d %6d %22.1f %22.1f %22.1f %10d\n", N, n_acc, run(0, n_acc, N, 0), run(1, n_acc, N, 0), run(2, n_acc, N, 0), 128 * N / 256);
     }
-  }
+  printf("ring protocol variants, 2 accumulators (cycles per MMA):\n%6s %22s %22s %22s %22s\n", "N", "8 per round", "8, no tcgen05.fence", "32 per round", "32, no fence");
+  for (int N : {64, 128})
+    printf("%6d %22.1f %22.1f %22.1f %22.1f\n", N, run(2, 2, N, 0), run(2, 2, N, 1), run(2, 2, N, 2), run(2, 2, N, 3));
   cudaFree(d);
   return 0;
 }
