@@ -2,6 +2,7 @@
 #include "conv_pair.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -149,6 +150,9 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   }
   p.sa = sa; p.sw = sw; p.n_epi_wg = nob >= 2 ? 2 : 1; p.out_bufs = nob == 4 ? 2 : 1;
   p.in_ring = in_slots / p.n_epi_wg;
+  if (getenv("GONOVA_PAIR_DEBUG"))
+    fprintf(stderr, "[gonova] pair C=%d k=%d mh=%d: x slabs %d x %d B, W ring %d x %d taps (%d B), staging bufs %d, in slots %d, total %zu B\n",
+            C, k, mh, sa, p.slab_bytes, sw, p.w_group, p.w_slot_bytes, nob, in_slots, total(sa, sw, nob));
   uint32_t off = 0;
   p.off_a = off; off += (uint32_t)sa * p.slab_bytes;
   p.off_w = off; off += (uint32_t)sw * p.w_slot_bytes;
