@@ -130,9 +130,11 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
   bool cta2 = false;
   if (!transposed && block_n >= 128 && opt.cta2 != 0) {
     const long pair_tiles = (long)g.B * ((g.M_rows + 255) / 256) * p.n_tiles_n;
-    // measured (B=64, T=500, bf16): pairs win on tensor-bound layers (N = 256: +13 %; N = 128 with K >= 896 and no
-    // residual traffic: +10 %) and lose 5-10 % on the HBM-bound ones (N = 128 conv2 / k = 3, source_downs)
-    const bool tensor_bound = block_n >= 256 || (g.n_taps * g.C_in >= 896 && !ep.res && !ep.raw_accum);
+    // measured (B=64, T=500, bf16): pairs win on tensor / operand-feed bound layers (N = 256: +13 %; N = 128 with
+    // K >= 896 and no residual traffic: +10 %; N = 128 with K >= 1408 even with the residual: +9 %) and lose 5-10 %
+    // on the HBM-bound ones (N = 128 conv2 at k <= 7, k = 3, source_downs)
+    const int K_total = g.n_taps * g.C_in;
+    const bool tensor_bound = block_n >= 256 || (K_total >= 896 && !ep.res && !ep.raw_accum) || K_total >= 1408;
     cta2 = opt.cta2 == 1 || (pair_tiles >= 2L * (opt.max_ctas / 2) && tensor_bound);
   }
   p.cta2 = cta2 ? 1 : 0;
