@@ -259,27 +259,42 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            uint64_t bd = w_desc0 + (uint64_t)rw.slot * w_slot_units;
-            uint64_t ad0 = ad_tap;
-            uint32_t ac0 = accum;
-            for (uint32_t g = 0; g < ng; ++g) {
+            const uint64_t bd_g0 = w_desc0 + (uint64_t)rw.slot * w_slot_units;
+            if (alt) {
+              // All descriptors of the group first, then up to 32 MMAs back to back.  The tensor queue is shallow: while
+              // the issuing thread computes addresses between taps the pipe drains and idles (ncu, B = 64: operand pipe
+              // busy 54 % of the time, the issuer blocked behind it for the same 54 %, address math and waits the rest).
               // k-step outer, half inner: consecutive MMAs alternate between the two accumulators, so an MMA never
-              // waits for the previous one's accumulate into the same TMEM tile (p.mma_order == 1 keeps the old order)
-              if (alt) {
-                const uint64_t ad1 = ad0 + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4));
-                const uint32_t acc1 = acc0 + colsC;
+              // waits for the previous one's accumulate into the same TMEM tile.
+              uint64_t ads[4], bds[4];
 #pragma unroll
-                for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
-                  const uint32_t ac = kk == 0 ? ac0 : 1u;
-                  if constexpr (CTA2) {
-                    umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
-                    umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
-                  } else {
-                    umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
-                    umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
+              for (int g = 0; g < 4; ++g) {
+                ads[g] = ad_tap + (uint64_t)g * a_step;
+                bds[g] = bd_g0 + (uint64_t)g * w_units;
+              }
+              const uint32_t acc1 = acc0 + colsC;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if ((uint32_t)g < ng) {
+                  const uint64_t ad0 = ads[g], ad1 = ads[g] + (uint64_t)(BLOCK_M * (KBLK_BYTES >> 4)), bd = bds[g];
+#pragma unroll
+                  for (int kk = 0; kk < KBLK_BYTES / 32; ++kk) {
+                    const uint32_t ac = (g == 0 && kk == 0) ? accum : 1u;
+                    if constexpr (CTA2) {
+                      umma_2sm<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
+                      umma_2sm<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
+                    } else {
+                      umma<E>(acc0, ad0 + 2u * kk, bd + 2u * kk, idesc, ac);
+                      umma<E>(acc1, ad1 + 2u * kk, bd + 2u * kk, idesc, ac);
+                    }
                   }
                 }
-              } else {
+              }
+            } else {
+              uint64_t bd = bd_g0;
+              uint64_t ad0 = ad_tap;
+              uint32_t ac0 = accum;
+              for (uint32_t g = 0; g < ng; ++g) {
                 for (int h = 0; h < mh; ++h) {
                   const uint64_t ad = ad0 + (uint64_t)(h * BLOCK_M * (KBLK_BYTES >> 4));
                   const uint32_t acc = acc0 + (uint32_t)h * colsC;
@@ -293,10 +308,10 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
                     for (int kk = 1; kk < KBLK_BYTES / 32; ++kk) umma<E>(acc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
                   }
                 }
+                ac0 = 1u;
+                bd += w_units;
+                ad0 += a_step;
               }
-              ac0 = 1u;
-              bd += w_units;
-              ad0 += a_step;
             }
             if constexpr (CTA2) umma_commit_2sm(b_w_empty + 8u * rw.slot); else umma_commit(b_w_empty + 8u * rw.slot);
           }
