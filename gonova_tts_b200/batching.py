@@ -23,16 +23,24 @@ SAMPLES_PER_FRAME = 480
 
 class MicroBatcher:
     def __init__(self, decode_fn: Callable[[torch.Tensor, List[int]], torch.Tensor], max_batch: int = 64,
-                 max_wait_ms: float = 2.0, max_queue: int = 500):
-        if max_batch < 1 or max_queue < 1:
-            raise ValueError("max_batch and max_queue must be positive")
+                 max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 1, workers: int = 1):
+        """pad_frames: the padded batch length is rounded up to a multiple of it (fewer distinct (B, T) shapes for the
+        decoder's launch-plan cache; the extra frames are masked through `lengths` like any other padding).
+        workers: gather / decode / deliver loops running side by side (decode_fn must then be thread-safe): one
+        assembles and hands out its batch on the host while the other's batch is on the GPU."""
+        if max_batch < 1 or max_queue < 1 or pad_frames < 1 or workers < 1:
+            raise ValueError("max_batch, max_queue, pad_frames and workers must be positive")
         self._decode = decode_fn
+        self.pad_frames = pad_frames
         self.max_batch, self.max_wait = max_batch, max_wait_ms / 1e3
         self._q: "queue.Queue[Optional[Tuple[torch.Tensor, Future]]]" = queue.Queue(maxsize=max_queue)
         self.metrics = {"requests": 0, "dropped": 0, "batches": 0, "frames": 0, "padded_frames": 0}
         self._closed = False
-        self._worker = threading.Thread(target=self._run, name="gonova-microbatcher", daemon=True)
-        self._worker.start()
+        self._mlock = threading.Lock()
+        self._workers = [threading.Thread(target=self._run, name=f"gonova-microbatcher-{i}", daemon=True)
+                         for i in range(workers)]
+        for w in self._workers:
+            w.start()
 
     # -- producer side ----------------------------------------------------------------------------
     def submit(self, mel: torch.Tensor) -> Future:
@@ -57,12 +65,14 @@ class MicroBatcher:
             return
         self._closed = True
         self._q.put(None)
-        self._worker.join(timeout)
+        for w in self._workers:
+            w.join(timeout)
 
     # -- worker -----------------------------------------------------------------------------------
     def _gather(self) -> Optional[List[Tuple[torch.Tensor, Future]]]:
         first = self._q.get()
         if first is None:
+            self._q.put(None)                   # every worker must see the stop marker
             return None
         batch = [first]
         deadline = time.monotonic() + self.max_wait
@@ -87,13 +97,14 @@ class MicroBatcher:
             if not live:
                 continue
             lengths = [int(m.shape[1]) for m, _ in live]
-            tmax = max(lengths)
+            tmax = -(-max(lengths) // self.pad_frames) * self.pad_frames
             x = torch.zeros(len(live), 80, tmax, dtype=torch.float32)
             for i, (m, _) in enumerate(live):
                 x[i, :, : m.shape[1]] = m
-            self.metrics["batches"] += 1
-            self.metrics["frames"] += sum(lengths)
-            self.metrics["padded_frames"] += tmax * len(live)
+            with self._mlock:
+                self.metrics["batches"] += 1
+                self.metrics["frames"] += sum(lengths)
+                self.metrics["padded_frames"] += tmax * len(live)
             try:
                 wav = self._decode(x, lengths)
                 if wav.shape[0] != len(live) or wav.shape[1] < tmax * SAMPLES_PER_FRAME:
@@ -106,14 +117,38 @@ class MicroBatcher:
                         f.set_exception(e)
 
 
-def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: int = 500) -> MicroBatcher:
-    """MicroBatcher in front of a B200HiFT: pinned staging, ragged batch through `lengths`, fp32 result on the host."""
+def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 16,
+                max_frames: int = 0, workers: int = 2) -> MicroBatcher:
+    """MicroBatcher in front of a B200HiFT: pinned staging, ragged batch through `lengths` (tiles past an utterance's
+    end are skipped on the device), fp32 result on the host.  max_frames > 0 reserves the workspace for
+    (max_batch, max_frames) once, so launch plans never move."""
     dev = hift.device
+    if max_frames > 0:
+        hift.reserve(max_batch, -(-max_frames // pad_frames) * pad_frames)
+    tls = threading.local()
+
+    def staging(B: int, T: int):
+        """Per worker thread: pinned mel / waveform mirrors, grown on demand and then reused (cudaHostAlloc per batch
+        costs more than the decode)."""
+        need_in, need_out = B * 80 * T, B * T * SAMPLES_PER_FRAME
+        if getattr(tls, "pin_in", None) is None or tls.pin_in.numel() < need_in:
+            tls.pin_in = torch.empty(max(need_in, max_batch * 80 * max(max_frames, T)), dtype=torch.float32).pin_memory()
+        if getattr(tls, "pin_out", None) is None or tls.pin_out.numel() < need_out:
+            tls.pin_out = torch.empty(max(need_out, max_batch * max(max_frames, T) * SAMPLES_PER_FRAME),
+                                      dtype=torch.float32).pin_memory()
+        return tls.pin_in[:need_in].view(B, 80, T), tls.pin_out[:need_out].view(B, T * SAMPLES_PER_FRAME)
 
     def decode(x: torch.Tensor, lengths: Sequence[int]) -> torch.Tensor:
+        B, _, T = x.shape
         with torch.cuda.device(dev):
-            xd = x.pin_memory().to(dev, non_blocking=True)
+            pin_in, pin_out = staging(B, T)
+            pin_in.copy_(x)
+            xd = pin_in.to(dev, non_blocking=True)
             wav, _ = hift.inference(xd, lengths=list(lengths))
-            return wav.cpu()
+            pin_out.copy_(wav, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            done.synchronize()                               # this batch only, not what the other worker queued behind it
+            return pin_out                                   # the batcher clones every caller's slice out of it
 
-    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue)
+    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers)

@@ -100,3 +100,17 @@ def test_full_queue_drops_like_the_reference_and_errors_reach_callers():
         mb.submit(torch.zeros(80, 2))
     with pytest.raises(ValueError):
         MicroBatcher(dec).submit(torch.zeros(79, 2))
+
+
+def test_pad_frames_rounds_the_batch_length_up_and_results_are_unchanged():
+    dec = FakeDecoder()
+    mb = MicroBatcher(dec, max_batch=4, max_wait_ms=20.0, pad_frames=16)
+    futs = [mb.submit(torch.full((80, n), float(n))) for n in (3, 17, 30)]
+    for n, f in zip((3, 17, 30), futs):
+        wav = f.result(timeout=10)
+        assert wav.shape == (n * 480,) and torch.all(wav == float(n))
+    mb.close()
+    for shape, lengths in dec.batches:
+        assert shape[2] % 16 == 0 and shape[2] >= max(lengths) and shape[2] - max(lengths) < 16
+    with pytest.raises(ValueError):
+        MicroBatcher(dec, pad_frames=0)
