@@ -36,6 +36,7 @@ class MicroBatcher:
         self._q: "queue.Queue[Optional[Tuple[torch.Tensor, Future]]]" = queue.Queue(maxsize=max_queue)
         self.metrics = {"requests": 0, "dropped": 0, "batches": 0, "frames": 0, "padded_frames": 0}
         self._closed = False
+        self._busy = 0                          # workers currently inside decode_fn
         self._mlock = threading.Lock()
         self._workers = [threading.Thread(target=self._run, name=f"gonova-microbatcher-{i}", daemon=True)
                          for i in range(workers)]
@@ -75,9 +76,13 @@ class MicroBatcher:
             self._q.put(None)                   # every worker must see the stop marker
             return None
         batch = [first]
-        deadline = time.monotonic() + self.max_wait
+        # Wait for company only while another batch is being decoded: those requests could not start any earlier.
+        # With the decoder idle, take what is already queued and go (a lone request pays no batching delay).
+        deadline = time.monotonic() + (self.max_wait if self._busy > 0 else 0.0)
         while len(batch) < self.max_batch:
             left = deadline - time.monotonic()
+            if left > 0 and self._busy == 0:
+                left = 0.0                      # the decoder went idle while we were waiting
             try:
                 item = self._q.get(timeout=left) if left > 0 else self._q.get_nowait()
             except queue.Empty:
@@ -106,7 +111,13 @@ class MicroBatcher:
                 self.metrics["frames"] += sum(lengths)
                 self.metrics["padded_frames"] += tmax * len(live)
             try:
-                wav = self._decode(x, lengths)
+                with self._mlock:
+                    self._busy += 1
+                try:
+                    wav = self._decode(x, lengths)
+                finally:
+                    with self._mlock:
+                        self._busy -= 1
                 if wav.shape[0] != len(live) or wav.shape[1] < tmax * SAMPLES_PER_FRAME:
                     raise RuntimeError(f"decode_fn returned {tuple(wav.shape)} for a batch of {len(live)} x {tmax} frames")
                 for i, (_, f) in enumerate(live):
@@ -125,18 +136,26 @@ def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: 
     dev = hift.device
     if max_frames > 0:
         hift.reserve(max_batch, -(-max_frames // pad_frames) * pad_frames)
-    tls = threading.local()
+    # Pinned mel / waveform mirrors, one pair per worker thread, reused for every batch (cudaHostAlloc per batch costs
+    # more than the decode).  With max_frames given they are allocated here, not in the middle of the traffic.
+    def alloc(frames: int):
+        return [torch.empty(max_batch * 80 * frames, dtype=torch.float32).pin_memory(),
+                torch.empty(max_batch * frames * SAMPLES_PER_FRAME, dtype=torch.float32).pin_memory()]
+
+    padded_max = -(-max_frames // pad_frames) * pad_frames if max_frames > 0 else 0
+    spare = [alloc(padded_max) for _ in range(workers)] if padded_max else []
+    by_thread, slock = {}, threading.Lock()
 
     def staging(B: int, T: int):
-        """Per worker thread: pinned mel / waveform mirrors, grown on demand and then reused (cudaHostAlloc per batch
-        costs more than the decode)."""
+        tid = threading.get_ident()
+        with slock:
+            st = by_thread.get(tid)
+            if st is None:
+                st = by_thread[tid] = spare.pop() if spare else alloc(max(T, 1))
         need_in, need_out = B * 80 * T, B * T * SAMPLES_PER_FRAME
-        if getattr(tls, "pin_in", None) is None or tls.pin_in.numel() < need_in:
-            tls.pin_in = torch.empty(max(need_in, max_batch * 80 * max(max_frames, T)), dtype=torch.float32).pin_memory()
-        if getattr(tls, "pin_out", None) is None or tls.pin_out.numel() < need_out:
-            tls.pin_out = torch.empty(max(need_out, max_batch * max(max_frames, T) * SAMPLES_PER_FRAME),
-                                      dtype=torch.float32).pin_memory()
-        return tls.pin_in[:need_in].view(B, 80, T), tls.pin_out[:need_out].view(B, T * SAMPLES_PER_FRAME)
+        if st[0].numel() < need_in or st[1].numel() < need_out:      # a longer batch than planned for: grow
+            st[:] = alloc(max(T, padded_max))
+        return st[0][:need_in].view(B, 80, T), st[1][:need_out].view(B, T * SAMPLES_PER_FRAME)
 
     def decode(x: torch.Tensor, lengths: Sequence[int]) -> torch.Tensor:
         B, _, T = x.shape

@@ -88,12 +88,16 @@ def test_full_queue_drops_like_the_reference_and_errors_reach_callers():
     first.result(timeout=5)
     mb.close()
 
-    dec = FakeDecoder(fail_on=1)
+    dec = FakeDecoder(fail_on=2, delay=0.1)
     mb = MicroBatcher(dec, max_batch=4, max_wait_ms=20.0)
-    futs = [mb.submit(torch.zeros(80, 2)) for _ in range(3)]
+    lone = mb.submit(torch.zeros(80, 2))                  # decoder idle: goes at once, alone (batch 1)
+    time.sleep(0.02)
+    futs = [mb.submit(torch.zeros(80, 2)) for _ in range(3)]   # arrive while batch 1 is decoding: one batch (2), which fails
+    assert lone.result(timeout=5).shape == (960,)
     for f in futs:
         with pytest.raises(RuntimeError, match="exploded"):
             f.result(timeout=5)
+    assert [len(l) for _, l in dec.batches] == [1, 3]
     assert mb.submit(torch.ones(80, 2)).result(timeout=5).shape == (960,)   # the worker survived
     mb.close()
     with pytest.raises(RuntimeError):
@@ -114,3 +118,12 @@ def test_pad_frames_rounds_the_batch_length_up_and_results_are_unchanged():
         assert shape[2] % 16 == 0 and shape[2] >= max(lengths) and shape[2] - max(lengths) < 16
     with pytest.raises(ValueError):
         MicroBatcher(dec, pad_frames=0)
+
+
+def test_a_lone_request_does_not_wait_for_company():
+    dec = FakeDecoder()
+    mb = MicroBatcher(dec, max_batch=64, max_wait_ms=2000.0)
+    t0 = time.monotonic()
+    assert mb.submit(torch.ones(80, 5)).result(timeout=5).shape == (2400,)
+    assert time.monotonic() - t0 < 1.0                    # max_wait only applies while another batch is decoding
+    mb.close()
