@@ -129,3 +129,26 @@ def test_result_does_not_depend_on_workspace_contents(lib, cuda_device, sd, dtyp
             assert torch.equal(alone[0], outs[0][0][0, : n * 480])
         one = dec.decode(mel[b:b + 1, :, :n].contiguous(), outs[0][1][b:b + 1, :, : n * 480].contiguous())
         assert torch.equal(one[0], outs[0][0][b, : n * 480]), (b, n)
+
+
+def test_out_of_range_lengths_are_clamped_not_trusted(lib, cuda_device, sd):
+    """`lengths` is device data the C ABI cannot inspect before launching: 0, negative and too-large entries behave as
+    clamp(lengths, 0, T) — a silent row for 0, the whole row for > T — and never touch memory outside the batch."""
+    from gonova_tts_b200 import B200HiFT
+
+    dec = B200HiFT(sd, device=cuda_device, dtype="bf16")
+    T = 24
+    mel = R.synthetic_mel(4, T, seed=31).to(cuda_device)
+    g = torch.Generator().manual_seed(32)
+    s = (torch.rand(4, 1, T * 480, generator=g) * 0.2 - 0.1).to(cuda_device)
+    guard = torch.full((1 << 20,), 7.0, device=cuda_device)              # allocated next to the outputs
+    wav = dec.decode(mel, s, lengths=[0, -5, 1000, 7])
+    torch.cuda.synchronize()
+    assert torch.isfinite(wav).all() and torch.all(guard == 7.0)
+    assert not wav[0].any() and not wav[1].any()
+    full = dec.decode(mel[2:3].contiguous(), s[2:3].contiguous())
+    assert torch.equal(wav[2], full[0])
+    part = dec.decode(mel[3:4, :, :7].contiguous(), s[3:4, :, : 7 * 480].contiguous())
+    assert torch.equal(wav[3, : 7 * 480], part[0]) and not wav[3, 7 * 480:].any()
+    w2, s2 = dec.inference(mel, lengths=[0, -5, 1000, 7], seed=4)
+    assert torch.isfinite(w2).all() and torch.isfinite(s2).all() and not w2[0].any() and not w2[1].any()
