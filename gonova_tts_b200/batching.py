@@ -23,13 +23,17 @@ SAMPLES_PER_FRAME = 480
 
 class MicroBatcher:
     def __init__(self, decode_fn: Callable[[torch.Tensor, List[int]], torch.Tensor], max_batch: int = 64,
-                 max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 1, workers: int = 1):
+                 max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 1, workers: int = 1,
+                 pad_batch: int = 1):
         """pad_frames: the padded batch length is rounded up to a multiple of it (fewer distinct (B, T) shapes for the
         decoder's launch-plan cache; the extra frames are masked through `lengths` like any other padding).
+        pad_batch: the batch is filled up to a multiple of it with zero-length rows (`lengths` 0: the decoder skips them),
+        again for fewer distinct shapes.
         workers: gather / decode / deliver loops running side by side (decode_fn must then be thread-safe): one
         assembles and hands out its batch on the host while the other's batch is on the GPU."""
-        if max_batch < 1 or max_queue < 1 or pad_frames < 1 or workers < 1:
-            raise ValueError("max_batch, max_queue, pad_frames and workers must be positive")
+        if max_batch < 1 or max_queue < 1 or pad_frames < 1 or workers < 1 or pad_batch < 1:
+            raise ValueError("max_batch, max_queue, pad_frames, pad_batch and workers must be positive")
+        self.pad_batch = pad_batch
         self._decode = decode_fn
         self.pad_frames = pad_frames
         self.max_batch, self.max_wait = max_batch, max_wait_ms / 1e3
@@ -103,7 +107,11 @@ class MicroBatcher:
                 continue
             lengths = [int(m.shape[1]) for m, _ in live]
             tmax = -(-max(lengths) // self.pad_frames) * self.pad_frames
-            x = torch.zeros(len(live), 80, tmax, dtype=torch.float32)
+            rows = min(-(-len(live) // self.pad_batch) * self.pad_batch, max(self.max_batch, len(live)))
+            if len(live) == 1:
+                rows = 1                                          # a lone sentence keeps the cheapest shape
+            lengths = lengths + [0] * (rows - len(live))          # filler rows: silent, skipped by the decoder
+            x = torch.zeros(rows, 80, tmax, dtype=torch.float32)
             for i, (m, _) in enumerate(live):
                 x[i, :, : m.shape[1]] = m
             with self._mlock:
@@ -118,8 +126,8 @@ class MicroBatcher:
                 finally:
                     with self._mlock:
                         self._busy -= 1
-                if wav.shape[0] != len(live) or wav.shape[1] < tmax * SAMPLES_PER_FRAME:
-                    raise RuntimeError(f"decode_fn returned {tuple(wav.shape)} for a batch of {len(live)} x {tmax} frames")
+                if wav.shape[0] != rows or wav.shape[1] < tmax * SAMPLES_PER_FRAME:
+                    raise RuntimeError(f"decode_fn returned {tuple(wav.shape)} for a batch of {rows} x {tmax} frames")
                 for i, (_, f) in enumerate(live):
                     f.set_result(wav[i, : lengths[i] * SAMPLES_PER_FRAME].clone())
             except BaseException as e:          # every caller of the batch sees the failure, the worker survives
@@ -129,7 +137,7 @@ class MicroBatcher:
 
 
 def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 16,
-                max_frames: int = 0, workers: int = 2) -> MicroBatcher:
+                max_frames: int = 0, workers: int = 2, pad_batch: int = 4) -> MicroBatcher:
     """MicroBatcher in front of a B200HiFT: pinned staging, ragged batch through `lengths` (tiles past an utterance's
     end are skipped on the device), fp32 result on the host.  max_frames > 0 reserves the workspace for
     (max_batch, max_frames) once, so launch plans never move."""
@@ -170,4 +178,4 @@ def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: 
             done.synchronize()                               # this batch only, not what the other worker queued behind it
             return pin_out                                   # the batcher clones every caller's slice out of it
 
-    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers)
+    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers, pad_batch)

@@ -127,3 +127,17 @@ def test_a_lone_request_does_not_wait_for_company():
     assert mb.submit(torch.ones(80, 5)).result(timeout=5).shape == (2400,)
     assert time.monotonic() - t0 < 1.0                    # max_wait only applies while another batch is decoding
     mb.close()
+
+
+def test_pad_batch_adds_silent_rows_only():
+    dec = FakeDecoder(delay=0.05)
+    mb = MicroBatcher(dec, max_batch=8, max_wait_ms=50.0, pad_batch=4)
+    first = mb.submit(torch.full((80, 2), 9.0))
+    time.sleep(0.01)
+    futs = [mb.submit(torch.full((80, 3), float(i))) for i in range(5)]      # gathered while the first one decodes
+    assert torch.all(first.result(timeout=5) == 9.0)
+    for i, f in enumerate(futs):
+        assert torch.all(f.result(timeout=5) == float(i))
+    mb.close()
+    assert [s[0] for s, _ in dec.batches] == [1, 8]                          # a lone request stays alone, 5 -> 8 rows
+    assert dec.batches[0][1] == [2] and dec.batches[1][1] == [3] * 5 + [0] * 3
