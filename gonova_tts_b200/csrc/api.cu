@@ -266,6 +266,7 @@ ConvTc2Options tc2_options_from_env() {
   if (const char* v = getenv("GONOVA_TC2_CTAS")) o.max_ctas = atoi(v);
   if (const char* v = getenv("GONOVA_TC2_WGROUP")) o.w_group = atoi(v);
   if (const char* v = getenv("GONOVA_TC2_CTA2")) o.cta2 = atoi(v);
+  if (const char* v = getenv("GONOVA_TC2_NARROW")) o.narrow_small = atoi(v);
   if (o.slab_mode < 0 || o.slab_mode > 2) o.slab_mode = 1;
   if (o.max_ctas < 1) o.max_ctas = 148;
   return o;

@@ -117,6 +117,13 @@ const char* make_conv_tc2_launch(ConvTc2Launch* out, int elem_bytes, const void*
     if (ep.up > kMaxPhase) return "conv_tc2: too many polyphase phases";
   } else {
     block_n = g.N_total <= 256 ? g.N_total : 256;
+    // Small problems (one sentence, a first chunk): narrower tiles, so that the weight stream and the k loop of a
+    // layer spread over more SMs instead of 2-8 CTAs walking all of K alone (latency, not throughput, is the metric)
+    long tiles = (long)g.B * ((g.M_rows + 127) / 128) * (g.N_total / block_n);
+    while (opt.narrow_small && block_n >= 128 && tiles * 2 <= opt.max_ctas && g.N_total % (block_n / 2) == 0) {
+      block_n /= 2;
+      tiles *= 2;
+    }
   }
   if (block_n % kEpiCols || block_n < 32 || block_n > 256) return "conv_tc2: N tile must be a multiple of 32 in [32,256]";
   if (g.N_total % block_n) return "conv_tc2: N_total must be a multiple of the N tile";

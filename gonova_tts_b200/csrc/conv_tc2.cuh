@@ -808,6 +808,7 @@ struct ConvTc2Options {
   int w_group = 0;       // 0 = choose (taps per weight barrier)
   int cta2 = -1;         // CTA pairs: -1 = choose, 0 = never, 1 = whenever the layer allows it
   int max_ctas = 148;
+  int narrow_small = 1;  // halve the N tile (down to 64) while the layer has fewer tiles than half the SMs
 };
 
 // `act` = A tensor [B, L_in, C_in_ld] (E); `w` = packed weights [w_rows_alloc, n_taps*C_in_ld] (E).
