@@ -16,6 +16,8 @@ CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libgonova_hift.so"
 INCLUDE = PKG.parent / "include"
+C_HOST_SRC = PKG.parent / "examples" / "c_host.c"
+C_HOST = LIBDIR / "hift_c_host"          # plain-C host over the C ABI (tests/test_gpu_c_host.py)
 
 SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "aux_kernels.cu"]
 NVCC_FLAGS = [
@@ -35,7 +37,10 @@ def _stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h"))
+    deps = (list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(INCLUDE.glob("*.h")) +
+            [C_HOST_SRC])
+    if not C_HOST.exists():
+        return True
     return any(p.stat().st_mtime > t for p in deps)
 
 
@@ -66,7 +71,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB)
+    build_c_host()
     return LIB
+
+
+def build_c_host() -> Path:
+    """examples/c_host.c -> lib/hift_c_host: gcc, the C ABI header, libcudart and the library; no C++ and no torch."""
+    cuda_home = Path(_nvcc()).resolve().parent.parent
+    cc = shutil.which("gcc") or "cc"
+    cmd = [cc, "-O2", "-std=c11", "-Wall", "-Wextra", "-I", str(INCLUDE), "-I", str(cuda_home / "include"),
+           str(C_HOST_SRC), "-o", str(C_HOST), "-L", str(LIBDIR), "-lgonova_hift", "-L", str(cuda_home / "lib64"),
+           "-lcudart", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + str(cuda_home / "lib64")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"building {C_HOST_SRC.name} failed:\n{r.stdout}\n{r.stderr}")
+    return C_HOST
 
 
 if __name__ == "__main__":

@@ -156,9 +156,12 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
     return (long)(t % p.tiles_m) * kSub * p.Mo < valid + kDeadMargin;
   };
   auto next_tile = [&](int t) -> int {
-    if constexpr (!RAGGED) return t + G;
-    do { t += G; } while (t < p.total_tiles && !tile_live(t));
-    return t;
+    if constexpr (!RAGGED) {
+      return t + G;
+    } else {
+      do { t += G; } while (t < p.total_tiles && !tile_live(t));
+      return t;
+    }
   };
   int tile_first = tile0, tile_second = tile0;
   if constexpr (RAGGED) {

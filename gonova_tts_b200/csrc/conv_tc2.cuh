@@ -462,9 +462,12 @@ conv_tc2_kernel(const ConvTc2Maps* __restrict__ maps_g, const __grid_constant__ 
     return first_row < valid + kDeadMargin;
   };
   auto next_tile = [&](int t) -> int {
-    if constexpr (!RAGGED) return t + tile_step;
-    do { t += tile_step; } while (t < p.total_tiles && !tile_live(t));
-    return t;
+    if constexpr (!RAGGED) {
+      return t + tile_step;
+    } else {
+      do { t += tile_step; } while (t < p.total_tiles && !tile_live(t));
+      return t;
+    }
   };
   const int tile_first = (RAGGED && tile0 < p.total_tiles && !tile_live(tile0)) ? next_tile(tile0) : tile0;
 

@@ -136,3 +136,20 @@ def fold_state_dict(sd: Dict[str, torch.Tensor], prefix: str = "") -> Dict[str, 
             raise KeyError(f"state dict has no '{bk}'")
         out[bk] = sd[bk].detach().to("cpu", torch.float32).contiguous()
     return out
+
+
+def write_flat(sd: Dict[str, torch.Tensor], path: str, prefix: str = "") -> int:
+    """Folded weights as one flat binary file for hosts that are not Python (examples/c_host.c):
+    int32 n; per tensor: int32 name_len, name, int32 ndim, int64 shape[ndim], float32 data (little endian)."""
+    import struct
+
+    folded = fold_state_dict(sd, prefix=prefix)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", len(folded)))
+        for name in sorted(folded):
+            t = folded[name].detach().to(torch.float32).contiguous().cpu()
+            nb = name.encode()
+            f.write(struct.pack("<i", len(nb)) + nb + struct.pack("<i", t.dim()))
+            f.write(struct.pack("<%dq" % t.dim(), *t.shape))
+            f.write(t.numpy().tobytes())
+    return len(folded)
