@@ -230,6 +230,8 @@ struct gnv_decoder {
   int fuse_max_c = 64;      // ... for stages with at most this many channels.  Measured (B=64, T=500, bf16): C=64
                             // pairs are 5-28 % faster fused; C=128 pairs must drop to 128-row tiles to fit TMEM
                             // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
+  int fuse_k3_max_c = 64;   // ... and for k = 3 ResBlocks up to this many channels (GONOVA_FUSE_K3_MAX_C).  Measured at C = 128:
+                            // the three fused k = 3 pairs take 1.51 ms against 1.59 ms in six launches, the step does not move
   std::map<std::pair<int, int>, int> launch_counts;   // (B, T) -> conv launches of the last plan built
   ConvTc2Options tc2opt;
   int snake_kind = ACT_SNAKE;
@@ -627,7 +629,8 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
         }
         // ---- fused: one kernel, the intermediate stays in shared memory.  The step reads `cur` with a
         // halo while other tiles write the successor's input, so input and output ping-pong (cur <-> E3).
-        if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() && kStageC[i] <= h->fuse_max_c) {
+        if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() &&
+            (kStageC[i] <= h->fuse_max_c || (kStageC[i] <= h->fuse_k3_max_c && R.c1[d].k == 3))) {
           EpiSpec ef = es;
           void* out_buf = (cur == E[3]) ? EA : E[3];
           if (has_next) {
@@ -887,6 +890,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   h->tc2opt = tc2_options_from_env();
   if (const char* v = getenv("GONOVA_FUSE_PAIRS")) h->fuse_pairs = atoi(v) != 0;
   if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
+  if (const char* v = getenv("GONOVA_FUSE_K3_MAX_C")) h->fuse_k3_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_PAIR_CTA2")) h->pair_cta2 = atoi(v);
   if (const char* v = getenv("GONOVA_MAX_PLANS")) h->max_plans = (size_t)(atoi(v) > 0 ? atoi(v) : 1);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
