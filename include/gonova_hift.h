@@ -87,7 +87,10 @@ int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed,
 
 /* replaces: HiFTGenerator.decode(x=mel, s=s).  lengths [B] (int32, mel frames, device) or NULL
  * for a rectangular batch; rows past an utterance's length decode as if the utterance ended
- * there and come back as zeros. */
+ * there and come back as zeros: every row of a ragged batch is bit-identical to that utterance
+ * decoded alone, and the work past its end is skipped, not computed and discarded.  Entries are
+ * read as clamp(lengths[b], 0, T) (0 = a silent filler row).  The workspace is pure scratch: its
+ * contents before the call do not matter and nothing in it survives the call. */
 int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* lengths,
                int B, int T, float* wav, void* workspace, size_t workspace_bytes, void* stream);
 
