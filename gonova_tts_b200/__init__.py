@@ -5,12 +5,12 @@ sm_100a CUDA (tcgen05/TMEM/TMA conv GEMMs, fused STFT / iSTFT+OLA / PCM-tail ker
 ABI in include/gonova_hift.h.  No CPU fallback: importing works anywhere, running needs the built
 library and a B200."""
 from .decoder import B200HiFT, SAMPLES_PER_FRAME, fade_window, mulaw_encode, pcm_tail, trim_fade_window  # noqa: F401
-from .streaming import GraphedInference, StreamingDecoder, chunk_plan  # noqa: F401
+from .streaming import GraphedInference, IncrementalDecoder, StreamingDecoder, chunk_plan  # noqa: F401
 from .dispatch import ShardedDecoder, round_robin, shard_range  # noqa: F401
 from .batching import MicroBatcher  # noqa: F401
 from .weights import fold_state_dict, random_state_dict  # noqa: F401
 
 __all__ = [
-    "B200HiFT", "StreamingDecoder", "GraphedInference", "MicroBatcher", "ShardedDecoder", "pcm_tail", "mulaw_encode", "fade_window", "trim_fade_window",
+    "B200HiFT", "StreamingDecoder", "IncrementalDecoder", "GraphedInference", "MicroBatcher", "ShardedDecoder", "pcm_tail", "mulaw_encode", "fade_window", "trim_fade_window",
     "chunk_plan", "shard_range", "round_robin", "fold_state_dict", "random_state_dict", "SAMPLES_PER_FRAME",
 ]

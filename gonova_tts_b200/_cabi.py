@@ -20,7 +20,7 @@ SYMBOLS = [
     "gnv_create", "gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_workspace_bytes", "gnv_f0",
     "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_pcm_mulaw", "gnv_stft", "gnv_istft", "gnv_conv1d",
     "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
-    "gnv_plan_stats",
+    "gnv_plan_stats", "gnv_source_stream",
 ]
 
 
@@ -74,6 +74,7 @@ def load():
     lib.gnv_decode_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_inference_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_plan_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.gnv_source_stream.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, vp, f32p, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("gnv_destroy", "gnv_last_error", "gnv_abi_version"):

@@ -969,6 +969,16 @@ int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed, const
   return 0;
 }
 
+int gnv_source_stream(gnv_handle h, const float* f0, int B, int T, uint64_t seed, int64_t sample0, const double* f0_sum0,
+                      float* s, double* f0_sum_out, void* stream) {
+  if (!h || !f0 || !s) return fail(h, "NULL argument");
+  if (B <= 0 || T <= 0 || sample0 < 0) return fail(h, "B and T must be positive, sample0 non-negative");
+  DeviceGuard dg(h->device);
+  GNV_CK(h, "source", launch_source(f0, B, T, seed, nullptr, nullptr, h->lin_w, h->lin_b, s, (cudaStream_t)stream,
+                                    f0_sum0, (long long)sample0, f0_sum_out));
+  return 0;
+}
+
 int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* lengths, int B, int T, float* wav,
                void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !mel || !s || !wav) return fail(h, "NULL argument");

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
                                                       const float* __restrict__ phase_vec,
                                                       const float* __restrict__ noise,
                                                       const float* __restrict__ lin_w,
-                                                      const float* __restrict__ lin_b, float* __restrict__ s) {
+                                                      const float* __restrict__ lin_b, float* __restrict__ s,
+                                                      const double* __restrict__ f0_sum0, long long sample0) {
   __shared__ double red[8];
   __shared__ double base_s[kSrcFramesPerBlock];
   __shared__ float f0_s[kSrcFramesPerBlock];
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double acc = 0.0;
+    double acc = f0_sum0 ? f0_sum0[b] : 0.0;             // streaming: sum of f0 over the frames already emitted
     for (int i = 0; i < 8; ++i) acc += red[i];
     acc /= 50.0;                                         // 480 / 24000 per frame
     for (int i = 0; i < kSrcFramesPerBlock; ++i) {
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         uint32_t r[4];
-        philox4x32_10((uint32_t)n, (uint32_t)(n >> 32) ^ ((uint32_t)b << 8), (uint32_t)g, 0u, (uint32_t)seed,
+        const unsigned long long na = (unsigned long long)n + (unsigned long long)sample0;   // absolute sample index
+        philox4x32_10((uint32_t)na, (uint32_t)(na >> 32) ^ ((uint32_t)b << 8), (uint32_t)g, 0u, (uint32_t)seed,
                       (uint32_t)(seed >> 32), r);
         const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
         float s0, c0, s1, c1;
@@ -215,10 +217,32 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
   }
 }
 
+// f0_sum_out[b] = (f0_sum0 ? f0_sum0[b] : 0) + sum_t f0[b, t]   (fp64: the running phase a stream carries between pushes)
+__global__ void __launch_bounds__(256) f0_sum_kernel(const float* __restrict__ f0, int T, const double* __restrict__ f0_sum0,
+                                                     double* __restrict__ f0_sum_out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  double part = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) part += (double)f0[(size_t)b * T + t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = f0_sum0 ? f0_sum0[b] : 0.0;
+    for (int i = 0; i < 8; ++i) acc += red[i];
+    f0_sum_out[b] = acc;
+  }
+}
+
 cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
-                          const float* lin_w, const float* lin_b, float* s, cudaStream_t st) {
+                          const float* lin_w, const float* lin_b, float* s, cudaStream_t st, const double* f0_sum0,
+                          long long sample0, double* f0_sum_out) {
   dim3 grid((T + kSrcFramesPerBlock - 1) / kSrcFramesPerBlock, B);
-  source_kernel<<<grid, 256, 0, st>>>(f0, T, seed, phase_vec, noise, lin_w, lin_b, s);
+  source_kernel<<<grid, 256, 0, st>>>(f0, T, seed, phase_vec, noise, lin_w, lin_b, s, f0_sum0, sample0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !f0_sum_out) return e;
+  f0_sum_kernel<<<B, 256, 0, st>>>(f0, T, f0_sum0, f0_sum_out);      // after the source kernel: out may alias f0_sum0
   return cudaGetLastError();
 }
 

@@ -208,6 +208,25 @@ class B200HiFT:
         return s
 
     @torch.no_grad()
+    def source_stream(self, f0: torch.Tensor, seed: int, frame0: int,
+                      f0_sum: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The source for frames [frame0, frame0 + T) of a longer utterance (gnv_source_stream): f0 [B, T] of those
+        frames, `f0_sum` [B] float64 = the running sum of f0 over the frames before them (None at frame 0).  Returns
+        (s [B, 1, 480 T], the updated running sum).  Pieces of any size concatenate to `source_from_f0` of the whole."""
+        f0 = self._check_in(f0, "f0")
+        B, T = f0.shape
+        if f0_sum is not None:
+            f0_sum = f0_sum.to(device=self.device, dtype=torch.float64).contiguous()
+            if f0_sum.shape != (B,):
+                raise ValueError("f0_sum must have shape [B]")
+        s = torch.empty(B, 1, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        rc = self._lib.gnv_source_stream(self._h, _ptr(f0), B, T, C.c_uint64(seed), C.c_int64(frame0 * SAMPLES_PER_FRAME),
+                                         _ptr(f0_sum), _ptr(s), _ptr(out), _stream_ptr(self.device))
+        _cabi.check(rc, self._h, "gnv_source_stream")
+        return s, out
+
+    @torch.no_grad()
     def decode(self, x: torch.Tensor, s: torch.Tensor, lengths=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """HiFTGenerator.decode(x=mel [B,80,T], s=source [B,1,480T]) -> wav [B,480T]."""
         x = self._check_in(x, "x")

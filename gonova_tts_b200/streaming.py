@@ -82,6 +82,113 @@ class StreamingDecoder:
         return (torch.cat(i16s, 1) if i16s else None), (torch.cat(f32s, 1) if f32s else None)
 
 
+class IncrementalDecoder:
+    """Intra-sentence streaming: mel frames arrive in pieces of any size (`push`), PCM leaves chunk by
+    chunk as soon as a chunk's look-ahead is there, `finish()` flushes the rest.
+
+    The stream is EXACTLY `StreamingDecoder.stream` of the whole utterance, whatever the piece sizes: same chunk
+    windows (chunk_plan), same crossfade, and the same NSF source — f0 of a frame is final once `f0_ctx` = 5 more
+    frames have arrived (the predictor's receptive field: five k = 3 convs), the source of a piece continues the
+    running phase of the pieces before it (fp64 sum of f0) and draws its noise by absolute sample index
+    (`gnv_source_stream`).  A chunk is emitted when frames up to own_hi + 1 + halo + f0_ctx exist: 22 frames = 0.44 s
+    of look-ahead at the defaults (upstream's token-chunk streaming re-decodes a 50-token context instead and accepts
+    the seam; `cache_source` of HiFTGenerator.inference is the same idea)."""
+
+    def __init__(self, hift: B200HiFT, B: int = 1, chunk: int = 100, halo: int = 16, fade: int = 480, limit: float = 0.99,
+                 seed: int = 1, f0_ctx: int = 5, want_i16: bool = True, want_f32: bool = False, trim_fade: bool = False):
+        if f0_ctx < 5:
+            raise ValueError("f0_ctx must cover the f0 predictor's receptive field (5 frames)")
+        self.hift, self.B = hift, B
+        self.chunk, self.halo, self.fade, self.limit, self.seed, self.f0_ctx = chunk, halo, fade, limit, seed, f0_ctx
+        self.want_i16, self.want_f32, self.trim_fade = want_i16, want_f32, trim_fade
+        self._w = fade_window(fade, hift.device)
+        self._tw = trim_fade_window(hift.device)
+        dev = hift.device
+        self._base = 0                                     # absolute index of the first frame still held
+        self._mel = torch.empty(B, 80, 0, dtype=torch.float32, device=dev)
+        self._s = torch.empty(B, 1, 0, dtype=torch.float32, device=dev)   # source of frames [_base, _f0_done)
+        self._f0_done = 0                                  # frames whose source exists
+        self._f0_sum = None
+        self._next = 0                                     # next chunk to emit
+        self._prev_tail = None
+        self._finished = False
+
+    @property
+    def frames_in(self) -> int:
+        return self._base + self._mel.shape[2]
+
+    @torch.no_grad()
+    def push(self, mel_piece: torch.Tensor):
+        """mel_piece [B, 80, n >= 0] on the decoder's device.  Returns the list of (int16 | None, fp32 | None) chunks
+        that became decodable (often empty)."""
+        if self._finished:
+            raise RuntimeError("the stream was finished")
+        if mel_piece.dim() != 3 or mel_piece.shape[0] != self.B or mel_piece.shape[1] != 80:
+            raise ValueError("mel_piece must be [B, 80, n]")
+        self._mel = torch.cat([self._mel, mel_piece.to(self.hift.device, torch.float32)], dim=2)
+        return self._advance(False)
+
+    @torch.no_grad()
+    def finish(self):
+        """End of the utterance: emits the remaining chunks (the last one without look-ahead, as the offline plan)."""
+        if self._finished:
+            return []
+        self._finished = True
+        return self._advance(True)
+
+    def _advance(self, final: bool):
+        hift, spf = self.hift, SAMPLES_PER_FRAME
+        T_av = self.frames_in
+        # 1. source for the frames whose f0 is final now
+        f_final = T_av if final else max(self._f0_done, T_av - self.f0_ctx)
+        if f_final > self._f0_done:
+            w0 = max(self._base, self._f0_done - self.f0_ctx, 0)
+            w1 = min(T_av, f_final + self.f0_ctx)
+            f0w = hift.predict_f0(self._mel[:, :, w0 - self._base:w1 - self._base].contiguous())
+            f0 = f0w[:, self._f0_done - w0:f_final - w0].contiguous()
+            s_new, self._f0_sum = hift.source_stream(f0, self.seed, self._f0_done, self._f0_sum)
+            self._s = torch.cat([self._s, s_new], dim=2)
+            self._f0_done = f_final
+        # 2. every chunk whose decode window is covered
+        out = []
+        while True:
+            own_lo = self._next * self.chunk
+            if own_lo >= T_av:
+                break
+            own_hi = min(T_av, own_lo + self.chunk)
+            last = final and own_hi >= T_av
+            lo = max(0, own_lo - self.halo)
+            if last:
+                hi = T_av
+            else:
+                hi = own_lo + self.chunk + 1 + self.halo
+                if own_lo + self.chunk > T_av or hi > self._f0_done:
+                    if not final:
+                        break
+                    hi = min(T_av, hi)                     # flushing: a full chunk near the end keeps what look-ahead exists
+            wav = hift.decode(self._mel[:, :, lo - self._base:hi - self._base].contiguous(),
+                              self._s[:, :, (lo - self._base) * spf:(hi - self._base) * spf].contiguous())
+            a = (own_lo - lo) * spf
+            n_emit = (own_hi - own_lo) * spf
+            cur = wav[:, a:a + n_emit]
+            if self._prev_tail is not None:
+                out.append(pcm_tail(cur, self._prev_tail, self._w, self.limit, self.want_i16, self.want_f32))
+            elif self._next == 0 and self.trim_fade:
+                out.append(pcm_tail(cur, None, self._tw, self.limit, self.want_i16, self.want_f32))
+            else:
+                out.append(pcm_tail(cur, None, None, self.limit, self.want_i16, self.want_f32))
+            self._prev_tail = None if last else wav[:, a + n_emit:a + n_emit + self.fade].clone()
+            self._next += 1
+            # frames no later chunk or f0 window needs: drop them
+            keep = max(0, min(self._next * self.chunk - self.halo, self._f0_done - self.f0_ctx))
+            if keep > self._base:
+                d = keep - self._base
+                self._mel = self._mel[:, :, d:].contiguous()
+                self._s = self._s[:, :, d * spf:].contiguous()
+                self._base = keep
+        return out
+
+
 class GraphedInference:
     """inference() + PCM tail for one fixed (B, T), captured once in a CUDA graph and replayed.
 
