@@ -139,6 +139,9 @@ class IncrementalDecoder:
     def _advance(self, final: bool):
         hift, spf = self.hift, SAMPLES_PER_FRAME
         T_av = self.frames_in
+        # nothing on the GPU until the next chunk's look-ahead is complete (a push of one token costs a torch.cat)
+        if not final and T_av - self.f0_ctx < self._next * self.chunk + self.chunk + 1 + self.halo:
+            return []
         # 1. source for the frames whose f0 is final now
         f_final = T_av if final else max(self._f0_done, T_av - self.f0_ctx)
         if f_final > self._f0_done:
