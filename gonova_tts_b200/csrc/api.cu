@@ -107,6 +107,8 @@ struct ConvOp {
   const void* W = nullptr;
   int variant = SV_FFF;
   std::string name;      // upstream module path of the layer ("resblocks.4.convs1.2")
+  int branch = 0;        // 1: source branch (source_downs.i, source_resblocks.i.*): depends on the STFT only
+  int stage = -1;        // upsampling stage of a source-branch op / of ups.i
   double flops = 0.0;    // algorithmic: 2 * B * L_out * C_out * C_in * k (convT: 2 * B * L_in * ...)
 };
 
@@ -246,6 +248,10 @@ struct gnv_decoder {
   size_t max_plans = 64;                            // LRU bound of `plans` (GONOVA_MAX_PLANS); pinned plans do not count out
   unsigned long long tick = 0;
   unsigned long long plans_built = 0, slots_allocated = 0;
+  // small problems: the source branch of every stage runs on a side stream beside conv_pre / the previous stages
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  int fork_max_frames = 1024;                       // B * T up to which the fork is used (GONOVA_FORK_MAX_FRAMES; 0 = never)
   std::mutex mu;
 };
 
@@ -710,6 +716,13 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     add(ops, h->conv_post, X, Lx, es, "conv_post");
   }
   if (!e.empty()) return e;
+  for (ConvOp& op : plan->decode_ops) {
+    for (int i = 0; i < 3; ++i) {
+      const std::string si = std::to_string(i);
+      if (op.name == "source_downs." + si || op.name.rfind("source_resblocks." + si + ".", 0) == 0) { op.branch = 1; op.stage = i; }
+      if (op.name == "ups." + si) op.stage = i;
+    }
+  }
   std::vector<ConvOp*> all;
   for (ConvOp& op : plan->f0_ops) all.push_back(&op);
   for (ConvOp& op : plan->decode_ops) all.push_back(&op);
@@ -824,9 +837,44 @@ int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const
   GNV_CK(h, "stft", launch_stft(s, B, T * kSPF, lengths, ws + w.spec, h->eb, h->dtype == GNV_DTYPE_TF32, h->spec_cs,
                                 kSpecFront, 120 * T + 1 + kSpecFront + kSpecBack, st));
   prof_mark(prof, "stft", GNV_LAUNCH_AUX);
-  for (const ConvOp& op : plan->decode_ops) {
-    GNV_CK(h, "conv", run_op(op, lengths, st));
-    prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
+  // Small problems are bound by the chain of ~75 dependent launches, not by the SMs.  The source branch of a stage
+  // (source_downs.i + source_resblocks.i: 18 launches in all) depends on the STFT only and meets the main path at
+  // ups.i, so it runs on a side stream beside conv_pre and the previous stages' ResBlocks.  Stage buffers are distinct,
+  // and the fork / join events are ordinary stream dependencies, also under stream capture.
+  const bool fork = !prof && h->fork_max_frames > 0 && (long)B * T <= h->fork_max_frames;
+  if (fork) {
+    if (!h->side) {
+      std::lock_guard<std::mutex> lk(h->mu);
+      if (!h->side) {
+        cudaStream_t sd = nullptr;
+        GNV_CK(h, "side stream", cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+        GNV_CK(h, "fork event", cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) GNV_CK(h, "join event", cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+        h->side = sd;
+      }
+    }
+    GNV_CK(h, "fork", cudaEventRecord(h->ev_fork, st));
+    GNV_CK(h, "fork", cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    const size_t n_ops = plan->decode_ops.size();
+    for (size_t k = 0; k < n_ops; ++k) {
+      const ConvOp& op = plan->decode_ops[k];
+      if (op.branch != 1) continue;
+      GNV_CK(h, "conv", run_op(op, lengths, h->side));
+      bool last_of_stage = true;
+      for (size_t m = k + 1; m < n_ops; ++m)
+        if (plan->decode_ops[m].branch == 1 && plan->decode_ops[m].stage == op.stage) { last_of_stage = false; break; }
+      if (last_of_stage) GNV_CK(h, "join", cudaEventRecord(h->ev_join[op.stage], h->side));
+    }
+    for (const ConvOp& op : plan->decode_ops) {
+      if (op.branch == 1) continue;
+      if (op.stage >= 0) GNV_CK(h, "join", cudaStreamWaitEvent(st, h->ev_join[op.stage], 0));   // ups.i adds the source branch
+      GNV_CK(h, "conv", run_op(op, lengths, st));
+    }
+  } else {
+    for (const ConvOp& op : plan->decode_ops) {
+      GNV_CK(h, "conv", run_op(op, lengths, st));
+      prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
+    }
   }
   GNV_CK(h, "istft", launch_istft((const float*)(ws + w.P), B, 120 * T + 1, kPostPitch, lengths, 0.99f, wav, st));
   prof_mark(prof, "istft_head", GNV_LAUNCH_AUX);
@@ -848,6 +896,9 @@ void gnv_destroy(gnv_handle h) {
     DeviceGuard dg(h->device);
     for (auto& kv : h->plans) free_slot(kv.second->slot);
     for (MapsSlot& sl : h->free_slots) free_slot(sl);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < 3; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
     for (void* p : h->allocs) cudaFree(p);
   }
   delete h;
@@ -892,6 +943,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_FUSE_K3_MAX_C")) h->fuse_k3_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_PAIR_CTA2")) h->pair_cta2 = atoi(v);
+  if (const char* v = getenv("GONOVA_FORK_MAX_FRAMES")) h->fork_max_frames = atoi(v);
   if (const char* v = getenv("GONOVA_MAX_PLANS")) h->max_plans = (size_t)(atoi(v) > 0 ? atoi(v) : 1);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
   Uploader up{h};
