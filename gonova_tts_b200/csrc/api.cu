@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -108,7 +109,9 @@ struct ConvOp {
   int variant = SV_FFF;
   std::string name;      // upstream module path of the layer ("resblocks.4.convs1.2")
   int branch = 0;        // 1: source branch (source_downs.i, source_resblocks.i.*): depends on the STFT only
-  int stage = -1;        // upsampling stage of a source-branch op / of ups.i
+  int stage = -1;        // upsampling stage of a source-branch op / of ups.i / of a ResBlock op
+  int rb = -1;           // ResBlock j = 0..2 of its stage (the three run in parallel in fork mode)
+  bool rb_last = false;  // the launch that adds the ResBlock into the stage's running sum: these stay ordered 0, 1, 2
   double flops = 0.0;    // algorithmic: 2 * B * L_out * C_out * C_in * k (convT: 2 * B * L_in * ...)
 };
 
@@ -141,6 +144,7 @@ inline void prof_mark(Profiler* p, const char* name, int kind, double fl = 0.0) 
 struct WsLayout {
   size_t melE = 0, spec = 0, X0 = 0, P = 0, H0 = 0, H1 = 0, f0 = 0;
   size_t F1[3], F2[3], F3[3], E[3][4];
+  size_t F1x[3][2], E3x[3][2];    // fork mode: residual stream / ping-pong buffer of ResBlocks 1 and 2 of a stage (else = F1 / E[3])
   size_t total = 0;
 };
 
@@ -251,6 +255,8 @@ struct gnv_decoder {
   // small problems: the source branch of every stage runs on a side stream beside conv_pre / the previous stages
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t rbs[2] = {nullptr, nullptr};         // ResBlocks 1 and 2 of a stage (ResBlock 0 stays on the caller's stream)
+  cudaEvent_t ev_ups = nullptr, ev_pre[2] = {nullptr, nullptr};
   int fork_max_frames = 1024;                       // B * T up to which the fork is used (GONOVA_FORK_MAX_FRAMES; 0 = never)
   std::mutex mu;
 };
@@ -438,6 +444,11 @@ bool pack_resblock(gnv_handle h, Uploader& up, const WeightMap& wm, const std::s
 }
 
 // ---- workspace ----------------------------------------------------------------------------------
+// Small problems run the independent branches of the decoder on forked streams (run_decode).
+inline bool fork_mode(const gnv_decoder* h, int B, int T) {
+  return h->fork_max_frames > 0 && (long)B * T <= h->fork_max_frames;
+}
+
 WsLayout make_layout(const gnv_decoder* h, int B, int T) {
   WsLayout w;
   size_t off = 0;
@@ -448,6 +459,7 @@ WsLayout make_layout(const gnv_decoder* h, int B, int T) {
   };
   const size_t eb = h->eb;
   const int F = 120 * T + 1;
+  const bool fork = fork_mode(h, B, T);
   w.melE = take((size_t)B * T * h->conv_pre.C_in_ld * eb);
   w.spec = take((size_t)B * (F + kSpecFront + kSpecBack) * h->spec_cs * eb);
   w.X0 = take((size_t)B * T * 512 * eb);
@@ -461,6 +473,10 @@ WsLayout make_layout(const gnv_decoder* h, int B, int T) {
     w.F2[i] = take(n * 4);
     w.F3[i] = take(n * 4);
     for (int j = 0; j < 4; ++j) w.E[i][j] = take(n * eb);
+    for (int j = 0; j < 2; ++j) {
+      w.F1x[i][j] = fork ? take(n * 4) : w.F1[i];
+      w.E3x[i][j] = fork ? take(n * eb) : w.E[i][3];
+    }
   }
   w.total = off;
   return w;
@@ -616,7 +632,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     float *F1 = Fp(w.F1[i]), *F2 = Fp(w.F2[i]), *F3 = Fp(w.F3[i]);
     void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
     auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
-                        int j, const std::string& rbname) {
+                        int j, const std::string& rbname, void* E3) {
       void* cur = EA;                 // the (activated) input of the next dilation step
       for (int d = 0; d < 3; ++d) {
         EpiSpec es; es.len_mul = lm; es.len_add = la;
@@ -638,7 +654,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
         if (h->use_tc && h->tc_version == 2 && h->fuse_pairs && e.empty() &&
             (kStageC[i] <= h->fuse_max_c || (kStageC[i] <= h->fuse_k3_max_c && R.c1[d].k == 3))) {
           EpiSpec ef = es;
-          void* out_buf = (cur == E[3]) ? EA : E[3];
+          void* out_buf = (cur == E3) ? EA : E3;
           if (has_next) {
             ActSpec a = next_act;
             if (!a.out) a.out = out_buf;
@@ -666,7 +682,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
         // ---- two launches: conv1 -> E3, conv2 -> (raw, next act written over the step's own input)
         {
           EpiSpec e1; e1.len_mul = lm; e1.len_add = la;
-          void* mid = (cur == E[3]) ? EA : E[3];
+          void* mid = (cur == E3) ? EA : E3;
           e1.acts.push_back({snake, R.a2[d], 0.f, mid});
           add(ops, R.c1[d], cur, Ls, e1, rbname + ".convs1." + std::to_string(d));
           if (has_next) {
@@ -696,7 +712,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
       }
       if (!done) add(ops, h->sdown[i], spec0 + (size_t)kSpecFront * Cs * h->eb, F, es, nm, Cs, (long long)Fp * Cs);
     }
-    resblock(h->srb[i], E[0], F1, F1, false, 0, "source_resblocks." + std::to_string(i));
+    resblock(h->srb[i], E[0], F1, F1, false, 0, "source_resblocks." + std::to_string(i), E[3]);
     // upsampling + fuse
     {
       EpiSpec es; es.len_mul = lm; es.len_add = la;
@@ -704,8 +720,9 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
       for (int j = 0; j < 3; ++j) es.acts.push_back({snake, h->rb[3 * i + j].a1[0], 0.f, E[j]});
       add(ops, h->ups[i], X, Lx, es, "ups." + std::to_string(i));
     }
-    for (int j = 0; j < 3; ++j)
-      resblock(h->rb[3 * i + j], E[j], F2, F1, true, j, "resblocks." + std::to_string(3 * i + j));
+    for (int j = 0; j < 3; ++j)       // fork mode: every ResBlock of the stage has its own residual stream and ping-pong buffer
+      resblock(h->rb[3 * i + j], E[j], F2, j == 0 ? F1 : Fp(w.F1x[i][j - 1]), true, j, "resblocks." + std::to_string(3 * i + j),
+               j == 0 ? E[3] : P(w.E3x[i][j - 1]));
     X = E[0];
     Lx = Ls;
   }
@@ -721,6 +738,12 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
       const std::string si = std::to_string(i);
       if (op.name == "source_downs." + si || op.name.rfind("source_resblocks." + si + ".", 0) == 0) { op.branch = 1; op.stage = i; }
       if (op.name == "ups." + si) op.stage = i;
+    }
+    if (op.name.rfind("resblocks.", 0) == 0) {
+      const int N = atoi(op.name.c_str() + 10);
+      op.stage = N / 3; op.rb = N % 3;
+      const std::string tail = op.name.substr(op.name.rfind('.') + 1);
+      op.rb_last = tail == "pair2" || (tail == "2" && op.name.find(".convs2.") != std::string::npos);
     }
   }
   std::vector<ConvOp*> all;
@@ -841,34 +864,72 @@ int run_decode(gnv_handle h, Plan* plan, const float* mel, const float* s, const
   // (source_downs.i + source_resblocks.i: 18 launches in all) depends on the STFT only and meets the main path at
   // ups.i, so it runs on a side stream beside conv_pre and the previous stages' ResBlocks.  Stage buffers are distinct,
   // and the fork / join events are ordinary stream dependencies, also under stream capture.
-  const bool fork = !prof && h->fork_max_frames > 0 && (long)B * T <= h->fork_max_frames;
+  const bool fork = fork_mode(h, B, T) && !prof;          // (a profiled run times launches on one stream)
   if (fork) {
     if (!h->side) {
       std::lock_guard<std::mutex> lk(h->mu);
       if (!h->side) {
         cudaStream_t sd = nullptr;
-        GNV_CK(h, "side stream", cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) GNV_CK(h, "side stream", cudaStreamCreateWithFlags(&h->rbs[i], cudaStreamNonBlocking));
         GNV_CK(h, "fork event", cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        GNV_CK(h, "fork event", cudaEventCreateWithFlags(&h->ev_ups, cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) GNV_CK(h, "join event", cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) GNV_CK(h, "join event", cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming));
+        GNV_CK(h, "side stream", cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
         h->side = sd;
       }
     }
+    const std::vector<ConvOp>& ops = plan->decode_ops;
+    const size_t n_ops = ops.size();
+    auto launch = [&](const ConvOp& op, cudaStream_t s2) -> int {
+      GNV_CK(h, "conv", run_op(op, lengths, s2));
+      prof_mark(prof, op.name.c_str(), op.tc ? GNV_LAUNCH_CONV_TC : GNV_LAUNCH_CONV_SIMT, op.flops);
+      return 0;
+    };
+    // (a) the source branch of all three stages, on its own stream, right behind the STFT
     GNV_CK(h, "fork", cudaEventRecord(h->ev_fork, st));
     GNV_CK(h, "fork", cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    const size_t n_ops = plan->decode_ops.size();
     for (size_t k = 0; k < n_ops; ++k) {
-      const ConvOp& op = plan->decode_ops[k];
+      const ConvOp& op = ops[k];
       if (op.branch != 1) continue;
-      GNV_CK(h, "conv", run_op(op, lengths, h->side));
+      if (int rc = launch(op, h->side)) return rc;
       bool last_of_stage = true;
       for (size_t m = k + 1; m < n_ops; ++m)
-        if (plan->decode_ops[m].branch == 1 && plan->decode_ops[m].stage == op.stage) { last_of_stage = false; break; }
+        if (ops[m].branch == 1 && ops[m].stage == op.stage) { last_of_stage = false; break; }
       if (last_of_stage) GNV_CK(h, "join", cudaEventRecord(h->ev_join[op.stage], h->side));
     }
-    for (const ConvOp& op : plan->decode_ops) {
-      if (op.branch == 1) continue;
-      if (op.stage >= 0) GNV_CK(h, "join", cudaStreamWaitEvent(st, h->ev_join[op.stage], 0));   // ups.i adds the source branch
-      GNV_CK(h, "conv", run_op(op, lengths, st));
+    // (b) the main path; the three ResBlocks of a stage side by side up to the launch that adds each into the running
+    // sum F3 — those three stay on the caller's stream in the order 0, 1, 2 (same arithmetic as the serial schedule)
+    for (size_t k = 0; k < n_ops;) {
+      const ConvOp& op = ops[k];
+      if (op.branch == 1) { ++k; continue; }
+      if (op.rb < 0) {
+        if (op.stage >= 0) GNV_CK(h, "join", cudaStreamWaitEvent(st, h->ev_join[op.stage], 0));   // ups.i adds the source branch
+        if (int rc = launch(op, st)) return rc;
+        ++k;
+        continue;
+      }
+      // ops[k ...) up to the end of this stage's ResBlocks
+      std::vector<const ConvOp*> pre[3];
+      const ConvOp* last[3] = {nullptr, nullptr, nullptr};
+      const int stage = op.stage;
+      size_t m = k;
+      for (; m < n_ops && ops[m].branch == 0 && ops[m].rb >= 0 && ops[m].stage == stage; ++m) {
+        if (ops[m].rb_last) last[ops[m].rb] = &ops[m]; else pre[ops[m].rb].push_back(&ops[m]);
+      }
+      GNV_CK(h, "fork", cudaEventRecord(h->ev_ups, st));
+      for (int j = 1; j < 3; ++j) GNV_CK(h, "fork", cudaStreamWaitEvent(h->rbs[j - 1], h->ev_ups, 0));
+      const size_t depth = std::max(pre[0].size(), std::max(pre[1].size(), pre[2].size()));
+      for (size_t d = 0; d < depth; ++d)                    // round robin, so that the host feeds all three streams early
+        for (int j = 0; j < 3; ++j)
+          if (d < pre[j].size())
+            if (int rc = launch(*pre[j][d], j == 0 ? st : h->rbs[j - 1])) return rc;
+      for (int j = 1; j < 3; ++j) GNV_CK(h, "join", cudaEventRecord(h->ev_pre[j - 1], h->rbs[j - 1]));
+      for (int j = 0; j < 3; ++j) {
+        if (j > 0) GNV_CK(h, "join", cudaStreamWaitEvent(st, h->ev_pre[j - 1], 0));
+        if (last[j]) if (int rc = launch(*last[j], st)) return rc;
+      }
+      k = m;
     }
   } else {
     for (const ConvOp& op : plan->decode_ops) {
@@ -897,8 +958,11 @@ void gnv_destroy(gnv_handle h) {
     for (auto& kv : h->plans) free_slot(kv.second->slot);
     for (MapsSlot& sl : h->free_slots) free_slot(sl);
     if (h->side) cudaStreamDestroy(h->side);
+    for (int i = 0; i < 2; ++i) if (h->rbs[i]) cudaStreamDestroy(h->rbs[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_ups) cudaEventDestroy(h->ev_ups);
     for (int i = 0; i < 3; ++i) if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    for (int i = 0; i < 2; ++i) if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
     for (void* p : h->allocs) cudaFree(p);
   }
   delete h;
