@@ -10,11 +10,14 @@
  *
  * Conventions
  *   - every entry point returns 0 on success, non-zero on failure; gnv_last_error() gives the text.
- *     Nothing aborts; nothing calls cudaDeviceSynchronize(); nothing allocates inside the decode
- *     calls (safe to capture in a CUDA graph).
+ *     Nothing aborts; nothing calls cudaDeviceSynchronize(); once a shape's launch plan exists (first call,
+ *     see gnv_plan_stats) nothing allocates inside the decode calls (safe to capture in a CUDA graph).
  *   - the caller owns all input, output and workspace buffers and passes raw DEVICE pointers
  *     (torch: tensor.data_ptr()).  The handle owns only re-packed weights.
- *   - `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).
+ *   - `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).  All work is
+ *     ordered on it: small batches (B*T <= 4096 frames) also use streams the handle owns for independent branches,
+ *     forked from and joined back into `stream` by events, so to the caller — and to a stream capture — a call
+ *     still is one piece of work on `stream`.  One call at a time per handle.
  *   - tensors are fp32, contiguous, in the layouts of the upstream PyTorch module:
  *     mel [B,80,T]  source s [B,1,480*T]  wav [B,480*T]  f0 [B,T].
  */
