@@ -152,3 +152,25 @@ def test_out_of_range_lengths_are_clamped_not_trusted(lib, cuda_device, sd):
     assert torch.equal(wav[3, : 7 * 480], part[0]) and not wav[3, 7 * 480:].any()
     w2, s2 = dec.inference(mel, lengths=[0, -5, 1000, 7], seed=4)
     assert torch.isfinite(w2).all() and torch.isfinite(s2).all() and not w2[0].any() and not w2[1].any()
+
+
+def test_large_ragged_batch_rows_equal_single_decodes(lib, cuda_device, sd):
+    """A ragged batch big enough for the throughput schedule (B*T > 4096 frames: no forked streams, CTA pairs, two
+    accumulators per tile, dead tiles skipped) against the same utterances decoded alone (small-problem schedule:
+    narrow tiles, forked streams): bit-identical rows, zeros after each length."""
+    from gonova_tts_b200 import B200HiFT
+
+    dec = B200HiFT(sd, device=cuda_device, dtype="bf16")
+    B, T = 24, 300
+    g = torch.Generator().manual_seed(44)
+    lens = torch.randint(20, T + 1, (B,), generator=g).tolist()
+    lens[0], lens[1] = T, 1
+    mel = R.synthetic_mel(B, T, seed=45).to(cuda_device)
+    s = (torch.rand(B, 1, T * 480, generator=g) * 0.2 - 0.1).to(cuda_device)
+    wav = dec.decode(mel, s, lengths=lens)
+    assert torch.isfinite(wav).all()
+    for b in (0, 1, 5, 11, 23):
+        n = lens[b]
+        one = dec.decode(mel[b:b + 1, :, :n].contiguous(), s[b:b + 1, :, : n * 480].contiguous())
+        assert torch.equal(one[0], wav[b, : n * 480]), (b, n)
+        assert not wav[b, n * 480:].any()
