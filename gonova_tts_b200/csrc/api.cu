@@ -249,7 +249,7 @@ struct gnv_decoder {
   float *f0_w = nullptr, *f0_b = nullptr, *lin_w = nullptr, *lin_b = nullptr;
   std::map<PlanKey, std::shared_ptr<Plan>> plans;   // shared: a call keeps its plan alive if another thread evicts the cache
   std::vector<MapsSlot> free_slots;                 // tensor-map slots of evicted plans, reused by the next plan built
-  size_t max_plans = 64;                            // LRU bound of `plans` (GONOVA_MAX_PLANS); pinned plans do not count out
+  size_t max_plans = 128;                           // LRU bound of `plans` (GONOVA_MAX_PLANS); pinned plans do not count out
   unsigned long long tick = 0;
   unsigned long long plans_built = 0, slots_allocated = 0;
   // small problems: the source branch of every stage runs on a side stream beside conv_pre / the previous stages

@@ -172,7 +172,7 @@ int gnv_decode_launches(gnv_handle h, int B, int T, int* out);
 int gnv_inference_launches(gnv_handle h, int B, int T, int* out);
 
 /* Launch-plan cache of a handle.  A plan (tensor maps, tile lists) is built on the first call for a new
- * (B, T, workspace) and kept in an LRU of 64 (env GONOVA_MAX_PLANS); an evicted plan's device slot is reused by the
+ * (B, T, workspace) and kept in an LRU of 128 (env GONOVA_MAX_PLANS); an evicted plan's device slot is reused by the
  * next plan, so a service that sees a new sentence length on every call (services/tts/server.py:118-182) neither
  * allocates nor grows.  A plan that was used inside a stream capture is pinned (the CUDA graph points at its slot);
  * the FIRST call for a shape must be made outside a capture.
