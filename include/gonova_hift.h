@@ -88,7 +88,9 @@ int gnv_f0(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T,
 int gnv_source(gnv_handle h, const float* f0, int B, int T, uint64_t seed,
                const float* phase_vec, const float* noise, float* s, void* stream);
 
-/* The same source for a piece of a longer utterance (intra-sentence streaming): frames
+/* No counterpart in the reference, which ships one chunk per sentence (services/tts/core/synthesizer.py:320-321,
+ * :352-357); upstream's token streaming carries `cache_source` across chunks for the same purpose.
+ * The same source for a piece of a longer utterance (intra-sentence streaming): frames
  * [t0, t0 + T) of an utterance whose earlier frames were generated by earlier calls.  sample0 = 480 * t0 keys the
  * noise by absolute sample index; f0_sum0 [B] (fp64, device, or NULL = 0) is the sum of f0 over frames [0, t0)
  * — the running phase — and f0_sum_out [B] (may alias f0_sum0, may be NULL) receives it for the next call.  A
@@ -171,7 +173,8 @@ int gnv_debug_cluster_probe(int smem_bytes, int grid, int* max_clusters);
 int gnv_decode_launches(gnv_handle h, int B, int T, int* out);
 int gnv_inference_launches(gnv_handle h, int B, int T, int* out);
 
-/* Launch-plan cache of a handle.  A plan (tensor maps, tile lists) is built on the first call for a new
+/* Diagnostics; no counterpart in the reference (its one-request-at-a-time worker, services/tts/server.py:118-182, is
+ * why the cache exists).  Launch-plan cache of a handle.  A plan (tensor maps, tile lists) is built on the first call for a new
  * (B, T, workspace) and kept in an LRU of 128 (env GONOVA_MAX_PLANS); an evicted plan's device slot is reused by the
  * next plan, so a service that sees a new sentence length on every call (services/tts/server.py:118-182) neither
  * allocates nor grows.  A plan that was used inside a stream capture is pinned (the CUDA graph points at its slot);
