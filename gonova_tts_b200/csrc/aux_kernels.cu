@@ -454,16 +454,22 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
       re[k] = live ? mag * cs : 0.f;
       im[k] = live ? mag * sn : 0.f;
     }
+    // k outer, n inner: the 16 coefficients of a bin are contiguous in constant memory, so they arrive as wide uniform
+    // loads (n outer made ptxas issue one LDCU per FMA, 298 of them: the kernel's whole run time).  The order of
+    // the additions into each acc[n] is unchanged (k ascending, cos term before sin term).
+    float acc[16];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-      float acc = 0.f;
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        acc = fmaf(re[k], c_istft_cb[k][n], acc);
-        acc = fmaf(im[k], c_istft_sb[k][n], acc);
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        acc[n] = fmaf(re[k], c_istft_cb[k][n], acc[n]);
+        acc[n] = fmaf(im[k], c_istft_sb[k][n], acc[n]);
       }
-      fr[threadIdx.x][n] = acc;
     }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) fr[threadIdx.x][n] = acc[n];
   }
   __syncthreads();
   if (threadIdx.x < kIstftNew) {
