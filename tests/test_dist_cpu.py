@@ -59,3 +59,32 @@ def test_two_rank_sharding_and_max_timing():
         assert ms == 20.0                       # max over ranks, not this rank's own time
         assert owned == [1] * n                 # every stream owned by exactly one rank
         assert units == n
+
+
+@pytest.mark.timeout(300)
+def test_reference_arm_prints_one_line_alone_and_under_torchrun():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) needs no GPU: one JSON line with the
+    contract's keys; under torchrun (N = 2) rank 0 alone prints it and the other rank exits 0 without work."""
+    import json
+    import subprocess
+
+    base = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+            "--frames", "40"]
+    r = subprocess.run(base, capture_output=True, text=True, timeout=200, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0", "--frames", "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
