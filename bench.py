@@ -47,7 +47,66 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-first-chunk", action="store_true")
     ap.add_argument("--profile-table", default="", help="write the per-launch timing table to this path")
+    ap.add_argument("--streams", type=int, default=512,
+                    help="BASELINE configs[3]: this many 10 s streams IN TOTAL, sharded over the ranks in batches of "
+                         "--batch (strong scaling; reported as the `streams512` block; 0 = skip)")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the tf32 (reference-precision) block")
+    ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-this-GPU block")
     return ap.parse_args()
+
+
+# Algorithmic bytes per mel frame of the bandwidth-bound kernels (eb = bytes per conv operand element).
+def aux_bytes_per_frame(name: str, eb: int):
+    if name == "istft_head":
+        return 18 * 120 * 4 + 1920                 # conv_post rows in (fp32), 480 samples out
+    if name == "stft":
+        return 1920 + 18 * 120 * eb                # source samples in, 18 channels x 120 frames out as conv operands
+    if name == "m_source":
+        return 4 + 1920                            # f0 in, 480 source samples out; the [9, 480] bank stays on chip
+    if name == "pcm_tail":
+        return 1920 + 960                          # 6 B per sample: fp32 in, int16 out
+    if name == "pack_mel":
+        return 80 * 4 + 80 * eb
+    if name == "f0_predictor.classifier":
+        return 512 * eb + 4
+    return None
+
+
+def measure_tf32_gemm_peak(dev, seconds: float = 1.5):
+    """TF32 tensor-core GEMM rate of THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: torch.matmul 8192^3
+    (2 N^3 flops) on fp32 operands with TF32 allowed; burst = best of 10, sustained = back to back for `seconds`."""
+    n = 8192
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        per = max(best, 1e-3)
+        reps = max(10, int(seconds * 1e3 / per))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sustained_ms = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": fl / (best / 1e3) / 1e12, "tf32_tflops_sustained": fl / (sustained_ms / 1e3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (2*N^3): best of 10 (burst) and {reps} back to back (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def synthetic_mel(B: int, T: int, seed: int) -> torch.Tensor:
@@ -301,6 +360,30 @@ def main():
     value = world * audio_s_per_gpu * args.steps / (ms_total / 1e3)
     e2e_value = world * audio_s_per_gpu * args.steps / (ms_e2e / 1e3)
 
+    # ---- BASELINE configs[3] as SURVEY 8d defines it: `--streams` streams IN TOTAL, sharded over the ranks and decoded in
+    # batches of B; aggregate = total audio seconds / max-over-ranks device time (strong scaling: the job is fixed).
+    streams512 = None
+    if args.streams > 0:
+        from gonova_tts_b200 import shard_range
+
+        lo, hi = shard_range(args.streams, world, rank)
+        mine = hi - lo
+        sizes = [min(B, mine - b0) for b0 in range(0, mine, B)]
+
+        def step_job(i):
+            for j, nb in enumerate(sizes):
+                dec.inference(mel[:nb], seed=1000 * (i + 1) + j, out=wav[:nb], source_out=src[:nb])
+                pcm_tail(wav[:nb], None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm[:nb])
+
+        job_steps = 3
+        ms_job, _ = timed(step_job, job_steps, 1)
+        streams512 = {
+            "streams_total": args.streams, "streams_this_rank": mine, "batches_per_rank": len(sizes), "batch": B,
+            "audio_seconds": args.streams * T / 50.0, "ms_per_job": ms_job / job_steps,
+            "value": args.streams * T / 50.0 * job_steps / (ms_job / 1e3), "unit": UNIT, "scaling": "strong",
+            "how": "SURVEY 8d config 4: the whole job (all streams once) per step, inputs resident, CUDA events, max over "
+                   "ranks; no collective on the data path"}
+
     out = None
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -321,8 +404,12 @@ def main():
         tc_ms, tc_flops = sum(r[2] for r in tc), sum(r[3] for r in tc)
         step_ms_profiled = sum(r[2] for r in rows_acc)
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        if args.dtype != "bf16":
-            peak_tf = peak_tf / 2 if args.dtype == "tf32" else 75.0    # tf32 = half the bf16 rate; fp32 FMA nominal
+        tf32_peak = None
+        if args.dtype == "tf32":
+            tf32_peak = measure_tf32_gemm_peak(dev)
+            peak_tf = tf32_peak["tf32_tflops_sustained"]
+        elif args.dtype != "bf16":
+            peak_tf = 75.0                                              # fp32 FMA nominal
         # The family's duration INSIDE the timed region = its share of the step (per-launch CUDA events of the profiled
         # passes above; the ncu launch list in profiles/ gives the same share) x the timed step.  The profiled passes
         # themselves run without launch overlap and, after the timed loops, deeper in the power cap: their absolute
@@ -334,10 +421,12 @@ def main():
         # DRAM bytes of the same launches from the committed ncu capture (profiles/), valid for the default workload
         traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            tname = "r02_conv_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) \
+                else "r01_conv_traffic.json"
+            with open(os.path.join(ROOT, "profiles", tname)) as f:
                 tj = json.load(f)
             if (B, T, args.dtype) == (64, 500, "bf16"):
-                traffic, traffic_src = tj["traffic_bytes"], "profiles/r01_conv_traffic.json (ncu dram__bytes_read+write, all conv launches of one step)"
+                traffic, traffic_src = tj["traffic_bytes"], f"profiles/{tname} (ncu dram__bytes_read+write, all conv launches of one step)"
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -351,7 +440,8 @@ def main():
                 "frac": traffic / (tc_ms / 1e3) / 1e9 / hbm_peak,
                 "note": "the family is close to balanced: the same launches at the HBM peak would take "
                         f"{traffic / hbm_peak / 1e6:.1f} ms, at the tensor peak {tc_flops / peak_tf / 1e9:.1f} ms"},
-            "peak_source": peak_src + (" bf16 sustained" if args.dtype == "bf16" else " derived for " + args.dtype),
+            "peak_source": peak_src + " bf16 sustained" if args.dtype == "bf16" else
+                           (tf32_peak["how"] if tf32_peak else "nominal fp32 FMA rate"),
             "algorithmic_flops_per_step": tc_flops, "kernel_ms_per_step": tc_ms,
             "kernel_ms_per_step_profiled": tc_ms_profiled, "share_of_step": share,
             "how": "achieved = algorithmic conv FLOPs of the family / (its share of the step from per-launch CUDA events "
@@ -359,6 +449,34 @@ def main():
         }
         breakdown = {"conv_tc_ms": tc_ms_profiled, "conv_simt_ms": sum(r[2] for r in simt), "aux_ms": sum(r[2] for r in aux),
                      "profiled_step_ms": step_ms_profiled}
+        # ---- one roofline entry per kernel family: the conv family against the tensor peak, every byte-moving kernel
+        # against the measured HBM copy bandwidth (algorithmic bytes of SURVEY 8d / its profiled launch time)
+        eb = 2 if args.dtype == "bf16" else 4
+        roofline_kernels = [{"kernel": "conv family (conv_tc2_kernel + conv_pair_kernel + conv_chain_kernel)", "bound": "tensor",
+                             "launches": len(tc), "ms": tc_ms, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": achieved_tf / peak_tf if peak_tf else None}]
+        # the PCM tail is not part of gnv_inference: time it alone (CUDA events, 20 launches back to back)
+        for _ in range(3):
+            pcm_tail(wav, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm)
+        torch.cuda.synchronize(dev)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record(stream)
+        for _ in range(20):
+            pcm_tail(wav, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm)
+        pe1.record(stream)
+        torch.cuda.synchronize(dev)
+        aux_rows = [(n, ms_) for (n, k, ms_, _) in rows_acc if k == _cabi.LAUNCH_AUX] + [("pcm_tail", pe0.elapsed_time(pe1) / 20)]
+        for n, ms_ in aux_rows:
+            bpf = aux_bytes_per_frame(n, eb)
+            if bpf is None or ms_ <= 0:
+                continue
+            nbytes = bpf * B * T
+            gbps = nbytes / (ms_ / 1e3) / 1e9
+            roofline_kernels.append({"kernel": {"istft_head": "istft_kernel", "stft": "stft_kernel", "m_source": "source_kernel",
+                                                "pcm_tail": "pcm_tail_kernel", "pack_mel": "nct_to_nlc_kernel",
+                                                "f0_predictor.classifier": "f0_head_kernel"}.get(n, n),
+                                     "bound": "hbm", "bytes": nbytes, "ms": ms_, "achieved": gbps, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": gbps / hbm_peak})
         if args.profile_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_table)), exist_ok=True)
             with open(args.profile_table, "w") as f:
@@ -408,6 +526,93 @@ def main():
                                    "memory, wall clock; p50/p99 = CUDA-graph replay (GraphedInference), eager_* = "
                                    "one C-ABI call per kernel launch", "dtype": args.dtype}
 
+        # ---- the reference-precision path: tf32 operands (what the reference's own GPU path computes in,
+        # services/tts/core/synthesizer.py:177-179), same workload, against a tf32 GEMM peak measured here
+        tf32_block = None
+        if world == 1 and args.dtype == "bf16" and not args.no_tf32:
+            try:
+                dec32 = B200HiFT(random_state_dict(0, False), device=dev, dtype="tf32")
+
+                def step32(i):
+                    dec32.inference(mel, seed=i + 1, out=wav, source_out=src)
+                    pcm_tail(wav, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm)
+
+                n32 = max(3, args.steps // 2)
+                ms32, _ = timed(step32, n32, 3)
+                rows32 = None
+                for r in range(3):
+                    _, rr = dec32.profile_inference(mel, seed=200 + r)
+                    if r == 0:
+                        continue
+                    if rows32 is None:
+                        rows32 = [[n, k, 0.0, f] for (n, k, _, f) in rr]
+                    for acc, row in zip(rows32, rr):
+                        acc[2] += row[2] / 2
+                tc32 = [r for r in rows32 if r[1] == _cabi.LAUNCH_CONV_TC]
+                share32 = sum(r[2] for r in tc32) / sum(r[2] for r in rows32)
+                fl32 = sum(r[3] for r in tc32)
+                fam_ms32 = share32 * ms32 / n32
+                pk = measure_tf32_gemm_peak(dev)
+                ach32 = fl32 / (fam_ms32 / 1e3) / 1e12
+                tf32_block = {"value": audio_s_per_gpu * n32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / n32, "steps": n32,
+                              "roofline": {"bound": "tensor", "achieved": ach32, "peak": pk["tf32_tflops_sustained"],
+                                           "peak_burst": pk["tf32_tflops"], "unit": "TFLOP/s",
+                                           "frac": ach32 / pk["tf32_tflops_sustained"], "share_of_step": share32,
+                                           "peak_source": pk["how"]}}
+                del dec32
+                torch.cuda.empty_cache()
+            except Exception as e:      # the headline must not die with an optional block
+                tf32_block = {"error": str(e)}
+
+        # ---- second comparator: stock PyTorch on this same GPU — the reference's modules as it runs them (cuDNN
+        # autotune + TF32, synthesizer.py:175-179).  A BASELINE leg like cpu_baseline: it runs the oracle's restatement of the
+        # engine's nn.Modules moved to cuda; nothing of it is on the product path.
+        stock_block = None
+        if world == 1 and not args.no_stock_torch:
+            try:
+                from oracle import hift_ref as R
+
+                old_flags = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+                torch.backends.cudnn.benchmark = True
+                torch.backends.cuda.matmul.allow_tf32 = True
+                torch.backends.cudnn.allow_tf32 = True
+                m = R.load_model(random_state_dict(0, False)).to(dev).eval()
+                gen = torch.Generator(device="cpu").manual_seed(6)
+                s_in = (torch.rand(B, 1, L, generator=gen) * 0.2 - 0.1).to(dev)
+
+                def stock_step():
+                    with torch.inference_mode():
+                        m.decode(mel, s_in)
+
+                for _ in range(2):
+                    stock_step()
+                torch.cuda.synchronize(dev)
+                se0, se1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                se0.record(stream)
+                for _ in range(3):
+                    stock_step()
+                se1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms_stock = se0.elapsed_time(se1) / 3
+                de0, de1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for _ in range(2):
+                    dec.decode(mel, s_in, out=wav)
+                de0.record(stream)
+                for _ in range(5):
+                    dec.decode(mel, s_in, out=wav)
+                de1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms_ours = de0.elapsed_time(de1) / 5
+                stock_block = {"value": audio_s_per_gpu / (ms_stock / 1e3), "unit": UNIT, "ms_per_decode": ms_stock,
+                               "ours_ms_per_decode": ms_ours, "ours_dtype": args.dtype, "speedup": ms_stock / ms_ours,
+                               "what": f"decode(x, s) of the same {B} x {T}-frame batch, inputs resident: the engine's nn.Modules "
+                                       "(oracle restatement) on cuda:0 with cudnn.benchmark + TF32 vs this repo's decode"}
+                torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_flags
+                del m, s_in
+                torch.cuda.empty_cache()
+            except Exception as e:
+                stock_block = {"error": str(e)}
+
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             v, sec, cores, times = cpu_decode_rate(2, T, reps=3)
@@ -433,7 +638,9 @@ def main():
                     "how": "pinned mel H2D and int16 PCM D2H every step on a copy stream, double-buffered (overlapping the "
                            "neighbouring steps' kernels); the host waits for step i-1's PCM while step i runs"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "breakdown": breakdown, "first_chunk": first_chunk, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_kernels": roofline_kernels, "breakdown": breakdown,
+            "first_chunk": first_chunk, "cpu_baseline": cpu_baseline, "tf32": tf32_block, "stock_torch_gpu": stock_block,
+            "streams512": streams512,
         }
     barrier()
     if world > 1:

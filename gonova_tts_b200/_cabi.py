@@ -20,7 +20,7 @@ SYMBOLS = [
     "gnv_create", "gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_workspace_bytes", "gnv_f0",
     "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_pcm_mulaw", "gnv_stft", "gnv_istft", "gnv_conv1d",
     "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
-    "gnv_plan_stats", "gnv_source_stream",
+    "gnv_plan_stats", "gnv_source_stream", "gnv_inference_dseed",
 ]
 
 
@@ -58,6 +58,8 @@ def load():
     lib.gnv_decode.argtypes = [vp, f32p, f32p, i32p, C.c_int, C.c_int, f32p, vp, C.c_size_t, vp]
     lib.gnv_inference.argtypes = [vp, f32p, f32p, C.c_int, i32p, C.c_int, C.c_int, C.c_uint64, f32p, f32p, vp,
                                   C.c_size_t, vp]
+    lib.gnv_inference_dseed.argtypes = [vp, f32p, f32p, C.c_int, i32p, C.c_int, C.c_int, vp, C.c_int, f32p, f32p, vp,
+                                        C.c_size_t, vp]
     lib.gnv_inference_profile.argtypes = [vp, f32p, i32p, C.c_int, C.c_int, C.c_uint64, f32p, f32p, vp, C.c_size_t, vp,
                                           C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                           C.c_char_p, C.POINTER(C.c_int)]

@@ -7,7 +7,9 @@ real time, B=64: 21 k x), so this collects the requests that arrive within a sho
 one ragged batch (`lengths`), runs the decoder once and hands every caller its own slice.
 
 Host-side only: `decode_fn(mel [B,80,Tmax] float32 host tensor, lengths list[int]) -> wav [B, 480*Tmax]`
-is the only thing that touches the GPU (see `for_decoder`)."""
+(`decode_fn(mel, lengths, seeds)` with `per_request_seeds=True`) is the only thing that touches the GPU (see
+`for_decoder`).  With per-request seeds a caller's audio does not depend on the batch it shared: row b of a batch gets
+the NSF source the utterance decoded alone with that seed gets (gnv_inference_dseed, per_row)."""
 from __future__ import annotations
 
 import queue
@@ -24,7 +26,7 @@ SAMPLES_PER_FRAME = 480
 class MicroBatcher:
     def __init__(self, decode_fn: Callable[[torch.Tensor, List[int]], torch.Tensor], max_batch: int = 64,
                  max_wait_ms: float = 2.0, max_queue: int = 500, pad_frames: int = 1, workers: int = 1,
-                 pad_batch: int = 1):
+                 pad_batch: int = 1, per_request_seeds: bool = False):
         """pad_frames: the padded batch length is rounded up to a multiple of it (fewer distinct (B, T) shapes for the
         decoder's launch-plan cache; the extra frames are masked through `lengths` like any other padding).
         pad_batch: the batch is filled up to a multiple of it with zero-length rows (`lengths` 0: the decoder skips them),
@@ -34,6 +36,8 @@ class MicroBatcher:
         if max_batch < 1 or max_queue < 1 or pad_frames < 1 or workers < 1 or pad_batch < 1:
             raise ValueError("max_batch, max_queue, pad_frames, pad_batch and workers must be positive")
         self.pad_batch = pad_batch
+        self.per_request_seeds = per_request_seeds
+        self._seed = 0
         self._decode = decode_fn
         self.pad_frames = pad_frames
         self.max_batch, self.max_wait = max_batch, max_wait_ms / 1e3
@@ -48,14 +52,20 @@ class MicroBatcher:
             w.start()
 
     # -- producer side ----------------------------------------------------------------------------
-    def submit(self, mel: torch.Tensor) -> Future:
+    def submit(self, mel: torch.Tensor, seed: Optional[int] = None) -> Future:
         """mel [80, T] (host).  Returns a Future of the fp32 waveform [480*T].  Like the reference queue,
-        a full queue drops the request: queue.Full is raised and counted."""
+        a full queue drops the request: queue.Full is raised and counted.  `seed` (per_request_seeds): the NSF seed
+        of this request; None draws the next one of the batcher's own counter."""
         if self._closed:
             raise RuntimeError("MicroBatcher is closed")
         if mel.dim() != 2 or mel.shape[0] != 80 or mel.shape[1] < 1:
             raise ValueError("mel must be [80, T] with T >= 1")
         fut: Future = Future()
+        if seed is None:
+            with self._mlock:
+                self._seed += 1
+                seed = self._seed
+        fut.gonova_seed = int(seed)             # rides on the future: the queue items stay (mel, future) pairs
         try:
             self._q.put_nowait((mel.to(torch.float32), fut))
         except queue.Full:
@@ -122,7 +132,11 @@ class MicroBatcher:
                 with self._mlock:
                     self._busy += 1
                 try:
-                    wav = self._decode(x, lengths)
+                    if self.per_request_seeds:
+                        seeds = [getattr(f, "gonova_seed", 0) for _, f in live] + [0] * (rows - len(live))
+                        wav = self._decode(x, lengths, seeds)
+                    else:
+                        wav = self._decode(x, lengths)
                 finally:
                     with self._mlock:
                         self._busy -= 1
@@ -165,17 +179,19 @@ def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: 
             st[:] = alloc(max(T, padded_max))
         return st[0][:need_in].view(B, 80, T), st[1][:need_out].view(B, T * SAMPLES_PER_FRAME)
 
-    def decode(x: torch.Tensor, lengths: Sequence[int]) -> torch.Tensor:
+    def decode(x: torch.Tensor, lengths: Sequence[int], seeds: Sequence[int]) -> torch.Tensor:
         B, _, T = x.shape
         with torch.cuda.device(dev):
             pin_in, pin_out = staging(B, T)
             pin_in.copy_(x)
             xd = pin_in.to(dev, non_blocking=True)
-            wav, _ = hift.inference(xd, lengths=list(lengths))
+            sd = torch.tensor(list(seeds), dtype=torch.int64).to(dev, non_blocking=True)
+            wav, _ = hift.inference(xd, lengths=list(lengths), seed_dev=sd)
             pin_out.copy_(wav, non_blocking=True)
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream(dev))
             done.synchronize()                               # this batch only, not what the other worker queued behind it
             return pin_out                                   # the batcher clones every caller's slice out of it
 
-    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers, pad_batch)
+    return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers, pad_batch,
+                        per_request_seeds=True)

@@ -43,6 +43,7 @@ using namespace gnv;
 namespace {
 
 thread_local std::string tl_error;
+thread_local std::string tl_error_ret;   // what gnv_last_error(h) hands out: a private copy of the handle's message
 
 constexpr int kSPF = 480;
 constexpr int kMelC = 80;
@@ -188,7 +189,7 @@ struct SlotChunks {
 constexpr int kSlotChunk = 32;
 
 // Uploads the tensor maps of every persistent-kernel op to the plan's slot (taken from `free_slots` when one is large
-// enough) and points the ops at it.  The copy is stream-ordered on `st`, from pinned memory.
+// enough) and points the ops at it.  The copy is issued on `st` from pinned memory and waited for.
 std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_slots, MapsSlot* slot, cudaStream_t st,
                         SlotChunks* chunks = nullptr) {
   size_t bytes = 0;
@@ -239,6 +240,9 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 3) { memcpy(sl.staging + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
   }
   cudaError_t e = cudaMemcpyAsync(sl.d, sl.staging, bytes, cudaMemcpyHostToDevice, st);
+  // `st` is the handle's own upload stream (or the test hook's stream): the copy is complete before the plan is
+  // published, so a later cache hit on ANY stream — or inside a stream capture — finds the maps in place
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaEventRecord(sl.last_use, st);
   if (e != cudaSuccess) { free_slots.push_back(sl); return std::string("cudaMemcpyAsync(tensor maps): ") + cudaGetErrorString(e); }
   sl.used = true;
@@ -285,6 +289,7 @@ struct gnv_decoder {
   unsigned long long tick = 0;
   unsigned long long plans_built = 0, slots_allocated = 0;
   // small problems: the source branch of every stage runs on a side stream beside conv_pre / the previous stages
+  cudaStream_t upload_st = nullptr;                 // tensor-map uploads of new plans (synchronised at build time)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   cudaStream_t rbs[2] = {nullptr, nullptr};         // ResBlocks 1 and 2 of a stage (ResBlock 0 stays on the caller's stream)
@@ -292,13 +297,17 @@ struct gnv_decoder {
   int fork_max_frames = 4096;                       // B * T up to which the fork is used (GONOVA_FORK_MAX_FRAMES; 0 = never): measured
                                                     // at T = 500: B = 1 -9 %, B = 4 -6 %, B = 6 -8 %, B = 8 -3 %, B >= 12 nothing
   std::mutex mu;
+  std::mutex err_mu;                                // guards `err`
 };
 
 namespace {
 
 int fail(gnv_handle h, const std::string& msg) {
   tl_error = msg;
-  if (h) h->err = msg;
+  if (h) {
+    std::lock_guard<std::mutex> lk(h->err_mu);
+    h->err = msg;
+  }
   return 1;
 }
 int fail_cuda(gnv_handle h, const char* what, cudaError_t e) {
@@ -820,7 +829,13 @@ int get_plan(gnv_handle h, int B, int T, void* ws, size_t ws_bytes, cudaStream_t
     }
     auto p = std::make_shared<Plan>();
     const auto t0 = std::chrono::steady_clock::now();
-    std::string e = build_plan(h, B, T, ws, p.get(), st);
+    if (!h->upload_st) {
+      cudaError_t ce = cudaStreamCreateWithFlags(&h->upload_st, cudaStreamNonBlocking);
+      if (ce != cudaSuccess) return fail_cuda(h, "upload stream", ce);
+    }
+    // the tensor maps go up on the handle's own stream and are waited for (about 20 us of a 0.4 ms build): not behind
+    // whatever the caller's stream still has queued, and visible to every stream that uses the plan afterwards
+    std::string e = build_plan(h, B, T, ws, p.get(), h->upload_st);
     if (!e.empty()) {
       if (p->slot.d) h->free_slots.push_back(p->slot);
       return fail(h, e);
@@ -984,7 +999,15 @@ extern "C" {
 
 int gnv_abi_version(void) { return GNV_ABI_VERSION; }
 
-const char* gnv_last_error(gnv_handle h) { return h ? h->err.c_str() : tl_error.c_str(); }
+const char* gnv_last_error(gnv_handle h) {
+  // always a thread-local string: another thread may be rewriting h->err
+  if (h) {
+    std::lock_guard<std::mutex> lk(h->err_mu);
+    tl_error_ret = h->err;
+    return tl_error_ret.c_str();
+  }
+  return tl_error.c_str();
+}
 
 void gnv_destroy(gnv_handle h) {
   if (!h) return;
@@ -994,6 +1017,7 @@ void gnv_destroy(gnv_handle h) {
     for (MapsSlot& sl : h->free_slots) free_slot(sl);
     for (void* q : h->slot_chunks.dev) cudaFree(q);
     for (void* q : h->slot_chunks.host) cudaFreeHost(q);
+    if (h->upload_st) cudaStreamDestroy(h->upload_st);
     if (h->side) cudaStreamDestroy(h->side);
     for (int i = 0; i < 2; ++i) if (h->rbs[i]) cudaStreamDestroy(h->rbs[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1018,7 +1042,8 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   cudaDeviceProp prop;
   ce = cudaGetDeviceProperties(&prop, device);
   if (ce != cudaSuccess) return fail_cuda(nullptr, "cudaGetDeviceProperties", ce);
-  if (prop.major != 10) return fail(nullptr, "libgonova_hift is built for sm_100a (B200) only; found sm_" +
+  // the library holds sm_100a cubins only (arch-specific code is not forward compatible, not even to sm_103)
+  if (prop.major != 10 || prop.minor != 0) return fail(nullptr, "libgonova_hift is built for sm_100a (B200) only; found sm_" +
                                                  std::to_string(prop.major) + std::to_string(prop.minor));
   DeviceGuard dg(device);
   if (!dg.ok) return fail(nullptr, "cudaSetDevice failed");
@@ -1146,7 +1171,8 @@ int gnv_decode(gnv_handle h, const float* mel, const float* s, const int32_t* le
 
 static int inference_impl(gnv_handle h, const float* mel, const float* cache_source, int cache_len,
                           const int32_t* lengths, int B, int T, uint64_t seed, float* wav, float* s_out,
-                          void* workspace, size_t workspace_bytes, cudaStream_t st, Profiler* prof) {
+                          void* workspace, size_t workspace_bytes, cudaStream_t st, Profiler* prof,
+                          uint64_t* seed_dev = nullptr, int seed_per_row = 0) {
   if (!h || !mel || !wav || !s_out) return fail(h, "NULL argument");
   if (cache_len < 0 || (cache_len > 0 && !cache_source)) return fail(h, "bad cache_source");
   DeviceGuard dg(h->device);
@@ -1158,7 +1184,8 @@ static int inference_impl(gnv_handle h, const float* mel, const float* cache_sou
   float* f0 = (float*)(ws + plan->lay.f0);
   if (prof) prof->begin(st);
   if (int rc = run_f0(h, plan, mel, lengths, B, T, f0, ws, true, st, prof)) return rc;
-  GNV_CK(h, "source", launch_source(f0, B, T, seed, nullptr, nullptr, h->lin_w, h->lin_b, s_out, st));
+  GNV_CK(h, "source", launch_source(f0, B, T, seed, nullptr, nullptr, h->lin_w, h->lin_b, s_out, st, nullptr, 0, nullptr,
+                                    seed_dev, seed_per_row));
   prof_mark(prof, "m_source", GNV_LAUNCH_AUX);
   const size_t L = (size_t)T * kSPF;
   if (cache_len > 0) {
@@ -1175,6 +1202,14 @@ int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int
                   void* stream) {
   return inference_impl(h, mel, cache_source, cache_len, lengths, B, T, seed, wav, s_out, workspace, workspace_bytes,
                         (cudaStream_t)stream, nullptr);
+}
+
+int gnv_inference_dseed(gnv_handle h, const float* mel, const float* cache_source, int cache_len, const int32_t* lengths,
+                        int B, int T, uint64_t* seed_dev, int per_row, float* wav, float* s_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!seed_dev) return fail(h, "seed_dev is NULL");
+  return inference_impl(h, mel, cache_source, cache_len, lengths, B, T, 0, wav, s_out, workspace, workspace_bytes,
+                        (cudaStream_t)stream, nullptr, seed_dev, per_row ? 1 : 0);
 }
 
 int gnv_inference_profile(gnv_handle h, const float* mel, const int32_t* lengths, int B, int T, uint64_t seed,

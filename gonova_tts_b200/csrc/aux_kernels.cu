@@ -135,7 +135,13 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
                                                       const float* __restrict__ noise,
                                                       const float* __restrict__ lin_w,
                                                       const float* __restrict__ lin_b, float* __restrict__ s,
-                                                      const double* __restrict__ f0_sum0, long long sample0) {
+                                                      const double* __restrict__ f0_sum0, long long sample0,
+                                                      const uint64_t* __restrict__ seed_dev, int seed_per_row) {
+  // a device-resident seed (gnv_inference_dseed) is read at run time: a captured CUDA graph then draws fresh noise at
+  // every replay (seed_bump_kernel advances it behind this kernel).  Per-row seeds: row b draws what an utterance
+  // decoded ALONE (as row 0) with seed_dev[b] draws — a micro-batched request gets its own noise stream.
+  if (seed_dev) seed = seed_per_row ? seed_dev[blockIdx.y] : *seed_dev;
+  const uint32_t bkey = (seed_dev && seed_per_row) ? 0u : (uint32_t)blockIdx.y;
   __shared__ double red[8];
   __shared__ double base_s[kSrcFramesPerBlock];
   __shared__ float f0_s[kSrcFramesPerBlock];
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
       ph = 0.f;                                          // the fundamental keeps phase 0
     } else {
       uint32_t r[4];
-      philox4x32_10((uint32_t)b, 0xFFFFFFFFu, threadIdx.x, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      philox4x32_10(bkey, 0xFFFFFFFFu, threadIdx.x, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
       ph = (2.f * u01(r[0]) - 1.f) * 3.14159265358979f;
     }
     phi_s[threadIdx.x] = ph;
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
     if (!noise) {
       const unsigned long long nq = ((unsigned long long)n0 + (unsigned long long)sample0) >> 2;   // absolute quad index
       uint32_t r[4];
-      philox4x32_10((uint32_t)nq, (uint32_t)(nq >> 32) ^ ((uint32_t)b << 8), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      philox4x32_10((uint32_t)nq, (uint32_t)(nq >> 32) ^ (bkey << 8), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
       const float r0 = sqrtf(-2.f * __logf(u01(r[0]))), r1 = sqrtf(-2.f * __logf(u01(r[2])));
       float s0, c0, s1, c1;
       __sincosf(6.2831853f * u01(r[1]) - 3.14159265f, &s0, &c0);       // argument in (-pi, pi]: MUFU accuracy range
@@ -246,12 +252,19 @@ __global__ void __launch_bounds__(256) f0_sum_kernel(const float* __restrict__ f
   }
 }
 
+__global__ void seed_bump_kernel(uint64_t* seed_dev) { *seed_dev += 1ull; }
+
 cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
                           const float* lin_w, const float* lin_b, float* s, cudaStream_t st, const double* f0_sum0,
-                          long long sample0, double* f0_sum_out) {
+                          long long sample0, double* f0_sum_out, uint64_t* seed_dev, int seed_per_row) {
   dim3 grid((T + kSrcFramesPerBlock - 1) / kSrcFramesPerBlock, B);
-  source_kernel<<<grid, 256, 0, st>>>(f0, T, seed, phase_vec, noise, lin_w, lin_b, s, f0_sum0, sample0);
+  source_kernel<<<grid, 256, 0, st>>>(f0, T, seed, phase_vec, noise, lin_w, lin_b, s, f0_sum0, sample0, seed_dev,
+                                      seed_per_row);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && seed_dev && !seed_per_row) {
+    seed_bump_kernel<<<1, 1, 0, st>>>(seed_dev);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess || !f0_sum_out) return e;
   f0_sum_kernel<<<B, 256, 0, st>>>(f0, T, f0_sum0, f0_sum_out);      // after the source kernel: out may alias f0_sum0
   return cudaGetLastError();

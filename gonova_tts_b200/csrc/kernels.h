@@ -17,7 +17,8 @@ cudaError_t launch_f0_head(const void* h, int elem_bytes, int rows, int T, const
 // SineGen + SourceModuleHnNSF: f0 [B,T] -> s [B, 480T]
 cudaError_t launch_source(const float* f0, int B, int T, uint64_t seed, const float* phase_vec, const float* noise,
                           const float* lin_w, const float* lin_b, float* s, cudaStream_t st,
-                          const double* f0_sum0 = nullptr, long long sample0 = 0, double* f0_sum_out = nullptr);
+                          const double* f0_sum0 = nullptr, long long sample0 = 0, double* f0_sum_out = nullptr,
+                          uint64_t* seed_dev = nullptr, int seed_per_row = 0);
 // STFT n_fft 16 hop 4, periodic Hann, center/reflect: s [B, L] (row stride L) ->
 // spec [B, total_rows, C_ld] (elem_bytes 2 = bf16 / 4 = fp32): front_rows zero rows, F = L/4+1 frames, zero rows after
 cudaError_t launch_stft(const float* s, int B, int L, const int* lengths, void* spec_nlc, int elem_bytes, int round_tf32,

@@ -50,7 +50,11 @@ class _SourceModule:
         return self._owner.source_from_f0(f0, seed=seed, phase_vec=phase_vec, noise=noise)
 
 
-class B200HiFT:
+class B200HiFT(torch.nn.Module):
+    """An nn.Module only so that it can sit where the engine keeps its vocoder: `s3gen.mel2wav` is a registered child
+    module, and nn.Module.__setattr__ refuses anything else there.  It has no parameters or buffers (the weights live
+    re-packed inside the C handle); `state_dict()` is empty and `S3Gen.load_state_dict` reaches `_load_from_state_dict`
+    below, which re-creates the handle from the `mel2wav.*` entries."""
     sampling_rate = 24000
     istft_params = {"n_fft": 16, "hop_len": 4}
     audio_limit = 0.99
@@ -61,6 +65,7 @@ class B200HiFT:
         """bucket_frames > 1: `inference()` rounds T up to a multiple of it and masks the tail through `lengths`, so a
         service that sees a new sentence length on every call (services/tts/server.py:118-182) keeps hitting the
         handle's launch-plan cache (gnv_plan_stats).  Results for the first T frames do not change."""
+        super().__init__()
         if dtype not in _cabi.DTYPE:
             raise ValueError(f"dtype must be one of {sorted(_cabi.DTYPE)}")
         self.device = torch.device(device)
@@ -70,6 +75,24 @@ class B200HiFT:
             raise RuntimeError("B200HiFT needs a CUDA device (B200, sm_100a); none is visible")
         self.dtype = dtype
         self._lib = _cabi.load()
+        self._flags = ((_cabi.FLAG_SIMT_CONV if simt_conv else 0) | (_cabi.FLAG_PRECISE_ACT if precise_act else 0) |
+                       (_cabi.FLAG_TC_V1 if tc_v1 else 0))
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self._h = None
+        self._h = self._create_handle(state_dict, prefix)
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_pinned = False        # a CUDA graph was captured over self._ws: it may never be freed or moved
+        self._ws_retired = []          # ... and if a larger one is needed anyway, the captured one is kept alive here
+        self.bucket_frames = int(bucket_frames)
+        self._lock = threading.Lock()
+        self._seed = 0
+        self._tap_hook = None          # service.chunk_tap: streams the PCM of an inference() call chunk by chunk
+        self.counters = {"calls": 0, "frames": 0}      # surfaced by service.decoder_stats (get_stats()["decoder"])
+        self.f0_predictor = _F0Predictor(self)
+        self.m_source = _SourceModule(self)
+
+    def _create_handle(self, state_dict: Dict[str, torch.Tensor], prefix: str = ""):
         folded = fold_state_dict(state_dict, prefix=prefix)
         names = sorted(folded)
         arr = (_cabi.GnvWeight * len(names))()
@@ -82,20 +105,31 @@ class B200HiFT:
             arr[i].ndim = t.dim()
             for d in range(t.dim()):
                 arr[i].shape[d] = t.shape[d]
-        flags = ((_cabi.FLAG_SIMT_CONV if simt_conv else 0) | (_cabi.FLAG_PRECISE_ACT if precise_act else 0) |
-                 (_cabi.FLAG_TC_V1 if tc_v1 else 0))
         h = C.c_void_p()
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.device = torch.device("cuda", dev_index)
-        rc = self._lib.gnv_create(arr, len(names), dev_index, _cabi.DTYPE[dtype], flags, C.byref(h))
+        rc = self._lib.gnv_create(arr, len(names), self.device.index, _cabi.DTYPE[self.dtype], self._flags, C.byref(h))
         _cabi.check(rc, None, "gnv_create")
-        self._h = h
-        self._ws: Optional[torch.Tensor] = None
-        self.bucket_frames = int(bucket_frames)
-        self._lock = threading.Lock()
-        self._seed = 0
-        self.f0_predictor = _F0Predictor(self)
-        self.m_source = _SourceModule(self)
+        del keep
+        return h
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """`S3Gen.load_state_dict(...)` with `mel2wav.*` entries (upstream key names, weight-norm folded or not):
+        the decoder handle is rebuilt from them.  No entries under the prefix: nothing happens (strict: reported as
+        missing, like a module whose parameters are absent)."""
+        sub = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        if not sub:
+            if strict:
+                missing_keys.append(prefix + "*")
+            return
+        try:
+            with self._lock:
+                new = self._create_handle(sub)
+                old, self._h = self._h, new
+                if old is not None and old.value:
+                    torch.cuda.synchronize(self.device)
+                    self._lib.gnv_destroy(old)
+        except Exception as e:   # load_state_dict reports, it does not raise from inside the walk
+            error_msgs.append(f"{prefix}: {e}")
 
     # -- construction helpers ---------------------------------------------------------------------
     @classmethod
@@ -137,15 +171,37 @@ class B200HiFT:
         _cabi.check(self._lib.gnv_workspace_bytes(self._h, B, T, C.byref(n)), self._h, "gnv_workspace_bytes")
         return n.value
 
-    def _workspace(self, B: int, T: int) -> torch.Tensor:
+    def _workspace(self, B: int, T: int, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The scratch tensor a (B, T) call runs in: the caller's `workspace` if given (checked), else the decoder's own,
+        grown on demand.  A workspace a CUDA graph was captured over (`pin_workspace`) is never freed: the graph's
+        kernel arguments and tensor maps point into it for good."""
         need = self.workspace_bytes(B, T)
+        if workspace is not None:
+            if (workspace.dtype != torch.uint8 or workspace.device != self.device or not workspace.is_contiguous()
+                    or workspace.numel() < need + 1024):
+                raise ValueError(f"workspace must be a contiguous uint8 tensor on {self.device} of at least "
+                                 f"{need + 1024} bytes (workspace_bytes(B, T) + 1024)")
+            return workspace
         if self._ws is None or self._ws.numel() < need + 1024:
             # every launch plan is tied to the workspace address: grow by at least half so that a run of slightly
             # longer sentences does not rebuild the plans each time
             grow = 0 if self._ws is None else self._ws.numel() + self._ws.numel() // 2
+            if self._ws_pinned:
+                self._ws_retired.append(self._ws)
+                self._ws_pinned = False
             self._ws = None
             self._ws = torch.empty(max(need + 1024, grow), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def pin_workspace(self) -> None:
+        """Called by whoever captures a CUDA graph over calls that used the decoder's own workspace."""
+        with self._lock:
+            if self._ws is not None:
+                self._ws_pinned = True
+
+    def new_workspace(self, B: int, T: int) -> torch.Tensor:
+        """A private workspace for (B, T) to pass as `workspace=` (e.g. one per captured CUDA graph)."""
+        return torch.empty(self.workspace_bytes(B, T) + 1024, dtype=torch.uint8, device=self.device)
 
     def reserve(self, B: int, T: int) -> None:
         """Allocate the workspace for the largest (B, T) the caller will send, once (e.g. at service start-up)."""
@@ -164,6 +220,25 @@ class B200HiFT:
         if t.device != self.device:
             raise RuntimeError(f"{name} is on {t.device}, the decoder is on {self.device}")
         return t.to(torch.float32).contiguous()
+
+    def _check_out(self, t: Optional[torch.Tensor], numel: int, name: str) -> Optional[torch.Tensor]:
+        """Caller-supplied output buffers go to the C ABI by raw pointer: anything but a contiguous fp32 tensor of
+        exactly the right size on the decoder's device would be written out of bounds or read back as garbage."""
+        if t is None:
+            return None
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.dtype != torch.float32 or t.device != self.device or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"{name} must be a contiguous float32 tensor on {self.device} with {numel} elements "
+                             f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()}, {t.numel()} elements)")
+        return t
+
+    def _next_seed(self, seed: Optional[int]) -> int:
+        if seed is not None:
+            return int(seed)
+        with self._lock:
+            self._seed += 1
+            return self._seed
 
     def _lengths(self, lengths, B):
         if lengths is None:
@@ -198,9 +273,7 @@ class B200HiFT:
             phase_vec = self._check_in(phase_vec, "phase_vec").reshape(B, 9)
         if noise is not None:
             noise = self._check_in(noise, "noise").reshape(B, 9, T * SAMPLES_PER_FRAME)
-        if seed is None:
-            self._seed += 1
-            seed = self._seed
+        seed = self._next_seed(seed)
         s = torch.empty(B, 1, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
         rc = self._lib.gnv_source(self._h, _ptr(f0), B, T, C.c_uint64(seed), _ptr(phase_vec), _ptr(noise), _ptr(s),
                                   _stream_ptr(self.device))
@@ -227,7 +300,8 @@ class B200HiFT:
         return s, out
 
     @torch.no_grad()
-    def decode(self, x: torch.Tensor, s: torch.Tensor, lengths=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def decode(self, x: torch.Tensor, s: torch.Tensor, lengths=None, out: Optional[torch.Tensor] = None,
+               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
         """HiFTGenerator.decode(x=mel [B,80,T], s=source [B,1,480T]) -> wav [B,480T]."""
         x = self._check_in(x, "x")
         s = self._check_in(s, "s")
@@ -237,9 +311,12 @@ class B200HiFT:
         if s.numel() != B * T * SAMPLES_PER_FRAME:
             raise ValueError(f"s must hold B*480*T = {B * T * SAMPLES_PER_FRAME} samples, got {s.numel()}")
         lengths = self._lengths(lengths, B)
+        out = self._check_out(out, B * T * SAMPLES_PER_FRAME, "out")
         wav = out if out is not None else torch.empty(B, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=self.device)
+        self.counters["calls"] += 1
+        self.counters["frames"] += B * T
         with self._lock:
-            ws = self._workspace(B, T)
+            ws = self._workspace(B, T, workspace)
             p, n = self._aligned(ws)
             rc = self._lib.gnv_decode(self._h, _ptr(x), _ptr(s), _ptr(lengths), B, T, _ptr(wav), C.c_void_p(p), n,
                                       _stream_ptr(self.device))
@@ -249,21 +326,38 @@ class B200HiFT:
     @torch.no_grad()
     def inference(self, speech_feat: torch.Tensor, cache_source: Optional[torch.Tensor] = None, lengths=None,
                   seed: Optional[int] = None, out: Optional[torch.Tensor] = None,
-                  source_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """HiFTGenerator.inference(speech_feat, cache_source) -> (wav [B,480T], source [B,1,480T])."""
+                  source_out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                  seed_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """HiFTGenerator.inference(speech_feat, cache_source) -> (wav [B,480T], source [B,1,480T]).
+
+        seed_dev: int64 CUDA tensor holding the NSF seed(s) (gnv_inference_dseed); `seed` is ignored then.
+          one element: the source kernel reads it at RUN time and a one-thread kernel adds 1 to it afterwards, so a
+            CUDA graph captured over this call draws fresh noise at every replay;
+          B elements (B > 1): one seed per row; row b gets exactly the source `inference(mel[b:b+1], seed=seed_dev[b])`
+            gets, whatever batch it rides in (the micro-batcher's per-request seeds)."""
         mel = self._check_in(speech_feat, "speech_feat")
         B, Cm, T = mel.shape
         if Cm != 80:
             raise ValueError("speech_feat must be [B, 80, T]")
+        hook = self._tap_hook
+        if hook is not None and out is None and source_out is None and seed_dev is None and lengths is None:
+            tapped = hook(self, mel, cache_source, seed)
+            if tapped is not None:
+                return tapped
+        self.counters["calls"] += 1
+        self.counters["frames"] += B * T
         cache_len = 0
         if cache_source is not None and cache_source.numel() != 0:
             cache_source = self._check_in(cache_source, "cache_source").reshape(B, -1)
             cache_len = cache_source.shape[1]
         else:
             cache_source = None
-        if seed is None:
-            self._seed += 1
-            seed = self._seed
+        if seed_dev is not None:
+            if (seed_dev.dtype != torch.int64 or seed_dev.device != self.device or not seed_dev.is_contiguous()
+                    or seed_dev.numel() not in (1, B)):
+                raise ValueError(f"seed_dev must be a contiguous int64 tensor on {self.device} with 1 or B elements")
+        else:
+            seed = self._next_seed(seed)
         T_true = T
         if self.bucket_frames > 1 and out is None and source_out is None and T % self.bucket_frames:
             T = -(-T // self.bucket_frames) * self.bucket_frames
@@ -272,14 +366,22 @@ class B200HiFT:
                 lengths = [T_true] * B
         lengths = self._lengths(lengths, B)
         L = T * SAMPLES_PER_FRAME
+        out = self._check_out(out, B * L, "out")
+        source_out = self._check_out(source_out, B * L, "source_out")
         wav = out if out is not None else torch.empty(B, L, dtype=torch.float32, device=self.device)
         src = source_out if source_out is not None else torch.empty(B, 1, L, dtype=torch.float32, device=self.device)
         with self._lock:
-            ws = self._workspace(B, T)
+            ws = self._workspace(B, T, workspace)
             p, n = self._aligned(ws)
-            rc = self._lib.gnv_inference(self._h, _ptr(mel), _ptr(cache_source), cache_len, _ptr(lengths), B, T,
-                                         C.c_uint64(seed), _ptr(wav), _ptr(src), C.c_void_p(p), n,
-                                         _stream_ptr(self.device))
+            if seed_dev is not None:
+                per_row = 1 if (seed_dev.numel() == B and B > 1) else 0
+                rc = self._lib.gnv_inference_dseed(self._h, _ptr(mel), _ptr(cache_source), cache_len, _ptr(lengths), B,
+                                                   T, _ptr(seed_dev), per_row, _ptr(wav), _ptr(src), C.c_void_p(p), n,
+                                                   _stream_ptr(self.device))
+            else:
+                rc = self._lib.gnv_inference(self._h, _ptr(mel), _ptr(cache_source), cache_len, _ptr(lengths), B, T,
+                                             C.c_uint64(seed), _ptr(wav), _ptr(src), C.c_void_p(p), n,
+                                             _stream_ptr(self.device))
             _cabi.check(rc, self._h, "gnv_inference")
         if T != T_true:                                   # bucketed: hand back exactly the caller's frames
             Lt = T_true * SAMPLES_PER_FRAME

@@ -198,9 +198,14 @@ class GraphedInference:
     The per-launch host cost of the ~70 kernels of a decode dominates the latency of a small chunk
     (BASELINE config 2: batch 1, first chunk); a graph removes it.  All C-ABI decode calls are
     capture-safe: they launch on the caller's current stream and neither allocate nor synchronise once
-    the (B, T) plan exists, which the warm-up below guarantees.  The NSF noise seed is baked into the
-    captured launch parameters, so every replay draws the same noise (use decode(x, s) with a host-side
-    source for per-call noise)."""
+    the (B, T) plan exists, which the warm-up below guarantees.
+
+    Two things a captured graph bakes in are kept out of harm's way:
+      * the workspace — the graph's kernel arguments and tensor maps point into it for good, so the graph owns a
+        PRIVATE workspace tensor (never the decoder's shared one, which later, larger eager calls regrow and free);
+      * the NSF noise seed — it lives in a device word (`self.seed_dev`) that the source kernel reads at run time and a
+        one-thread kernel in the graph bumps, so every replay draws fresh noise like upstream's `torch.randn_like`
+        (`reseed()` sets it; replay i after reseed(s) equals an eager `inference(seed=s + i)`)."""
 
     def __init__(self, hift: B200HiFT, B: int, T: int, emit_frames: Optional[int] = None, seed: int = 1,
                  limit: float = 0.99, want_i16: bool = True, trim_fade: bool = False):
@@ -211,10 +216,12 @@ class GraphedInference:
         self.wav = torch.empty(B, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=dev)
         self.src = torch.empty(B, 1, T * SAMPLES_PER_FRAME, dtype=torch.float32, device=dev)
         self.pcm = torch.empty(B, n_emit, dtype=torch.int16 if want_i16 else torch.float32, device=dev)
+        self.seed_dev = torch.full((1,), int(seed), dtype=torch.int64, device=dev)
+        self._ws = hift.new_workspace(B, T)
         fw = trim_fade_window(dev) if trim_fade else None
 
         def body():
-            hift.inference(self.mel, seed=seed, out=self.wav, source_out=self.src)
+            hift.inference(self.mel, out=self.wav, source_out=self.src, workspace=self._ws, seed_dev=self.seed_dev)
             pcm_tail(self.wav[:, :n_emit], None, fw, limit, want_i16=want_i16, want_f32=not want_i16,
                      out_i16=self.pcm if want_i16 else None, out_f32=None if want_i16 else self.pcm)
 
@@ -228,6 +235,10 @@ class GraphedInference:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             body()
+        self.reseed(seed)                           # the warm-up calls advanced the device seed
+
+    def reseed(self, seed: int) -> None:
+        self.seed_dev.fill_(int(seed))
 
     @torch.no_grad()
     def __call__(self, mel: torch.Tensor) -> torch.Tensor:

@@ -17,7 +17,10 @@
  *   - `stream` is a cudaStream_t passed as void* (torch: torch.cuda.current_stream().cuda_stream).  All work is
  *     ordered on it: small batches (B*T <= 4096 frames) also use streams the handle owns for independent branches,
  *     forked from and joined back into `stream` by events, so to the caller — and to a stream capture — a call
- *     still is one piece of work on `stream`.  One call at a time per handle.
+ *     still is one piece of work on `stream`.  ONE CALL AT A TIME PER HANDLE: the fork streams and events belong to the
+ *     handle, so two threads (or two streams) driving one handle concurrently must serialise their calls themselves
+ *     (the Python shim holds a lock); calls on different streams one after the other are fine — a launch plan built
+ *     on one stream is waited for by the first call that uses it from another.
  *   - tensors are fp32, contiguous, in the layouts of the upstream PyTorch module:
  *     mel [B,80,T]  source s [B,1,480*T]  wav [B,480*T]  f0 [B,T].
  */
@@ -31,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GNV_ABI_VERSION 1
+#define GNV_ABI_VERSION 2
 
 /* arithmetic of the conv GEMMs (activations/weights as stored in HBM; accumulation is fp32) */
 #define GNV_DTYPE_TF32 0      /* tcgen05 kind::tf32 — the "fp32 parity" path                       */
@@ -113,6 +116,18 @@ int gnv_inference(gnv_handle h, const float* mel, const float* cache_source, int
                   const int32_t* lengths, int B, int T, uint64_t seed,
                   float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* gnv_inference with the NSF seed(s) in DEVICE memory.  Same replaced call as gnv_inference.
+ *   per_row == 0: one word; the source kernel reads *seed_dev when it RUNS and a one-thread kernel adds 1 to it behind
+ *     it.  For CUDA-graph capture of a fixed chunk shape (first-chunk latency, BASELINE configs[1]): a by-value seed
+ *     would be baked into the graph and every replay would repeat the same noise, which upstream's
+ *     `torch.randn_like` (SineGen) never does.  Replay i after *seed_dev = s equals gnv_inference(seed = s + i).
+ *   per_row != 0: seed_dev[B], one seed per utterance of the batch (not modified).  Row b gets exactly the source an
+ *     utterance decoded alone — gnv_inference(B = 1, seed = seed_dev[b]) — gets: a request's audio does not depend on
+ *     which micro-batch (services/tts/server.py:110-186) it happened to share. */
+int gnv_inference_dseed(gnv_handle h, const float* mel, const float* cache_source, int cache_len,
+                        const int32_t* lengths, int B, int T, uint64_t* seed_dev, int per_row,
+                        float* wav, float* s_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement hook (bench.py's roofline): one gnv_inference with a CUDA event recorded after every
  * launch on `stream`; synchronises the stream before returning.  For launch i < *n_out:
  * ms_out[i] device time, kind_out[i] one of GNV_LAUNCH_*, flops_out[i] the layer's algorithmic flops
@@ -143,7 +158,9 @@ int gnv_pcm_tail(const float* cur, int64_t cur_stride, const float* prev_tail, c
  * replaces nothing in the reference (it ships float32 only, server.py:152); SURVEY 8f-3. */
 int gnv_pcm_mulaw(const int16_t* pcm, int64_t n, uint8_t* out, void* stream);
 
-/* ---- unit-test hooks (one kernel each; used by tests/, not by the service) -------------------- */
+/* ---- unit-test hooks (one kernel each; used by tests/, not by the service) --------------------
+ * TEST ONLY: unlike every entry point above, gnv_stft / gnv_istft / gnv_conv1d allocate scratch with cudaMalloc and
+ * synchronise the stream before returning.  Never call them from a serving path or inside a stream capture. */
 
 /* HiFTGenerator._stft + cat(real, imag): s [B, L] -> spec [B, 18, L/4+1] (fp32, NCT). */
 int gnv_stft(const float* s, int B, int L, float* spec_nct, void* stream);

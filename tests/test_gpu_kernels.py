@@ -234,10 +234,13 @@ def test_conv_tcgen05_matches_torch(lib, cuda_device, geom, dtype):
     snr = snr_db(got, want)
     # operands rounded to 10 (tf32) / 7 (bf16) mantissa bits, fp32 accumulate; the activation output
     # is stored in the operand type of the next conv, so bf16 adds one more rounding of the result.
+    # The rounding alone (operands and stored activation rounded on the CPU, fp32 accumulate) gives, over these
+    # geometries: tf32 max-abs <= 1.8e-3 / SNR >= 68.5 dB, bf16 <= 1.43e-2 / >= 50.5 dB.  Bounds at < 2x that.
+    print(f"[parity] layer {name} {dtype}: max-abs {err:.3e} SNR {snr:.1f} dB")
     if dtype == "tf32":
-        assert err < 4e-3 and snr > 60.0, (err, snr)
+        assert err < 3e-3 and snr > 64.0, (err, snr)
     else:
-        assert err < 4e-2 and snr > 40.0, (err, snr)
+        assert err < 2.5e-2 and snr > 46.0, (err, snr)
 
 
 def test_conv_tcgen05_equals_cuda_core_kernel_on_same_operands(lib, cuda_device):

@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(raw, name), f"{name} is declared in the header but not exported"
     assert sorted(_cabi.SYMBOLS) == declared
-    assert lib.gnv_abi_version() == 1
+    assert lib.gnv_abi_version() == 2
 
 
 def test_create_fails_loudly_without_a_gpu_or_weights(lib):
