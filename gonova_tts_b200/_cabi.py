@@ -21,6 +21,7 @@ SYMBOLS = [
     "gnv_source", "gnv_decode", "gnv_inference", "gnv_inference_profile", "gnv_pcm_tail", "gnv_pcm_mulaw", "gnv_stft", "gnv_istft", "gnv_conv1d",
     "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
     "gnv_plan_stats", "gnv_source_stream", "gnv_inference_dseed",
+    "gnv_debug_chain_trace",
 ]
 
 
@@ -72,6 +73,7 @@ def load():
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_float, f32p, f32p,
                                C.c_int, vp]
     lib.gnv_debug_tap.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, vp, f32p, C.c_size_t, C.POINTER(C.c_int64), vp]
+    lib.gnv_debug_chain_trace.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_cluster_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_decode_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_inference_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]

@@ -36,6 +36,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv_pair.cuh"
+#include "conv_chain.cuh"
 #include "kernels.h"
 
 using namespace gnv;
@@ -99,10 +100,12 @@ enum SimtVariant { SV_FFF = 0, SV_BBB = 1, SV_FFB = 2 };
 
 struct ConvOp {
   bool tc = false;
-  int tcv = 1;           // 1: conv_tc_kernel (one tile per CTA), 2: conv_tc2_kernel (persistent), 3: conv_pair_kernel
+  int tcv = 1;           // 1: conv_tc_kernel (one tile per CTA), 2: conv_tc2_kernel (persistent), 3: conv_pair_kernel,
+                         // 4: conv_chain_kernel (a whole ResBlock)
   ConvTcLaunch tcl;
   ConvTc2Launch tc2l;
   ConvPairLaunch pairl;
+  ConvChainLaunch chainl;
   ConvGeom g;
   EpiParams ep;
   const void* A = nullptr;
@@ -196,6 +199,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
   for (ConvOp* op : ops) {
     if (op->tc && op->tcv == 2) bytes += sizeof(ConvTc2Maps);
     if (op->tc && op->tcv == 3) bytes += sizeof(ConvPairMaps);
+    if (op->tc && op->tcv == 4) bytes += sizeof(ConvChainMaps);
   }
   if (!bytes) return "";
   MapsSlot sl;
@@ -238,6 +242,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
   for (ConvOp* op : ops) {
     if (op->tc && op->tcv == 2) { memcpy(sl.staging + off, &op->tc2l.maps, sizeof(ConvTc2Maps)); off += sizeof(ConvTc2Maps); }
     if (op->tc && op->tcv == 3) { memcpy(sl.staging + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
+    if (op->tc && op->tcv == 4) { memcpy(sl.staging + off, &op->chainl.maps, sizeof(ConvChainMaps)); off += sizeof(ConvChainMaps); }
   }
   cudaError_t e = cudaMemcpyAsync(sl.d, sl.staging, bytes, cudaMemcpyHostToDevice, st);
   // `st` is the handle's own upload stream (or the test hook's stream): the copy is complete before the plan is
@@ -250,6 +255,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
   for (ConvOp* op : ops) {
     if (op->tc && op->tcv == 2) { op->tc2l.d_maps = reinterpret_cast<const ConvTc2Maps*>((char*)sl.d + off); off += sizeof(ConvTc2Maps); }
     if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)sl.d + off); off += sizeof(ConvPairMaps); }
+    if (op->tc && op->tcv == 4) { op->chainl.d_maps = reinterpret_cast<const ConvChainMaps*>((char*)sl.d + off); off += sizeof(ConvChainMaps); }
   }
   *slot = sl;
   return "";
@@ -273,6 +279,8 @@ struct gnv_decoder {
                             // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
   int fuse_k3_max_c = 64;   // ... and for k = 3 ResBlocks up to this many channels (GONOVA_FUSE_K3_MAX_C).  Measured at C = 128:
                             // the three fused k = 3 pairs take 1.51 ms against 1.59 ms in six launches, the step does not move
+  int chain_max_k = 3;      // whole-ResBlock kernel (conv_chain_kernel) for the blocks that open a stage's running sum (j = 0)
+  int chain_max_c = 64;     // ... with at most this many taps / channels (GONOVA_CHAIN_MAX_K / _MAX_C; 0 = never)
   std::map<std::pair<int, int>, int> launch_counts;   // (B, T) -> conv launches of the last plan built
   ConvTc2Options tc2opt;
   int snake_kind = ACT_SNAKE;
@@ -610,6 +618,7 @@ std::string make_epi_only(const gnv_decoder* h, const ConvLayer& L, int B, int L
 
 cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   if (op.tc) {
+    if (op.tcv == 4) return launch_conv_chain(op.chainl, lengths, st);
     if (op.tcv == 3) return launch_conv_pair(op.pairl, lengths, st);
     if (op.tcv == 2) return launch_conv_tc2(op.tc2l, lengths, st);
     if (!lengths) return launch_conv_tc(op.tcl, st);
@@ -673,8 +682,37 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     const int lm = i == 0 ? 8 : (i == 1 ? 40 : 120), la = i == 2 ? 1 : 0;
     float *F1 = Fp(w.F1[i]), *F2 = Fp(w.F2[i]), *F3 = Fp(w.F3[i]);
     void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
+    auto chain_block = [&](const ResBlockW& R, int stage, int j, bool final_to_sum) {
+      return h->use_tc && h->tc_version == 2 && final_to_sum && j == 0 && R.c1[0].k <= h->chain_max_k &&
+             kStageC[stage] <= h->chain_max_c && R.c1[0].k >= 3;
+    };
     auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
                         int j, const std::string& rbname, void* E3) {
+      // ---- the whole block in one kernel (conv_chain_kernel): reads the fp32 stage input, keeps the residual stream in
+      // TMEM across the six convs, writes out_scale * x.  For the block that OPENS the stage's running sum (j = 0: no
+      // accumulate, no successor activation).
+      if (chain_block(R, i, j, final_to_sum) && e.empty()) {
+        ConvChainSpec cs;
+        for (int d = 0; d < 3; ++d) {
+          cs.w1[d] = R.c1[d].w; cs.w2[d] = R.c2[d].w;
+          cs.bias1[d] = R.c1[d].bias; cs.bias2[d] = R.c2[d].bias;
+          cs.alpha1[d] = R.a1[d]; cs.alpha2[d] = R.a2[d];
+          cs.dil[d] = R.c1[d].dil;
+        }
+        ConvOp op;
+        memset(&op.g, 0, sizeof(op.g));
+        memset(&op.ep, 0, sizeof(op.ep));
+        const char* ce = make_conv_chain_launch(&op.chainl, h->eb, res_first, F3, cs, B, Ls, kStageC[i], R.c1[0].k,
+                                                1.f / 3.f, snake, h->dtype == GNV_DTYPE_TF32 ? 1 : 0, lm, la,
+                                                h->tc2opt.max_ctas);
+        if (!*ce) {
+          op.tc = true; op.tcv = 4;
+          op.name = rbname + ".chain";
+          op.flops = 6.0 * (2.0 * B * (double)Ls * kStageC[i] * kStageC[i] * R.c1[0].k);
+          ops.push_back(op);
+          return;
+        }
+      }
       void* cur = EA;                 // the (activated) input of the next dilation step
       for (int d = 0; d < 3; ++d) {
         EpiSpec es; es.len_mul = lm; es.len_add = la;
@@ -759,7 +797,8 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     {
       EpiSpec es; es.len_mul = lm; es.len_add = la;
       es.res = F1; es.raw = F2; es.reflect_front = (i == 2);
-      for (int j = 0; j < 3; ++j) es.acts.push_back({snake, h->rb[3 * i + j].a1[0], 0.f, E[j]});
+      for (int j = 0; j < 3; ++j)     // (a chained block applies its own first Snake to the F2 tile it loads anyway)
+        if (!chain_block(h->rb[3 * i + j], i, j, true)) es.acts.push_back({snake, h->rb[3 * i + j].a1[0], 0.f, E[j]});
       add(ops, h->ups[i], X, Lx, es, "ups." + std::to_string(i));
     }
     for (int j = 0; j < 3; ++j)       // fork mode: every ResBlock of the stage has its own residual stream and ping-pong buffer
@@ -785,7 +824,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
       const int N = atoi(op.name.c_str() + 10);
       op.stage = N / 3; op.rb = N % 3;
       const std::string tail = op.name.substr(op.name.rfind('.') + 1);
-      op.rb_last = tail == "pair2" || (tail == "2" && op.name.find(".convs2.") != std::string::npos);
+      op.rb_last = tail == "pair2" || tail == "chain" || (tail == "2" && op.name.find(".convs2.") != std::string::npos);
     }
   }
   std::vector<ConvOp*> all;
@@ -1069,6 +1108,8 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
   if (const char* v = getenv("GONOVA_FUSE_MAX_C")) h->fuse_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_FUSE_K3_MAX_C")) h->fuse_k3_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_PAIR_CTA2")) h->pair_cta2 = atoi(v);
+  if (const char* v = getenv("GONOVA_CHAIN_MAX_K")) h->chain_max_k = atoi(v);
+  if (const char* v = getenv("GONOVA_CHAIN_MAX_C")) h->chain_max_c = atoi(v);
   if (const char* v = getenv("GONOVA_FORK_MAX_FRAMES")) h->fork_max_frames = atoi(v);
   if (const char* v = getenv("GONOVA_MAX_PLANS")) h->max_plans = (size_t)(atoi(v) > 0 ? atoi(v) : 1);
   h->snake_kind = (dtype == GNV_DTYPE_FP32 || (flags & GNV_FLAG_PRECISE_ACT)) ? ACT_SNAKE : ACT_SNAKE_FAST;
@@ -1106,6 +1147,7 @@ int gnv_create(const GnvWeight* weights, int n_weights, int device, int dtype, u
     ce = conv_tc_init();
     if (ce == cudaSuccess) ce = conv_tc2_init();
     if (ce == cudaSuccess) ce = conv_pair_init();
+    if (ce == cudaSuccess) ce = conv_chain_init();
     if (ce != cudaSuccess) {
       gnv_destroy(h);
       return fail_cuda(nullptr, "conv_tc_init", ce);
@@ -1415,6 +1457,14 @@ int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace,
   if ((size_t)B * L * C > out_capacity_elems) return fail(h, "tap output buffer too small");
   out_shape3[0] = B; out_shape3[1] = C; out_shape3[2] = L;
   GNV_CK(h, "tap", launch_nlc_to_nct(src, B, L, C, Cld ? Cld : C, 4, out_nct, (cudaStream_t)stream));
+  return 0;
+}
+
+int gnv_debug_chain_trace(unsigned long long* out, int cap, int* n_out) {
+  if (!out || !n_out) return fail(nullptr, "NULL argument");
+  const int n = conv_chain_read_trace(out, cap);
+  if (n < 0) return fail(nullptr, "chain trace: CUDA error");
+  *n_out = n;
   return 0;
 }
 

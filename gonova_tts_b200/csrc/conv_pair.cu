@@ -214,8 +214,8 @@ cudaError_t launch_conv_pair(const ConvPairLaunch& L, const int* lengths, cudaSt
   const ConvPairMaps* dm = L.d_maps;
   // the RAGGED instantiation (dead tiles skipped) only when the batch carries lengths: the dense walk stays as it was
   const auto go = [&](auto dense, auto ragged, bool pair) {
-    return lengths ? launch_persistent(ragged, L.grid, L.smem_bytes, st, pair, dm, p)
-                   : launch_persistent(dense, L.grid, L.smem_bytes, st, pair, dm, p);
+    return lengths ? launch_persistent(ragged, L.grid, L.smem_bytes, st, pair, 384, dm, p)
+                   : launch_persistent(dense, L.grid, L.smem_bytes, st, pair, 384, dm, p);
   };
   if (!p.cta2) {
     if (L.elem_bytes == 2) return go(conv_pair_kernel<__nv_bfloat16, false, false>, conv_pair_kernel<__nv_bfloat16, false, true>, false);

@@ -773,10 +773,11 @@ __device__ __noinline__ void emit_row0(const ConvTc2Params& p, const float* tab,
 bool pdl_enabled();      // GONOVA_PDL=0 switches programmatic dependent launch off
 int in_slots_cap();      // GONOVA_IN_SLOTS caps the epilogue-input prefetch slots
 template <typename Kern, typename... Args>
-inline cudaError_t launch_persistent(Kern kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, Args... args) {
+inline cudaError_t launch_persistent(Kern kernel, int grid, size_t smem, cudaStream_t st, bool cluster2, int threads,
+                                     Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -183,6 +183,10 @@ int gnv_conv1d(int device, int dtype, unsigned flags, int transposed,
 int gnv_debug_tap(gnv_handle h, const char* name, int B, int T, void* workspace, float* out_nct,
                   size_t out_capacity_elems, int64_t* out_shape3, void* stream);
 
+/* diagnostics (tuning only, env GONOVA_CHAIN_DBG=8): per-phase clock stamps CTA 0 of the whole-ResBlock kernel recorded since
+ * the last call; synchronises the device.  Word = role<<56 | lane<<48 | phase<<40 | event<<32 | clock32. */
+int gnv_debug_chain_trace(unsigned long long* out, int cap, int* n_out);
+
 /* diagnostics: resident 2-CTA clusters of the persistent conv kernel for a dynamic shared-memory size */
 int gnv_debug_cluster_probe(int smem_bytes, int grid, int* max_clusters);
 

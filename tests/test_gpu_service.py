@@ -109,7 +109,6 @@ def test_chunk_tap_streams_inside_generate(engines, cuda_device):
     eng.generate("Hello.")
     assert len(got) == n_before
     # the stream is the offline chunked decode of the same mel + source, bit for bit
-    mel = eng.last_mel
     with chunk_tap(dec, lambda *a: None):
         w2, src = dec.inference(ref.mel_for(text).to(cuda_device), seed=77)
     _, f32 = StreamingDecoder(dec, trim_fade=True).decode_all(ref.mel_for(text).to(cuda_device), src, want_i16=False)
@@ -121,8 +120,7 @@ def test_chunk_tap_streams_inside_generate(engines, cuda_device):
     want[:, :960] *= R.trim_fade_window()
     err, snr = float((w2.cpu() - want).abs().max()), snr_db(w2.cpu().numpy(), want.numpy())
     print(f"[parity] chunk_tap stream vs oracle single-shot decode: max-abs {err:.3e} SNR {snr:.1f} dB")
-    assert err <= 1e-3 and snr >= 40.0
-    assert mel.shape[2] == 324
+    assert err <= 2e-4 and snr >= 58.0
 
 
 def test_patched_synthesizer_yields_chunks_and_stats(engines, cuda_device):
