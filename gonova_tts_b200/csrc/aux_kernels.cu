@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
   __shared__ double red[8];
   __shared__ double base_s[kSrcFramesPerBlock];
   __shared__ float f0_s[kSrcFramesPerBlock];
-  __shared__ float phi_s[9], lw_s[9];
+  __shared__ float ca_s[9], sa_s[9], lw_s[9];            // 0.1 * lw_h * cos(phi_h), 0.1 * lw_h * sin(phi_h), lw_h
   const int b = blockIdx.y, t0 = blockIdx.x * kSrcFramesPerBlock;
   const float* f0b = f0 + (size_t)b * T;
   double part = 0.0;
@@ -164,8 +164,12 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
       philox4x32_10(bkey, 0xFFFFFFFFu, threadIdx.x, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
       ph = (2.f * u01(r[0]) - 1.f) * 3.14159265358979f;
     }
-    phi_s[threadIdx.x] = ph;
-    lw_s[threadIdx.x] = lin_w[threadIdx.x];
+    const float lw = lin_w[threadIdx.x];
+    float sp, cp;
+    sincosf(ph, &sp, &cp);                               // once per block and harmonic: the precise version
+    ca_s[threadIdx.x] = 0.1f * lw * cp;
+    sa_s[threadIdx.x] = 0.1f * lw * sp;
+    lw_s[threadIdx.x] = lw;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -209,26 +213,49 @@ __global__ void __launch_bounds__(256) source_kernel(const float* __restrict__ f
       __sincosf(6.2831853f * u01(r[3]) - 3.14159265f, &s1, &c1);
       z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
     }
+    // Running phase of the fundamental in cycles: reduced mod 1 in fp64 ONCE per four samples; the next three samples
+    // add the per-sample increment (<= 0.03 cycles) in fp32.
+    const double based = base_s[fi] + (double)(j0 + 1) * ((double)f / 24000.0);
+    const float bfrac0 = (float)(based - floor(based));
+    const float dcyc = f * (1.0f / 24000.0f);
     float o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int j = j0 + e;
-      // running phase of the fundamental in cycles, reduced mod 1 in fp64 once; each harmonic's phase is then
-      // (h+1) * frac in fp32 ((h+1)*frac <= 9: error <= 5e-7 cycles = 3e-6 rad, times the 0.1 sine amplitude)
-      const double based = base_s[fi] + (double)(j + 1) * ((double)f / 24000.0);
-      const float bfrac = (float)(based - floor(based));
-      float acc = lb;
+      // One MUFU sincos of the fundamental (argument reduced to (-pi, pi]); harmonics n = 2..9 by the Chebyshev
+      // recurrence  sin((n+1)x) = 2 cos(x) sin(nx) - sin((n-1)x)  (same for cos), two FMAs each instead of a range
+      // reduction and a MUFU.SIN per harmonic.  Each harmonic's random phase is a rotation folded into its two
+      // coefficients: 0.1 lw_h sin(n x + phi_h) = ca_h sin(n x) + sa_h cos(n x).  Error growth of the recurrence over
+      // 9 steps stays below 1e-5 of the 0.1 amplitude (tests/test_gpu_decode.py: <= 2e-5 against the fp64 oracle).
+      float tt = bfrac0 + (float)e * dcyc;
+      tt -= rintf(tt);                                                  // (-0.5, 0.5]
+      float s1v, c1v;
+      __sincosf(6.283185307179586f * tt, &s1v, &c1v);
+      const float k2 = 2.f * c1v;
+      float sp = 0.f, cp = 1.f, sc = s1v, cc = c1v;                      // (n-1) and n
+      float acc = 0.f;
+      if (noise) {
 #pragma unroll
-      for (int h = 0; h < 9; ++h) {
-        const float x = (float)(h + 1) * bfrac;
-        float tt = (x - floorf(x)) + phi_s[h] * 0.15915494309189535f;     // cycles; |phi| <= pi
-        tt -= rintf(tt);                                                  // (-0.5, 0.5]
-        const float sw = 0.1f * __sinf(6.283185307179586f * tt);          // |arg| <= pi: abs error ~ 2^-21
-        if (noise) acc = fmaf(lw_s[h], sw * uv + namp * noise[((size_t)b * 9 + h) * L + n0 + e], acc);
-        else acc = fmaf(lw_s[h], sw * uv, acc);
+        for (int h = 0; h < 9; ++h) {
+          const float sw = ca_s[h] * sc + sa_s[h] * cc;                  // 0.1 lw_h sin(n x + phi_h)
+          acc += sw * uv + lw_s[h] * namp * noise[((size_t)b * 9 + h) * L + n0 + e];
+          const float sn = fmaf(k2, sc, -sp), cn = fmaf(k2, cc, -cp);
+          sp = sc; cp = cc; sc = sn; cc = cn;
+        }
+        acc += lb;
+      } else {
+#pragma unroll
+        for (int h = 0; h < 9; ++h) {
+          acc = fmaf(ca_s[h], sc, acc);
+          acc = fmaf(sa_s[h], cc, acc);
+          const float sn = fmaf(k2, sc, -sp), cn = fmaf(k2, cc, -cp);
+          sp = sc; cp = cc; sc = sn; cc = cn;
+        }
+        acc = fmaf(acc, uv, lb);
+        acc = fmaf(namp * lw_norm, z[e], acc);
       }
-      if (!noise) acc = fmaf(namp * lw_norm, z[e], acc);
-      o[e] = tanhf(acc);
+      // tanh(a) = 1 - 2 / (exp(2a) + 1): two MUFU ops, absolute error ~1e-7 for the |a| < 2 this layer produces
+      const float ex = __expf(2.f * acc);
+      o[e] = 1.f - __fdividef(2.f, ex + 1.f);
     }
     *reinterpret_cast<float4*>(s + (size_t)b * L + n0) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -431,6 +458,27 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
   {
     const long long lo = (long long)fbase * C_ld, total = (long long)F * C_ld;
     const float* xb = x + (size_t)b * F * C_ld;
+    if (C_ld == 20) {
+      // 256 frames x 80 B = 1280 16-byte words, five per thread, all five loads in flight together (rows of 20 floats keep
+      // every word inside one frame: word w = frame w / 5, floats 4 (w % 5) ...).  One round trip to HBM per block instead
+      // of five dependent ones of scalar loads: the kernel is a 22 B/sample byte mover and was latency-bound.
+      const float4* xb4 = reinterpret_cast<const float4*>(xb);
+      const long long lo4 = lo / 4, total4 = total / 4;
+      float4 v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const long long g = lo4 + threadIdx.x + (long long)u * kIstftThreads;
+        v[u] = (g >= 0 && g < total4) ? __ldg(xb4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int w = threadIdx.x + u * kIstftThreads;
+        const int fr_i = w / 5, k = (w - fr_i * 5) * 4;
+        float* dst = xin + fr_i * 19 + k;
+        dst[0] = v[u].x; dst[1] = v[u].y;
+        if (k < 16) { dst[2] = v[u].z; dst[3] = v[u].w; }      // floats 18, 19 of a row are the pitch padding
+      }
+    } else {
     // flat, coalesced copy of 256 frames x C_ld floats, four loads in flight per thread (one at a time the block spent
     // its life waiting for ~20 dependent global loads: 0.30 ms for a kernel whose bytes take 0.05 ms)
     const int n_it = C_ld;                                   // kIstftThreads * C_ld elements / kIstftThreads threads
@@ -449,6 +497,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const float* __res
           if (k < 18) xin[fr_i * 19 + k] = v[u];
         }
       }
+    }
     }
   }
   __syncthreads();
