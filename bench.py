@@ -389,7 +389,7 @@ def main():
         peaks, peak_src = measured_peaks()
         # ---- per-launch table: which kernel dominates, and its achieved rate ----
         rows_acc = None
-        n_prof = 3
+        n_prof = int(os.environ.get("GONOVA_BENCH_NPROF", "3"))
         for r in range(n_prof + 1):
             _, rows = dec.profile_inference(mel, seed=100 + r)
             if r == 0:

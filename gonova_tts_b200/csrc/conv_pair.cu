@@ -86,6 +86,8 @@ const char* make_conv_pair_launch(ConvPairLaunch* out, int elem_bytes, const voi
   const bool cta2 = cta2_opt == 1 || (cta2_opt != 0 && (long)B * ((cta_tiles + 1) / 2) >= 2L * (max_ctas / 2));
   p.cta2 = cta2 ? 1 : 0;
   p.mma_order = getenv("GONOVA_MMA_ORDER") ? atoi(getenv("GONOVA_MMA_ORDER")) : 0;
+  p.dbg = getenv("GONOVA_PAIR_DBG") ? atoi(getenv("GONOVA_PAIR_DBG")) : 0;
+  p.slabs_first = getenv("GONOVA_PAIR_SLABS_FIRST") ? atoi(getenv("GONOVA_PAIR_SLABS_FIRST")) : 0;   // measured: inside run-to-run noise (+-3 %)
   p.tiles_m = cta2 ? (cta_tiles + 1) / 2 : cta_tiles;
   p.total_tiles = B * p.tiles_m;
   const uint32_t fmt = elem_bytes == 2 ? 1u : 2u;

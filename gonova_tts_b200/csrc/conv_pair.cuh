@@ -36,6 +36,8 @@ struct ConvPairParams {
   int w_group, w_slot_bytes;       // taps per weight barrier / ring slot
   int sa, sw, n_epi_wg, out_bufs, in_ring;
   int cta2;                        // CTA pairs: tiles_m / total_tiles then count PAIRS of CTA tiles
+  int slabs_first;                 // producer order: the next conv1's x slab before the weight groups of the conv2 in between
+  int dbg;                         // timing experiments only (GONOVA_PAIR_DBG): 1 no epilogue-1 math/stores, 2 no epilogue-2 finish
   int mma_order;                   // 0: alternate the two accumulators per MMA, 1: four k-steps per accumulator in a row
   uint32_t idesc;
   int n_in, has_raw, n_act, act_bytes, c_tab;
@@ -193,26 +195,33 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
           rw.advance(p.sw);
         }
       };
-      auto load_m1 = [&](int t) {
+      // x slab(s) of a tile and conv1's weight groups are separate rings: `slabs_first` issues the slab loads of the NEXT
+      // conv1 before the weight groups of the conv2 in between (a slab comes from HBM, ~1.5 us; issued after conv2's
+      // weights it arrived late and conv1 waited for it)
+      auto load_slab = [&](int t, int ch) {
         const int m_tile = (t % p.tiles_m) * kSub + crank, b = t / p.tiles_m;
         const int r0 = m_tile * p.Mo - p.p2 - p.p1;                 // first x row of the slab
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
-          const uint32_t dst = sA + ra.slot * p.slab_bytes;
-          if (elect_one()) {
-            if (crank == 0)
-              mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES * kSub);
-            for (int bx = 0; bx < p.a_n_boxes; ++bx) {
-              if constexpr (CTA2)
-                tma_load_3d_2sm(&maps.X, (b_a_full + 8u * ra.slot) & kPeerBitMask,
-                                dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
-              else
-                tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
-                            r0 + bx * p.a_box_rows, b);
-            }
+        mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
+        const uint32_t dst = sA + ra.slot * p.slab_bytes;
+        if (elect_one()) {
+          if (crank == 0)
+            mbar_expect_tx(b_a_full + 8u * ra.slot, (uint32_t)(p.a_n_boxes * p.a_box_rows) * KBLK_BYTES * kSub);
+          for (int bx = 0; bx < p.a_n_boxes; ++bx) {
+            if constexpr (CTA2)
+              tma_load_3d_2sm(&maps.X, (b_a_full + 8u * ra.slot) & kPeerBitMask,
+                              dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE, r0 + bx * p.a_box_rows, b);
+            else
+              tma_load_3d(&maps.X, b_a_full + 8u * ra.slot, dst + (uint32_t)(bx * p.a_box_rows) * KBLK_BYTES, ch * KBE,
+                          r0 + bx * p.a_box_rows, b);
           }
-          __syncwarp();
-          ra.advance(p.sa);
+        }
+        __syncwarp();
+        ra.advance(p.sa);
+      };
+      const bool slabs_first = p.slabs_first != 0 && p.n_chunks <= p.sa;
+      auto load_m1 = [&](int t, bool slabs_done) {
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          if (!slabs_done) load_slab(t, ch);
           load_w_groups(&maps.W1, ch);
         }
       };
@@ -223,20 +232,24 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
       // (the dense walk is kept in its plain strided form: ptxas keeps the issuer's descriptors in uniform registers
       // for it, and loses that — R2UR before every MMA, 16 % slower k = 11 pairs — with the rotating live-tile walk)
       if constexpr (RAGGED) {
-        if (tile_first < p.total_tiles) load_m1(tile_first);
-        if (tile_second < p.total_tiles) load_m1(tile_second);
+        if (tile_first < p.total_tiles) load_m1(tile_first, false);
+        if (tile_second < p.total_tiles) load_m1(tile_second, false);
         for (int t = tile_first, t1 = tile_second; t < p.total_tiles;) {
-          load_m2();
           const int t2 = t1 < p.total_tiles ? next_tile(t1) : t1;
-          if (t2 < p.total_tiles) load_m1(t2);
+          if (slabs_first && t2 < p.total_tiles)
+            for (int ch = 0; ch < p.n_chunks; ++ch) load_slab(t2, ch);
+          load_m2();
+          if (t2 < p.total_tiles) load_m1(t2, slabs_first);
           t = t1; t1 = t2;
         }
       } else {
-        if (tile0 < p.total_tiles) load_m1(tile0);
-        if (tile0 + G < p.total_tiles) load_m1(tile0 + G);
+        if (tile0 < p.total_tiles) load_m1(tile0, false);
+        if (tile0 + G < p.total_tiles) load_m1(tile0 + G, false);
         for (int t = tile0; t < p.total_tiles; t += G) {
+          if (slabs_first && t + 2 * G < p.total_tiles)
+            for (int ch = 0; ch < p.n_chunks; ++ch) load_slab(t + 2 * G, ch);
           load_m2();
-          if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G);
+          if (t + 2 * G < p.total_tiles) load_m1(t + 2 * G, slabs_first);
         }
       }
     }
@@ -447,7 +460,11 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         const float4* al = reinterpret_cast<const float4*>(tab1 + Cp + c0);
         const float4* iv = reinterpret_cast<const float4*>(tab1 + 2 * Cp + c0);
         float y[32];
-        if (p.mid_kind == ACT_SNAKE_FAST) {
+        if (p.dbg & 1) {
+          if (v[0] != 12345.f) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = v[j];
+        } else if (p.mid_kind == ACT_SNAKE_FAST) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b4 = bt[j], a4 = al[j], i4 = iv[j];
@@ -525,6 +542,16 @@ conv_pair_kernel(const ConvPairMaps* __restrict__ maps_g, const __grid_constant_
         // the tile's last half stores only its first 128 - (k-1) rows (the rest belongs to the next tile): every warp
         // stores its own 32 rows, the last warp of the last half a (32 - (k-1))-row box
         const CUtensorMap* m6 = &maps.epi[(h == p.mh - 1 && q == 3) ? 1 : 0][0];
+        if (p.dbg & 2) {
+          if (p.n_in > 0) {
+            const int in_slot = wg * p.in_ring + rin.slot;
+            mbar_wait(b_in_full + 8u * in_slot, rin.phase, 5);
+            __syncwarp();
+            if (elect_one()) mbar_arrive(b_in_empty + 8u * in_slot);
+            rin.advance(p.in_ring);
+          }
+          continue;
+        }
         epi_finish_item<E>(ectx, v, live, c0, m6, c0, m0 + h * BLOCK_M, b, rin, ob);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
