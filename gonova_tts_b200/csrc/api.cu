@@ -663,7 +663,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     size_t outs[2] = {w.H0, w.H1};
     for (int i = 0; i < 5; ++i) {
       EpiSpec es;
-      es.acts.push_back({ACT_ELU, nullptr, 0.f, P(outs[i & 1])});
+      es.acts.push_back({h->snake_kind == ACT_SNAKE_FAST ? ACT_ELU_FAST : ACT_ELU, nullptr, 0.f, P(outs[i & 1])});
       add(plan->f0_ops, h->f0c[i], in, T, es, "f0_predictor.condnet." + std::to_string(2 * i));
       in = P(outs[i & 1]);
     }
@@ -784,7 +784,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
       const char* spec0 = (const char*)P(w.spec);
       const std::string nm = "source_downs." + std::to_string(i);
       bool done = false;
-      if (h->use_tc && h->tc_version == 2) {
+      if (h->use_tc && h->tc_version == 2 && e.empty()) {       // (an EARLIER layer's error must survive: only this layer's own is cleared)
         const ConvLayer& Lf = h->sdown_flat[i];
         const void* Av = spec0 + (size_t)(kSpecFront - Lf.conv_pad) * Cs * h->eb;
         done = add(ops, Lf, Av, Ls, es, nm, (long long)Lf.conv_stride * Cs, (long long)Fp * Cs);

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cy
       t1 = clock64();
       if (lane == 0) cycles[blockIdx.x] = t1 - t0;
     } else {
+      // flags & 4: a tcgen05.commit (to a barrier nobody waits on) after every group of 8 — isolates the cost of the
+      // commit itself from the cost of the full/empty handshake
       t0 = clock64();
       for (int g = 0; g < groups; ++g) {
         if (elect_one()) {
@@ -118,8 +120,12 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int groups, long long* cy
 #pragma unroll
           for (int i = 0; i < per_group; ++i)
             umma(tmem + (uint32_t)((i % NACC) * N), ag + 2 * (i & 3), b0 + 2 * (i & 3), idesc, (g | (i >= NACC)) ? 1u : 0u);
+          if (flags & 4) umma_commit(smem_u32(&empty[g & 3]));
         }
         __syncwarp();
+        if (flags & 8) {      // ... plus a wait on an already-completed barrier phase (the cost of the wait instruction alone)
+          mbar_wait(smem_u32(&full[0]), 1u);
+        }
       }
       if (elect_one()) umma_commit(smem_u32(&bar));
       __syncwarp();
@@ -164,7 +170,7 @@ int main() {
       if (style == 0 && n_acc == 1) bench<0, 1><<<sms, 128, smem>>>(N, groups, d);
       if (style == 0 && n_acc == 2) bench<0, 2><<<sms, 128, smem>>>(N, groups, d);
       if (style == 1 && n_acc == 1) bench<1, 1><<<sms, 128, smem>>>(N, groups, d);
-      if (style == 1 && n_acc == 2) bench<1, 2><<<sms, 128, smem>>>(N, groups, d);
+      if (style == 1 && n_acc == 2) bench<1, 2><<<sms, 128, smem>>>(N, groups, d, flags);
       if (style == 2 && n_acc == 1) bench<2, 1><<<sms, 128, smem>>>(N, groups, d, flags);
       if (style == 2 && n_acc == 2) bench<2, 2><<<sms, 128, smem>>>(N, groups, d, flags);
       cudaError_t e = cudaDeviceSynchronize();
@@ -183,6 +189,9 @@ int main() {
   printf("ring protocol variants, 2 accumulators (cycles per MMA):\n%6s %22s %22s %22s %22s\n", "N", "8 per round", "8, no tcgen05.fence", "32 per round", "32, no fence");
   for (int N : {64, 128})
     printf("%6d %22.1f %22.1f %22.1f %22.1f\n", N, run(2, 2, N, 0), run(2, 2, N, 1), run(2, 2, N, 2), run(2, 2, N, 3));
+  printf("no handshake, 2 accumulators (cycles per MMA):\n%6s %22s %22s %22s\n", "N", "plain", "commit per 8", "commit + passed wait per 8");
+  for (int N : {64, 128})
+    printf("%6d %22.1f %22.1f %22.1f\n", N, run(1, 2, N, 0), run(1, 2, N, 4), run(1, 2, N, 12));
   cudaFree(d);
   return 0;
 }
