@@ -682,8 +682,10 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
     const int lm = i == 0 ? 8 : (i == 1 ? 40 : 120), la = i == 2 ? 1 : 0;
     float *F1 = Fp(w.F1[i]), *F2 = Fp(w.F2[i]), *F3 = Fp(w.F3[i]);
     void* E[4] = {P(w.E[i][0]), P(w.E[i][1]), P(w.E[i][2]), P(w.E[i][3])};
+    // j = 0 opens the stage's running sum, j = 1 adds into it; j = 2 also emits the next stage's input (an activated
+    // copy the chain kernel does not write) and stays on the pair path
     auto chain_block = [&](const ResBlockW& R, int stage, int j, bool final_to_sum) {
-      return h->use_tc && h->tc_version == 2 && final_to_sum && j == 0 && R.c1[0].k <= h->chain_max_k &&
+      return h->use_tc && h->tc_version == 2 && final_to_sum && j <= 1 && R.c1[0].k <= h->chain_max_k &&
              kStageC[stage] <= h->chain_max_c && R.c1[0].k >= 3;
     };
     auto resblock = [&](const ResBlockW& R, void* EA, const float* res_first, float* raw_stream, bool final_to_sum,
@@ -703,7 +705,7 @@ std::string build_plan(gnv_decoder* h, int B, int T, void* ws, Plan* plan, cudaS
         memset(&op.g, 0, sizeof(op.g));
         memset(&op.ep, 0, sizeof(op.ep));
         const char* ce = make_conv_chain_launch(&op.chainl, h->eb, res_first, F3, cs, B, Ls, kStageC[i], R.c1[0].k,
-                                                1.f / 3.f, snake, h->dtype == GNV_DTYPE_TF32 ? 1 : 0, lm, la,
+                                                1.f / 3.f, j > 0 ? 1 : 0, snake, h->dtype == GNV_DTYPE_TF32 ? 1 : 0, lm, la,
                                                 h->tc2opt.max_ctas);
         if (!*ce) {
           op.tc = true; op.tcv = 4;

@@ -13,7 +13,7 @@
 
 namespace gnv {
 
-enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3, ACT_SNAKE_FAST = 4, ACT_ELU_FAST = 5 };
+enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3, ACT_SNAKE_FAST = 4, ACT_ELU_FAST = 5, ACT_GELU = 6 };
 
 constexpr int kMaxAct = 3;
 
@@ -88,6 +88,7 @@ __device__ __forceinline__ float act_apply(int kind, float x, float alpha, float
     case ACT_ELU:   return x > 0.f ? x : expm1f(x);
     // exp(x) - 1 through MUFU.EX2: absolute error ~6e-8 near 0, far below the bf16 / tf32 rounding of the stored operand
     case ACT_ELU_FAST: return x > 0.f ? x : __expf(x) - 1.0f;
+    case ACT_GELU:  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));     // exact (erf) GELU, torch's default
     default:        return x;
   }
 }

@@ -59,8 +59,8 @@ const char* encode_rows(PFN_encodeTiled enc, CUtensorMap* m, const void* base, i
 }  // namespace
 
 const char* make_conv_chain_launch(ConvChainLaunch* out, int elem_bytes, const float* in, float* out_raw,
-                                   const ConvChainSpec& spec, int B, int L, int C, int k, float out_scale, int snake_kind,
-                                   int round_tf32, int len_mul, int len_add, int max_ctas) {
+                                   const ConvChainSpec& spec, int B, int L, int C, int k, float out_scale, int out_accum,
+                                   int snake_kind, int round_tf32, int len_mul, int len_add, int max_ctas) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
   const int kbe = 128 / elem_bytes;
@@ -103,6 +103,7 @@ const char* make_conv_chain_launch(ConvChainLaunch* out, int elem_bytes, const f
   p.w_slot_bytes = p.w_group * p.w_bytes;
   p.in_ring = 1;          // F2 chunk slots per warpgroup (C = 64: exactly one tile ahead)
   p.out = out_raw;
+  p.out_accum = out_accum ? 1 : 0;
   p.dbg = getenv("GONOVA_CHAIN_DBG") ? atoi(getenv("GONOVA_CHAIN_DBG")) : 0;
   const uint32_t tab_bytes = up1024((uint32_t)18 * p.c_tab * 4);
   const uint32_t bar_bytes = 1024;

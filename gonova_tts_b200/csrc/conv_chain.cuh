@@ -54,6 +54,7 @@ struct ConvChainParams {
   const int* lengths;
   int len_mul, len_add;
   float* out;                      // fp32 [B, L, C]
+  int out_accum;                   // out += ... (the stage's running sum already holds the earlier ResBlocks)
   int dbg;                         // timing experiments only (GONOVA_CHAIN_DBG): 1 no Snake math, 2 no slab stores, 4 no TMEM loads
   int c_tab;
   uint32_t off_slab, off_w, off_in, off_tab, off_bar;
@@ -479,12 +480,13 @@ conv_chain_kernel(const ConvChainMaps* __restrict__ maps_g, const __grid_constan
           const int r = h * BLOCK_M + erow;
           const int g = g0 + r;
           const int c0 = cc * kEpiCols;
+          const bool store = r >= p.halo && r < p.halo + p.Mo && g < p.L;
+          const bool live = g < vr;
+          float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)b * p.L + (store ? g : 0)) * C + c0);
           float v[32];
           tmem_ld32(lane_base + acc2_col + (uint32_t)(h * C + c0), v);
-          if (r >= p.halo && r < p.halo + p.Mo && g < p.L) {
-            const bool live = g < vr;
+          if (store) {
             const float4* bt = reinterpret_cast<const float4*>(bias_t + c0);
-            float4* dst = reinterpret_cast<float4*>(p.out + ((size_t)b * p.L + g) * C + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b4 = bt[j];
@@ -493,7 +495,13 @@ conv_chain_kernel(const ConvChainMaps* __restrict__ maps_g, const __grid_constan
               o.y = live ? (v[4 * j + 1] + b4.y) * p.out_scale : 0.f;
               o.z = live ? (v[4 * j + 2] + b4.z) * p.out_scale : 0.f;
               o.w = live ? (v[4 * j + 3] + b4.w) * p.out_scale : 0.f;
-              dst[j] = o;
+              // adding into the stage's running sum: a vector reduction at L2 (one writer per element, so the result is the
+              // same fp32 add a load-add-store would do) — no load to wait for, no registers held for it
+              if (p.out_accum)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                             : "memory");
+              else
+                dst[j] = o;
             }
           }
         }
@@ -534,8 +542,8 @@ struct ConvChainSpec {
 
 // in / out: fp32 [B, L, C].  Returns "" or the reason the block cannot run fused.
 const char* make_conv_chain_launch(ConvChainLaunch* out, int elem_bytes, const float* in, float* out_raw,
-                                   const ConvChainSpec& spec, int B, int L, int C, int k, float out_scale, int snake_kind,
-                                   int round_tf32, int len_mul, int len_add, int max_ctas);
+                                   const ConvChainSpec& spec, int B, int L, int C, int k, float out_scale, int out_accum,
+                                   int snake_kind, int round_tf32, int len_mul, int len_add, int max_ctas);
 cudaError_t launch_conv_chain(const ConvChainLaunch& L, const int* lengths, cudaStream_t st);
 cudaError_t conv_chain_init();
 

@@ -324,6 +324,9 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
         // active 22 %, ~50 instructions per element — at 0.11 ms per layer against 0.04 ms of MMA time)
 #pragma unroll
         for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.0f;
+      } else if (kind == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
       } else if (kind == ACT_ELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);

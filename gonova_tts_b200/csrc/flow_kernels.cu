@@ -1,0 +1,334 @@
+// Byte-moving and small kernels of the CFM flow decoder (oracle/flow_ref.py): time embedding, input pack,
+// LayerNorm (+ Mish, + time bias, + mask), self-attention, CFG + Euler step.  The GEMMs of the estimator (causal 3-tap
+// convs, 1x1 convs, q/k/v / output / feed-forward projections) run on conv_tc2_kernel (tcgen05 / TMEM / TMA) with fused
+// bias / residual / GELU epilogues; these kernels are what sits between them.
+// Activations are time-major [B2, T, C] (B2 = 2 B: the conditioned rows, then the zero-condition rows of classifier-free
+// guidance); rows at or beyond an utterance's length are kept at zero.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "flow_kernels.h"
+
+namespace gnv {
+
+__device__ __forceinline__ float mish_f(float x) {
+  // x * tanh(softplus(x)); softplus with torch's threshold 20
+  const float sp = x > 20.f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Time embedding for every Euler step at once: block s computes, for t = t_steps[s],
+//   emb = [sin(1000 t w_i), cos(1000 t w_i)] (320)  ->  Linear 320 -> 1024, SiLU  ->  Linear 1024 -> 1024 = temb
+//   and for each ResNet block r:  tb[s][r][:] = Linear_r(Mish(temb))   (1024 -> 256)
+// (the same for every batch row: t is shared).  fp32 weights, PyTorch [out, in] layout.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flow_time_kernel(const float* __restrict__ t_steps, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, const float* const* __restrict__ wr,
+                                                        const float* const* __restrict__ br, int n_res,
+                                                        float* __restrict__ tb) {
+  __shared__ float emb[320], h1[1024], m[1024];
+  const int s = blockIdx.x;
+  const float t = t_steps[s];
+  const int half = 160;
+  const float kf = logf(10000.f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float a = 1000.f * t * expf(-kf * (float)i);
+    emb[i] = sinf(a);
+    emb[half + i] = cosf(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 1024; o += blockDim.x) {
+    float acc = b1[o];
+    const float* w = w1 + (size_t)o * 320;
+    for (int i = 0; i < 320; ++i) acc = fmaf(w[i], emb[i], acc);
+    h1[o] = acc / (1.f + expf(-acc));                       // SiLU
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 1024; o += blockDim.x) {
+    float acc = b2[o];
+    const float* w = w2 + (size_t)o * 1024;
+    for (int i = 0; i < 1024; ++i) acc = fmaf(w[i], h1[i], acc);
+    m[o] = mish_f(acc);
+  }
+  __syncthreads();
+  for (int r = 0; r < n_res; ++r) {
+    const float* W = wr[r];
+    const float* Bv = br[r];
+    for (int o = threadIdx.x; o < 256; o += blockDim.x) {
+      float acc = Bv[o];
+      const float* w = W + (size_t)o * 1024;
+      for (int i = 0; i < 1024; ++i) acc = fmaf(w[i], m[i], acc);
+      tb[((size_t)s * n_res + r) * 256 + o] = acc;
+    }
+  }
+}
+
+cudaError_t launch_flow_time(const float* t_steps, int n_steps, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* const* wr, const float* const* br, int n_res, float* tb,
+                             cudaStream_t st) {
+  flow_time_kernel<<<n_steps, 256, 0, st>>>(t_steps, w1, b1, w2, b2, wr, br, n_res, tb);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input pack (once per decode): X0 [2B, T, 320] (E) = [x | mu | spks | cond] for the conditioned rows, [x | 0 | 0 | 0] for the
+// guidance rows; x state [B, T, 80] fp32 = z.  Inputs are upstream's layouts: z, mu, cond [B, 80, T] fp32, spks [B, 80].
+// Rows >= length are zero.
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void flow_pack_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ spks,
+                                 const float* __restrict__ cond, const int* __restrict__ lengths, int B, int T,
+                                 float* __restrict__ x_state, E* __restrict__ X0) {
+  __shared__ float tile[3][80][33];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const int len = lengths ? min(T, max(0, lengths[b])) : T;
+  for (int i = threadIdx.x; i < 3 * 80 * 32; i += blockDim.x) {
+    const int which = i / (80 * 32), c = (i / 32) % 80, tt = i % 32;
+    const int t = t0 + tt;
+    const float* src = which == 0 ? z : (which == 1 ? mu : cond);
+    tile[which][c][tt] = (t < len) ? src[((size_t)b * 80 + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 320; i += blockDim.x) {
+    const int tt = i / 320, c = i % 320;
+    const int t = t0 + tt;
+    if (t >= T) continue;
+    const bool live = t < len;
+    float v;
+    if (c < 80) v = tile[0][c][tt];
+    else if (c < 160) v = tile[1][c - 80][tt];
+    else if (c < 240) v = live ? spks[b * 80 + (c - 160)] : 0.f;
+    else v = tile[2][c - 240][tt];
+    ElemIO<E>::store(X0 + ((size_t)b * T + t) * 320 + c, v);
+    ElemIO<E>::store(X0 + ((size_t)(B + b) * T + t) * 320 + c, c < 80 ? v : 0.f);
+    if (c < 80) x_state[((size_t)b * T + t) * 80 + c] = v;
+  }
+}
+
+cudaError_t launch_flow_pack(const float* z, const float* mu, const float* spks, const float* cond, const int* lengths,
+                             int B, int T, float* x_state, void* X0, int elem_bytes, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, B);
+  if (elem_bytes == 2)
+    flow_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(z, mu, spks, cond, lengths, B, T, x_state, (__nv_bfloat16*)X0);
+  else
+    flow_pack_kernel<float><<<grid, 256, 0, st>>>(z, mu, spks, cond, lengths, B, T, x_state, (float*)X0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the 256 channels of a row (eps 1e-5), optional Mish, optional per-channel bias (the ResNet block's time
+// embedding), mask; writes the conv / GEMM operand (E) and / or fp32.  One warp per row, 8 channels per lane.
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256) flow_ln_kernel(const float* __restrict__ in, int rows, int T,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ tb, const int* __restrict__ lengths,
+                                                      int mish, int round_tf32v, E* __restrict__ out_e, float* __restrict__ out_f) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = row / T, t = row - b * T;
+  const bool live = !lengths || t < lengths[b];
+  float v[8];
+  if (live) {
+    const float4* p = reinterpret_cast<const float4*>(in + (size_t)row * 256 + lane * 8);
+    const float4 a = p[0], c = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 256.f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c0 = lane * 8 + i;
+      float y = (v[i] - mean) * rstd * gamma[c0] + beta[c0];
+      if (mish) y = mish_f(y);
+      if (tb) y += tb[c0];
+      v[i] = y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+  if (out_f) {
+    float4* o = reinterpret_cast<float4*>(out_f + (size_t)row * 256 + lane * 8);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (out_e) {
+    if constexpr (sizeof(E) == 4) {
+      if (round_tf32v) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = round_tf32(v[i]);
+      }
+    }
+    ElemIO<E>::template store_vec<8>(out_e + (size_t)row * 256 + lane * 8, v);
+  }
+}
+
+cudaError_t launch_flow_ln(const float* in, int rows, int T, const float* gamma, const float* beta, const float* tb,
+                           const int* lengths, int mish, int round_tf32v, void* out_e, int elem_bytes, float* out_f,
+                           cudaStream_t st) {
+  const int wpb = 8;
+  dim3 grid((rows + wpb - 1) / wpb);
+  if (elem_bytes == 2)
+    flow_ln_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>(in, rows, T, gamma, beta, tb, lengths, mish, 0,
+                                                             (__nv_bfloat16*)out_e, out_f);
+  else
+    flow_ln_kernel<float><<<grid, wpb * 32, 0, st>>>(in, rows, T, gamma, beta, tb, lengths, mish, round_tf32v, (float*)out_e,
+                                                     out_f);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention, 8 heads x 64, full (non-causal) over the valid keys of the utterance.
+// QKV [B2, T, 1536] (E): q | k | v, each 8 heads x 64.  O [B2, T, 512] (E).
+// First correct version on CUDA cores: one warp per query row (a lane owns two of the 64 dimensions), K / V tiles of 64 keys
+// staged in shared memory, online softmax in fp32.  (The tcgen05 version — S = Q K^T into TMEM, softmax in the epilogue
+// warps, P back through shared memory as the A operand of P V, the structure of conv_pair_kernel — is the next step.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttQ = 8;       // queries (warps) per block
+constexpr int kAttK = 64;      // keys per shared-memory tile
+
+template <typename E>
+__global__ void __launch_bounds__(kAttQ * 32) flow_attn_kernel(const E* __restrict__ qkv, int T,
+                                                               const int* __restrict__ lengths, float scale, int round_tf32v,
+                                                               E* __restrict__ out) {
+  __shared__ float2 ks[kAttK][32], vs[kAttK][32];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tq = blockIdx.x * kAttQ + warp;
+  const int len = lengths ? min(T, max(0, lengths[b])) : T;
+  const E* base = qkv + (size_t)b * T * 1536 + h * 64;
+  float2 q = make_float2(0.f, 0.f);
+  const bool qlive = tq < len;
+  if (qlive) {
+    const E* qp = base + (size_t)tq * 1536 + 2 * lane;
+    q = make_float2(ElemIO<E>::load(qp) * scale, ElemIO<E>::load(qp + 1) * scale);
+  }
+  float m = -INFINITY, l = 0.f;
+  float2 o = make_float2(0.f, 0.f);
+  for (int k0 = 0; k0 < len; k0 += kAttK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAttK * 32; i += blockDim.x) {
+      const int kk = i >> 5, d2 = i & 31;
+      const int tk = k0 + kk;
+      float2 kv = make_float2(0.f, 0.f), vv = make_float2(0.f, 0.f);
+      if (tk < len) {
+        const E* kp = base + (size_t)tk * 1536 + 512 + 2 * d2;
+        kv = make_float2(ElemIO<E>::load(kp), ElemIO<E>::load(kp + 1));
+        vv = make_float2(ElemIO<E>::load(kp + 512), ElemIO<E>::load(kp + 513));
+      }
+      ks[kk][d2] = kv;
+      vs[kk][d2] = vv;
+    }
+    __syncthreads();
+    const int nk = min(kAttK, len - k0);
+    if (qlive) {
+      for (int kk = 0; kk < nk; ++kk) {
+        const float2 kv = ks[kk][lane];
+        float s = fmaf(q.x, kv.x, q.y * kv.y);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const float mn = fmaxf(m, s);
+        const float corr = __expf(m - mn), p = __expf(s - mn);
+        const float2 vv = vs[kk][lane];
+        l = fmaf(l, corr, p);
+        o.x = fmaf(o.x, corr, p * vv.x);
+        o.y = fmaf(o.y, corr, p * vv.y);
+        m = mn;
+      }
+    }
+  }
+  if (tq < T) {
+    float ox = 0.f, oy = 0.f;
+    if (qlive && l > 0.f) { ox = o.x / l; oy = o.y / l; }
+    if constexpr (sizeof(E) == 4) {
+      if (round_tf32v) { ox = round_tf32(ox); oy = round_tf32(oy); }
+    }
+    E* op = out + ((size_t)b * T + tq) * 512 + h * 64 + 2 * lane;
+    ElemIO<E>::store(op, ox);
+    ElemIO<E>::store(op + 1, oy);
+  }
+}
+
+cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths, float scale, int round_tf32v, void* out,
+                             int elem_bytes, cudaStream_t st) {
+  dim3 grid((T + kAttQ - 1) / kAttQ, 8, B2);
+  if (elem_bytes == 2)
+    flow_attn_kernel<__nv_bfloat16><<<grid, kAttQ * 32, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, 0,
+                                                                 (__nv_bfloat16*)out);
+  else
+    flow_attn_kernel<float><<<grid, kAttQ * 32, 0, st>>>((const float*)qkv, T, lengths, scale, round_tf32v, (float*)out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Classifier-free guidance + Euler step:  v = (1 + cfg) v[b] - cfg v[B + b];  x += dt v;  the x channels of X0 (both
+// halves) are rewritten for the next estimator call.  v [2B, T, v_pitch] fp32 (80 channels used).
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void flow_euler_kernel(const float* __restrict__ v, int v_pitch, int B, int T, const int* __restrict__ lengths,
+                                  float dt, float cfg, float* __restrict__ x_state, E* __restrict__ X0, int round_tf32v) {
+  const size_t n = (size_t)B * T * 80;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 80);
+    const size_t row = i / 80;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    const bool live = !lengths || t < lengths[b];
+    const float vc = v[row * v_pitch + c], vu = v[(row + (size_t)B * T) * v_pitch + c];
+    float x = x_state[i] + dt * ((1.f + cfg) * vc - cfg * vu);
+    if (!live) x = 0.f;
+    x_state[i] = x;
+    float xe = x;
+    if constexpr (sizeof(E) == 4) { if (round_tf32v) xe = round_tf32(xe); }
+    ElemIO<E>::store(X0 + row * 320 + c, xe);
+    ElemIO<E>::store(X0 + (row + (size_t)B * T) * 320 + c, xe);
+  }
+}
+
+cudaError_t launch_flow_euler(const float* v, int v_pitch, int B, int T, const int* lengths, float dt, float cfg,
+                              float* x_state, void* X0, int elem_bytes, int round_tf32v, cudaStream_t st) {
+  const size_t n = (size_t)B * T * 80;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (elem_bytes == 2)
+    flow_euler_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(v, v_pitch, B, T, lengths, dt, cfg, x_state, (__nv_bfloat16*)X0, 0);
+  else
+    flow_euler_kernel<float><<<blocks, 256, 0, st>>>(v, v_pitch, B, T, lengths, dt, cfg, x_state, (float*)X0, round_tf32v);
+  return cudaGetLastError();
+}
+
+// x_state [B, T, 80] fp32 -> mel [B, 80, T] fp32 (upstream's layout)
+__global__ void flow_unpack_kernel(const float* __restrict__ x_state, int T, float* __restrict__ mel) {
+  __shared__ float tile[32][81];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * 80; i += blockDim.x) {
+    const int tt = i / 80, c = i % 80;
+    tile[tt][c] = (t0 + tt < T) ? x_state[((size_t)b * T + t0 + tt) * 80 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
+    const int c = i / 32, tt = i % 32;
+    if (t0 + tt < T) mel[((size_t)b * 80 + c) * T + t0 + tt] = tile[tt][c];
+  }
+}
+
+cudaError_t launch_flow_unpack(const float* x_state, int B, int T, float* mel, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, B);
+  flow_unpack_kernel<<<grid, 256, 0, st>>>(x_state, T, mel);
+  return cudaGetLastError();
+}
+
+}  // namespace gnv
