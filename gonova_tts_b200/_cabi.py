@@ -22,6 +22,7 @@ SYMBOLS = [
     "gnv_debug_tap", "gnv_debug_cluster_probe", "gnv_decode_launches", "gnv_inference_launches",
     "gnv_plan_stats", "gnv_source_stream", "gnv_inference_dseed",
     "gnv_debug_chain_trace",
+    "gnv_flow_create", "gnv_flow_destroy", "gnv_flow_workspace_bytes", "gnv_flow_decode", "gnv_flow_launches",
 ]
 
 
@@ -73,6 +74,13 @@ def load():
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_float, f32p, f32p,
                                C.c_int, vp]
     lib.gnv_debug_tap.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, vp, f32p, C.c_size_t, C.POINTER(C.c_int64), vp]
+    lib.gnv_flow_create.argtypes = [C.POINTER(GnvWeight), C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]
+    lib.gnv_flow_destroy.argtypes = [vp]
+    lib.gnv_flow_destroy.restype = None
+    lib.gnv_flow_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    lib.gnv_flow_decode.argtypes = [vp, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, vp,
+                                    C.c_size_t, vp]
+    lib.gnv_flow_launches.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_chain_trace.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_cluster_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_decode_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -81,7 +89,7 @@ def load():
     lib.gnv_source_stream.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, vp, f32p, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("gnv_destroy", "gnv_last_error", "gnv_abi_version"):
+        if name not in ("gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_flow_destroy"):
             fn.restype = C.c_int
     _LIB = lib
     return lib

@@ -25,14 +25,14 @@ __device__ __forceinline__ float mish_f(float x) {
 //   and for each ResNet block r:  tb[s][r][:] = Linear_r(Mish(temb))   (1024 -> 256)
 // (the same for every batch row: t is shared).  fp32 weights, PyTorch [out, in] layout.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) flow_time_kernel(const float* __restrict__ t_steps, const float* __restrict__ w1,
+__global__ void __launch_bounds__(256) flow_time_kernel(const FlowTimes t_steps, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
                                                         const float* __restrict__ b2, const float* const* __restrict__ wr,
                                                         const float* const* __restrict__ br, int n_res,
                                                         float* __restrict__ tb) {
   __shared__ float emb[320], h1[1024], m[1024];
   const int s = blockIdx.x;
-  const float t = t_steps[s];
+  const float t = t_steps.t[s];
   const int half = 160;
   const float kf = logf(10000.f) / (float)(half - 1);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) flow_time_kernel(const float* __restrict_
   }
 }
 
-cudaError_t launch_flow_time(const float* t_steps, int n_steps, const float* w1, const float* b1, const float* w2,
+cudaError_t launch_flow_time(const FlowTimes& t_steps, int n_steps, const float* w1, const float* b1, const float* w2,
                              const float* b2, const float* const* wr, const float* const* br, int n_res, float* tb,
                              cudaStream_t st) {
   flow_time_kernel<<<n_steps, 256, 0, st>>>(t_steps, w1, b1, w2, b2, wr, br, n_res, tb);
@@ -189,6 +189,41 @@ cudaError_t launch_flow_ln(const float* in, int rows, int T, const float* gamma,
   else
     flow_ln_kernel<float><<<grid, wpb * 32, 0, st>>>(in, rows, T, gamma, beta, tb, lengths, mish, round_tf32v, (float*)out_e,
                                                      out_f);
+  return cudaGetLastError();
+}
+
+template <typename E>
+__global__ void flow_cast_kernel(const float* __restrict__ in, int rows, int T, const int* __restrict__ lengths,
+                                 E* __restrict__ dst, int dst_pitch, int dst_off, int round_tf32v) {
+  const size_t n = (size_t)rows * 64;                      // four channels per thread
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i >> 6;
+    const int c = (int)(i & 63) * 4;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    const bool live = !lengths || t < lengths[b];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float4 a = *reinterpret_cast<const float4*>(in + row * 256 + c);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    if constexpr (sizeof(E) == 4) {
+      if (round_tf32v) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = round_tf32(v[k]);
+      }
+    }
+    ElemIO<E>::template store_vec<4>(dst + row * dst_pitch + dst_off + c, v);
+  }
+}
+
+cudaError_t launch_flow_cast(const float* in, int rows, int T, const int* lengths, void* dst, int dst_pitch, int dst_off,
+                             int elem_bytes, int round_tf32v, cudaStream_t st) {
+  const size_t n = (size_t)rows * 64;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  if (elem_bytes == 2)
+    flow_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, rows, T, lengths, (__nv_bfloat16*)dst, dst_pitch, dst_off, 0);
+  else
+    flow_cast_kernel<float><<<blocks, 256, 0, st>>>(in, rows, T, lengths, (float*)dst, dst_pitch, dst_off, round_tf32v);
   return cudaGetLastError();
 }
 

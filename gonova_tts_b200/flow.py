@@ -1,0 +1,128 @@
+"""B200Flow — the CFM flow decoder (tokens' encoder output `mu` -> mel), the step before the vocoder.
+
+Reference boundary: services/tts/core/synthesizer.py:344-350 `model.generate(...)` -> S3Gen.inference -> flow_inference ->
+`self.decoder(mu=..., mask=..., spks=..., cond=..., n_timesteps=10)` (upstream CausalConditionalCFM.forward); this class
+mirrors that call.  All arithmetic runs in libgonova_hift.so (`gnv_flow_*`, include/gonova_hift.h): the estimator's convs and
+projections on the tcgen05 implicit-GEMM kernel, LayerNorm / attention / CFG + Euler in small CUDA kernels.  No fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from . import _cabi
+
+N_TIMESTEPS = 10
+CFG_RATE = 0.7
+
+
+class B200Flow(torch.nn.Module):
+    """`forward(mu, mask, n_timesteps, temperature, spks, cond)` like upstream's CausalConditionalCFM (returns (mel, None)).
+    `state_dict` = the estimator's weights under upstream's names (`flow.decoder.estimator.*` with the prefix stripped)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dtype: str = "bf16", prefix: str = "",
+                 noise_seed: int = 0, max_frames: int = 50 * 300):
+        super().__init__()
+        if dtype not in ("bf16", "tf32"):
+            raise ValueError("dtype must be 'bf16' or 'tf32'")
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("B200Flow needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.dtype = dtype
+        self._lib = _cabi.load()
+        sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)} if prefix else dict(state_dict)
+        names = sorted(sd)
+        arr = (_cabi.GnvWeight * len(names))()
+        keep = []
+        for i, n in enumerate(names):
+            t = sd[n].detach().to("cpu", torch.float32).contiguous()
+            keep.append(t)
+            arr[i].name = n.encode()
+            arr[i].data = C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float))
+            arr[i].ndim = max(1, t.dim())
+            for d in range(t.dim()):
+                arr[i].shape[d] = t.shape[d]
+        h = C.c_void_p()
+        rc = self._lib.gnv_flow_create(arr, len(names), self.device.index, _cabi.DTYPE[dtype], 0, C.byref(h))
+        _cabi.check(rc, None, "gnv_flow_create")
+        self._h = h
+        self._ws: Optional[torch.Tensor] = None
+        self._lock = threading.Lock()
+        # upstream keeps ONE fixed noise buffer (`self.rand_noise = torch.randn([1, 80, 50 * 300])`) and slices it per call
+        g = torch.Generator().manual_seed(noise_seed)
+        self.rand_noise = torch.randn(1, 80, max_frames, generator=g).to(self.device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.gnv_flow_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def workspace_bytes(self, B: int, T: int) -> int:
+        n = C.c_size_t()
+        _cabi.check(self._lib.gnv_flow_workspace_bytes(self._h, B, T, C.byref(n)), None, "gnv_flow_workspace_bytes")
+        return n.value
+
+    def _workspace(self, B: int, T: int) -> torch.Tensor:
+        need = self.workspace_bytes(B, T) + 1024
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _f32(self, t: torch.Tensor, name: str, shape) -> torch.Tensor:
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, the flow decoder is on {self.device}")
+        t = t.to(torch.float32).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, mu: torch.Tensor, spks: torch.Tensor, cond: torch.Tensor, lengths=None,
+               n_timesteps: int = N_TIMESTEPS, cfg_rate: float = CFG_RATE) -> torch.Tensor:
+        """solve_euler from the initial noise z: all [B, 80, T] but spks [B, 80]; lengths [B] frames or None -> mel [B, 80, T]."""
+        B, Cm, T = mu.shape
+        if Cm != 80:
+            raise ValueError("mu must be [B, 80, T]")
+        z = self._f32(z, "z", (B, 80, T))
+        mu = self._f32(mu, "mu", (B, 80, T))
+        cond = self._f32(cond, "cond", (B, 80, T))
+        spks = self._f32(spks, "spks", (B, 80))
+        if lengths is not None:
+            lengths = torch.as_tensor(lengths, dtype=torch.int32, device=self.device).contiguous()
+            if lengths.shape != (B,):
+                raise ValueError("lengths must have shape [B]")
+        mel = torch.empty(B, 80, T, dtype=torch.float32, device=self.device)
+        with self._lock:
+            ws = self._workspace(B, T)
+            base = ws.data_ptr()
+            off = (-base) % 1024
+            rc = self._lib.gnv_flow_decode(self._h, C.c_void_p(z.data_ptr()), C.c_void_p(mu.data_ptr()),
+                                           C.c_void_p(spks.data_ptr()), C.c_void_p(cond.data_ptr()),
+                                           None if lengths is None else C.c_void_p(lengths.data_ptr()), B, T, int(n_timesteps),
+                                           C.c_float(cfg_rate), C.c_void_p(mel.data_ptr()), C.c_void_p(base + off),
+                                           ws.numel() - off, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            _cabi.check(rc, None, "gnv_flow_decode")
+        return mel
+
+    @torch.no_grad()
+    def forward(self, mu, mask, n_timesteps: int = N_TIMESTEPS, temperature: float = 1.0, spks=None, cond=None, **_):
+        """Upstream's call shape: `decoder(mu=h, mask=mask, spks=embedding, cond=conds, n_timesteps=10)` -> (mel, None)."""
+        B, _, T = mu.shape
+        if T > self.rand_noise.shape[2]:
+            raise ValueError("utterance longer than the noise buffer")
+        z = (self.rand_noise[:, :, :T] * temperature).expand(B, -1, -1).contiguous()
+        lengths = mask.reshape(B, T).sum(dim=1).to(torch.int32)
+        return self.decode(z, mu, spks, cond, lengths=lengths, n_timesteps=n_timesteps), None
+
+    def launches(self, n_timesteps: int = N_TIMESTEPS) -> int:
+        n = C.c_int()
+        _cabi.check(self._lib.gnv_flow_launches(self._h, n_timesteps, C.byref(n)), None, "gnv_flow_launches")
+        return n.value

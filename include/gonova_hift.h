@@ -203,6 +203,26 @@ int gnv_inference_launches(gnv_handle h, int B, int T, int* out);
  * out[0] = plans cached, out[1] = plans built so far, out[2] = device slots ever allocated, out[3] = pinned plans. */
 int gnv_plan_stats(gnv_handle h, uint64_t out[4]);
 
+/* ---- the step before the vocoder: the CFM flow decoder ---------------------------------------------
+ * replaces: CausalConditionalCFM.forward -> solve_euler -> ConditionalDecoder.forward of the engine's S3Gen flow
+ * (`flow.decoder(mu, mask, spks, cond, n_timesteps)` inside S3Gen.flow_inference), reached from
+ * services/tts/core/synthesizer.py:344-350 (model.generate -> S3Gen.inference).  Weights: the estimator's state dict under
+ * upstream's names ("time_mlp.linear_1.weight", "down_blocks.0.0.block1.block.0.weight", "mid_blocks.3.1.2.attn1.to_q.weight",
+ * "up_blocks.0.2.weight", "final_proj.bias", ...), HOST fp32 in PyTorch layout.  dtype GNV_DTYPE_BF16 or GNV_DTYPE_TF32.
+ * Same conventions as above: caller-owned device buffers, caller's stream, status + gnv_last_error(NULL). */
+typedef struct gnv_flow* gnv_flow_handle;
+int gnv_flow_create(const GnvWeight* weights, int n_weights, int device, int dtype, unsigned flags, gnv_flow_handle* out);
+void gnv_flow_destroy(gnv_flow_handle f);
+int gnv_flow_workspace_bytes(gnv_flow_handle f, int B, int T, size_t* out_bytes);
+/* z (the initial noise), mu, cond [B,80,T], spks [B,80] fp32 device tensors; lengths [B] int32 device or NULL (frames past
+ * an utterance's length are masked like upstream's `mask`); n_timesteps Euler steps on the cosine grid with classifier-free
+ * guidance `cfg_rate` (upstream: 10 and 0.7) -> mel [B,80,T] fp32. */
+int gnv_flow_decode(gnv_flow_handle f, const float* z, const float* mu, const float* spks, const float* cond,
+                    const int32_t* lengths, int B, int T, int n_timesteps, float cfg_rate, float* mel,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* kernel launches of one gnv_flow_decode with the plan last built (bench bookkeeping) */
+int gnv_flow_launches(gnv_flow_handle f, int n_timesteps, int* out);
+
 #ifdef __cplusplus
 }
 #endif
