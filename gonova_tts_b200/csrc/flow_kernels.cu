@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "flow_kernels.h"
@@ -299,9 +300,137 @@ __global__ void __launch_bounds__(kAttQ * 32) flow_attn_kernel(const E* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The bf16 path: flash-attention on the warp-level tensor-core instruction (mma.sync m16n8k16, fp32 accumulate).
+// Block = 4 warps = 64 queries of one (utterance, head); K / V tiles of 64 keys in shared memory (rows padded to 144 B: the
+// fragment loads are conflict-free); S = Q K^T stays in registers, its accumulator layout IS the A-fragment layout of P V
+// (two adjacent 8-key tiles make one 16-key k-step), V fragments come through ldmatrix.trans; online softmax in fp32 with
+// exp2.  28x faster than the CUDA-core kernel above at B2 = 16, T = 500 — and the next candidate for tcgen05 (S in TMEM).
+// ------------------------------------------------------------------------------------------------
+constexpr int kAmQ = 64, kAmK = 64, kAmPitch = 72;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128) flow_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int T,
+                                                            const int* __restrict__ lengths, float scale,
+                                                            __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[kAmK][kAmPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vs[kAmK][kAmPitch];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAmQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int len = lengths ? min(T, max(0, lengths[b])) : T;
+  const __nv_bfloat16* base = qkv + (size_t)b * T * 1536 + h * 64;
+  const int r0 = q0 + 16 * warp + g, r1 = r0 + 8;          // this thread's two query rows
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = 16 * ks + 2 * t;
+    qa[ks][0] = r0 < len ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 1536 + c) : 0u;
+    qa[ks][1] = r1 < len ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 1536 + c) : 0u;
+    qa[ks][2] = r0 < len ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * 1536 + c + 8) : 0u;
+    qa[ks][3] = r1 < len ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * 1536 + c + 8) : 0u;
+  }
+  const float sc2 = scale * 1.4426950408889634f;           // softmax in base 2
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int k0 = 0; k0 < len; k0 += kAmK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAmK * 8; i += 128) {     // 64 rows x 8 sixteen-byte words, K and V
+      const int kk = i >> 3, w = i & 7;
+      const int tk = k0 + kk;
+      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+      if (tk < len) {
+        const __nv_bfloat16* kp = base + (size_t)tk * 1536 + 512 + 8 * w;
+        kv = *reinterpret_cast<const uint4*>(kp);
+        vv = *reinterpret_cast<const uint4*>(kp + 512);
+      }
+      *reinterpret_cast<uint4*>(&Ks[kk][8 * w]) = kv;
+      *reinterpret_cast<uint4*>(&Vs[kk][8 * w]) = vv;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[8 * j + g][16 * ks + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[8 * j + g][16 * ks + 2 * t + 8]);
+        mma_bf16_16816(s[j], qa[ks], b0, b1);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + 8 * j + 2 * t;
+      if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0 * sc2), mn1 = fmaxf(m1, mx1 * sc2);      // finite: the tile holds at least one valid key
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+      s[j][0] = exp2f(fmaf(s[j][0], sc2, -mn0)); s[j][1] = exp2f(fmaf(s[j][1], sc2, -mn0));
+      s[j][2] = exp2f(fmaf(s[j][2], sc2, -mn1)); s[j][3] = exp2f(fmaf(s[j][3], sc2, -mn1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {                        // 16 keys per k-step: S tiles 2 kk and 2 kk + 1
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const uint32_t vrow = (uint32_t)__cvta_generic_to_shared(&Vs[16 * kk + (lane & 15)][0]);
+#pragma unroll
+      for (int dj = 0; dj < 8; ++dj) {
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(vrow + 16u * dj));
+        mma_bf16_16816(o[dj], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = (r0 < len && l0 > 0.f) ? 1.f / l0 : 0.f, i1 = (r1 < len && l1 > 0.f) ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int dj = 0; dj < 8; ++dj) {
+    const int c = h * 64 + 8 * dj + 2 * t;
+    if (r0 < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + r0) * 512 + c) = pack_bf16x2(o[dj][0] * i0, o[dj][1] * i0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + r1) * 512 + c) = pack_bf16x2(o[dj][2] * i1, o[dj][3] * i1);
+  }
+}
+
 cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths, float scale, int round_tf32v, void* out,
                              int elem_bytes, cudaStream_t st) {
   dim3 grid((T + kAttQ - 1) / kAttQ, 8, B2);
+  static const bool use_mma = [] { const char* v = getenv("GONOVA_FLOW_ATTN_MMA"); return !(v && atoi(v) == 0); }();
+  if (elem_bytes == 2 && use_mma) {
+    dim3 gm((T + kAmQ - 1) / kAmQ, 8, B2);
+    flow_attn_mma_kernel<<<gm, 128, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, (__nv_bfloat16*)out);
+    return cudaGetLastError();
+  }
   if (elem_bytes == 2)
     flow_attn_kernel<__nv_bfloat16><<<grid, kAttQ * 32, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, 0,
                                                                  (__nv_bfloat16*)out);
