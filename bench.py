@@ -52,6 +52,7 @@ def parse_args():
                          "--batch (strong scaling; reported as the `streams512` block; 0 = skip)")
     ap.add_argument("--no-tf32", action="store_true", help="skip the tf32 (reference-precision) block")
     ap.add_argument("--no-stock-torch", action="store_true", help="skip the stock-PyTorch-on-this-GPU block")
+    ap.add_argument("--no-flow", action="store_true", help="skip the flow-decoder (SURVEY 8f-1) block")
     return ap.parse_args()
 
 
@@ -613,6 +614,43 @@ def main():
             except Exception as e:
                 stock_block = {"error": str(e)}
 
+        # ---- the step before the vocoder: CFM flow decoder, ten Euler steps with classifier-free guidance
+        flow_block = None
+        if world == 1 and not args.no_flow:
+            try:
+                from gonova_tts_b200 import B200Flow
+
+                fg = torch.Generator().manual_seed(0)
+                # seeded random weights of the estimator's architecture (names / shapes: gonova_tts_b200/flow.py)
+                from gonova_tts_b200.flow import random_flow_state_dict
+
+                flow = B200Flow(random_flow_state_dict(0), device=dev, dtype=args.dtype if args.dtype in ("bf16", "tf32") else "bf16")
+                fB, fT = 32, T
+                fz = torch.randn(fB, 80, fT, generator=fg).to(dev)
+                fmu = (torch.randn(fB, 80, fT, generator=fg) * 0.5 - 1.0).to(dev)
+                fsp = torch.nn.functional.normalize(torch.randn(fB, 80, generator=fg), dim=1).to(dev)
+                fcond = torch.zeros(fB, 80, fT, device=dev)
+                for _ in range(2):
+                    flow.decode(fz, fmu, fsp, fcond)
+                torch.cuda.synchronize(dev)
+                fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                fe0.record(stream)
+                for _ in range(3):
+                    flow.decode(fz, fmu, fsp, fcond)
+                fe1.record(stream)
+                torch.cuda.synchronize(dev)
+                fms = fe0.elapsed_time(fe1) / 3
+                gemm_flops = 2.0 * 65.1e6 * 2 * fB * fT * 10 + 10 * 56 * 2 * fB * 8 * 4.0 * fT * fT * 64
+                flow_block = {"value": fB * fT / 50.0 / (fms / 1e3), "unit": UNIT, "ms_per_decode": fms, "batch": fB, "frames": fT,
+                              "n_timesteps": 10, "cfg_rate": 0.7, "gpu_launches": flow.launches(10),
+                              "algorithmic_tflops": gemm_flops / (fms / 1e3) / 1e12,
+                              "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
+                                      "(classifier-free guidance); estimator GEMMs on the tcgen05 conv kernel, attention on mma.sync"}
+                del flow
+                torch.cuda.empty_cache()
+            except Exception as e:
+                flow_block = {"error": str(e)}
+
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             v, sec, cores, times = cpu_decode_rate(2, T, reps=3)
@@ -640,7 +678,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "roofline_kernels": roofline_kernels, "breakdown": breakdown,
             "first_chunk": first_chunk, "cpu_baseline": cpu_baseline, "tf32": tf32_block, "stock_torch_gpu": stock_block,
-            "streams512": streams512,
+            "streams512": streams512, "flow_decoder": flow_block,
         }
     barrier()
     if world > 1:

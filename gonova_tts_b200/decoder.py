@@ -156,7 +156,7 @@ class B200HiFT(torch.nn.Module):
                 self._lib.gnv_destroy(h)
             except Exception:
                 pass
-            self._h = None
+            self.__dict__["_h"] = None          # (not nn.Module.__setattr__: it may be half torn down at interpreter exit)
 
     # nn.Module-ish no-ops so the engine's `.to(device).eval()` chains keep working
     def eval(self):

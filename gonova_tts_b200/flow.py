@@ -18,6 +18,62 @@ N_TIMESTEPS = 10
 CFG_RATE = 0.7
 
 
+def flow_layer_shapes():
+    """(name, shape) of every tensor of the estimator's state dict, upstream names (ConditionalDecoder: in_channels 320,
+    channels [256], 4 transformer blocks per level, 12 mid blocks, 8 heads x 64, feed-forward x4)."""
+    out = [("time_mlp.linear_1.weight", (1024, 320)), ("time_mlp.linear_1.bias", (1024,)),
+           ("time_mlp.linear_2.weight", (1024, 1024)), ("time_mlp.linear_2.bias", (1024,))]
+
+    def level(pre, cin):
+        out.extend([(f"{pre}.0.mlp.1.weight", (256, 1024)), (f"{pre}.0.mlp.1.bias", (256,))])
+        for blk, ci in (("block1", cin), ("block2", 256)):
+            out.extend([(f"{pre}.0.{blk}.block.0.weight", (256, ci, 3)), (f"{pre}.0.{blk}.block.0.bias", (256,)),
+                        (f"{pre}.0.{blk}.block.2.weight", (256,)), (f"{pre}.0.{blk}.block.2.bias", (256,))])
+        out.extend([(f"{pre}.0.res_conv.weight", (256, cin, 1)), (f"{pre}.0.res_conv.bias", (256,))])
+        for j in range(4):
+            tp = f"{pre}.1.{j}"
+            out.extend([(f"{tp}.norm1.weight", (256,)), (f"{tp}.norm1.bias", (256,)),
+                        (f"{tp}.attn1.to_q.weight", (512, 256)), (f"{tp}.attn1.to_k.weight", (512, 256)),
+                        (f"{tp}.attn1.to_v.weight", (512, 256)), (f"{tp}.attn1.to_out.0.weight", (256, 512)),
+                        (f"{tp}.attn1.to_out.0.bias", (256,)), (f"{tp}.norm3.weight", (256,)), (f"{tp}.norm3.bias", (256,)),
+                        (f"{tp}.ff.net.0.proj.weight", (1024, 256)), (f"{tp}.ff.net.0.proj.bias", (1024,)),
+                        (f"{tp}.ff.net.2.weight", (256, 1024)), (f"{tp}.ff.net.2.bias", (256,))])
+
+    level("down_blocks.0", 320)
+    out.extend([("down_blocks.0.2.weight", (256, 256, 3)), ("down_blocks.0.2.bias", (256,))])
+    for i in range(12):
+        level(f"mid_blocks.{i}", 256)
+    level("up_blocks.0", 512)
+    out.extend([("up_blocks.0.2.weight", (256, 256, 3)), ("up_blocks.0.2.bias", (256,)),
+                ("final_block.block.0.weight", (256, 256, 3)), ("final_block.block.0.bias", (256,)),
+                ("final_block.block.2.weight", (256,)), ("final_block.block.2.bias", (256,)),
+                ("final_proj.weight", (80, 256, 1)), ("final_proj.bias", (80,))])
+    return out
+
+
+def random_flow_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic weights of the estimator's architecture (no checkpoint exists here): U(+-1/sqrt(fan_in)) weights
+    and biases like torch's default initialisers, LayerNorm weight 1 / bias 0."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    fan = {}
+    for name, shape in flow_layer_shapes():
+        is_ln = ".block.2." in name or ".norm1." in name or ".norm3." in name
+        if is_ln:
+            sd[name] = torch.ones(shape) if name.endswith("weight") else torch.zeros(shape)
+            continue
+        if name.endswith("weight"):
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            fan[name[:-6]] = fan_in
+            bound = 1.0 / fan_in ** 0.5
+        else:
+            bound = 1.0 / fan[name[:-4]] ** 0.5
+        sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
+
+
 class B200Flow(torch.nn.Module):
     """`forward(mu, mask, n_timesteps, temperature, spks, cond)` like upstream's CausalConditionalCFM (returns (mel, None)).
     `state_dict` = the estimator's weights under upstream's names (`flow.decoder.estimator.*` with the prefix stripped)."""
@@ -62,7 +118,7 @@ class B200Flow(torch.nn.Module):
                 self._lib.gnv_flow_destroy(h)
             except Exception:
                 pass
-            self._h = None
+            self.__dict__["_h"] = None          # (not nn.Module.__setattr__: it may be half torn down at interpreter exit)
 
     def workspace_bytes(self, B: int, T: int) -> int:
         n = C.c_size_t()

@@ -49,6 +49,30 @@ def install(model, dtype: Optional[str] = None, device=None, bucket_frames: int 
     return new
 
 
+def install_flow(model, dtype: Optional[str] = None, device=None):
+    """Swap `model.s3gen.flow.decoder` (upstream CausalConditionalCFM: the estimator + the Euler loop that turn the encoder's
+    `mu` into mel frames) for a B200Flow built from its estimator's weights and its fixed noise buffer.  The
+    engine keeps calling `self.decoder(mu=..., mask=..., spks=..., cond=..., n_timesteps=10)` and gets `(mel, None)` back.
+    Same placement as install(): right after ChatterboxTTS.from_pretrained (synthesizer.py:185)."""
+    from .flow import B200Flow
+
+    dtype = dtype or os.environ.get("GONOVA_FLOW_DTYPE", "bf16")
+    old = model.s3gen.flow.decoder
+    if device is None:
+        try:
+            device = next(old.parameters()).device
+        except StopIteration:
+            device = "cuda:0"
+        if torch.device(device).type != "cuda":
+            device = "cuda:0"
+    new = B200Flow(old.estimator.state_dict(), device=device, dtype=dtype)
+    noise = getattr(old, "rand_noise", None)
+    if isinstance(noise, torch.Tensor):                 # the same noise the engine would have used: same mel
+        new.rand_noise = noise.detach().to(new.device, torch.float32).contiguous()
+    model.s3gen.flow.decoder = new
+    return new
+
+
 # -------------------------------------------------------------------------------------------------
 # intra-sentence streaming through the engine's own call
 # -------------------------------------------------------------------------------------------------

@@ -231,6 +231,23 @@ def solve_euler(est: ConditionalDecoder, z: torch.Tensor, mu: torch.Tensor, mask
     return x
 
 
+class CausalConditionalCFM(nn.Module):
+    """The module the engine keeps at `s3gen.flow.decoder`: the estimator, the fixed noise buffer, and
+    forward(mu, mask, n_timesteps, temperature, spks, cond) -> (mel, None)."""
+
+    def __init__(self, estimator: ConditionalDecoder, noise_seed: int = 0, max_frames: int = 50 * 300):
+        super().__init__()
+        self.estimator = estimator
+        g = torch.Generator().manual_seed(noise_seed)
+        self.rand_noise = torch.randn(1, MEL, max_frames, generator=g)
+
+    @torch.inference_mode()
+    def forward(self, mu, mask, n_timesteps: int = N_TIMESTEPS, temperature: float = 1.0, spks=None, cond=None):
+        z = self.rand_noise[:, :, :mu.size(2)].to(mu.device).to(mu.dtype) * temperature
+        z = z.expand(mu.shape[0], -1, -1)
+        return solve_euler(self.estimator, z, mu, mask, spks, cond, n_timesteps=n_timesteps), None
+
+
 def make_estimator(seed: int = 0) -> ConditionalDecoder:
     torch.manual_seed(seed)
     m = ConditionalDecoder().eval()

@@ -190,3 +190,35 @@ def test_parent_load_state_dict_rebuilds_the_decoder(lib, cuda_device, sd):
     assert dec.state_dict() == {} and list(dec.parameters()) == []
     with pytest.raises(RuntimeError, match="missing|weight"):
         eng.s3gen.load_state_dict({"mel2wav.conv_pre.bias": torch.zeros(512)}, strict=False)
+
+
+def test_install_flow_swaps_the_cfm_decoder(lib, cuda_device):
+    """service.install_flow on an engine-shaped object: `s3gen.flow.decoder` (estimator + noise buffer + Euler loop) becomes a
+    B200Flow that answers upstream's keyword call with the oracle module's mel (same weights, same noise buffer)."""
+    from types import SimpleNamespace
+
+    from gonova_tts_b200 import B200Flow
+    from gonova_tts_b200.service import install_flow
+    from oracle import flow_ref as FR
+
+    class FakeFlowHolder(torch.nn.Module):
+        def __init__(self, cfm):
+            super().__init__()
+            self.decoder = cfm
+
+    cfm = FR.CausalConditionalCFM(FR.make_estimator(2), noise_seed=11)
+    s3gen = torch.nn.Module()
+    s3gen.flow = FakeFlowHolder(cfm)
+    eng = SimpleNamespace(s3gen=s3gen)
+    new = install_flow(eng, dtype="tf32", device=cuda_device)
+    assert isinstance(new, B200Flow) and eng.s3gen.flow.decoder is new
+    assert "decoder" in dict(eng.s3gen.flow.named_children())
+    B, T = 1, 45
+    _, mu, mask, spks, cond = FR.synthetic_inputs(B, T, seed=4)
+    want, _ = cfm(mu=mu, mask=mask, spks=spks, cond=cond, n_timesteps=10)
+    dev = cuda_device
+    got, none = eng.s3gen.flow.decoder(mu=mu.to(dev), mask=mask.to(dev), spks=spks.to(dev), cond=cond.to(dev), n_timesteps=10)
+    assert none is None
+    err, snr = float((got.cpu() - want).abs().max()), snr_db(got.cpu().numpy(), want.numpy())
+    print(f"[parity] installed flow decoder vs oracle CFM module: max-abs {err:.3e} SNR {snr:.1f} dB")
+    assert err <= 1e-2 and snr >= 55.0
