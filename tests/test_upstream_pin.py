@@ -82,3 +82,24 @@ def test_regenerate_golden_from_upstream(T, corners):
         old["wav"] = up.decode(x=mel, s=s).numpy()
         old["f0"] = up.f0_predictor(mel).numpy().reshape(old["f0"].shape) if "f0" in old else None
     np.savez_compressed(path, **{k: v for k, v in old.items() if v is not None}, source=np.array("upstream chatterbox"))
+
+
+def test_flow_oracle_equals_upstream_estimator():
+    """oracle/flow_ref.py against upstream's ConditionalDecoder(causal) + CausalConditionalCFM.solve_euler."""
+    from chatterbox.models.s3gen.decoder import ConditionalDecoder
+    from chatterbox.models.s3gen.flow_matching import CausalConditionalCFM
+    from oracle import flow_ref as FR
+
+    sd = FR.random_state_dict(0)
+    est = ConditionalDecoder(in_channels=320, out_channels=80, causal=True, channels=[256], dropout=0.0, attention_head_dim=64,
+                             n_blocks=4, num_mid_blocks=12, num_heads=8, act_fn="gelu").eval()
+    missing, unexpected = est.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    mine = FR.load_estimator(sd)
+    z, mu, mask, spks, cond = FR.synthetic_inputs(2, 40, seed=1)
+    t = torch.full((2,), 0.37)
+    with torch.inference_mode():
+        want = est(z, mask, mu, t, spks, cond)
+        got = mine(z, mask, mu, t, spks, cond)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5, rtol=1e-4)
+    assert CausalConditionalCFM is not None
