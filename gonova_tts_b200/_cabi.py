@@ -23,6 +23,7 @@ SYMBOLS = [
     "gnv_plan_stats", "gnv_source_stream", "gnv_inference_dseed",
     "gnv_debug_chain_trace",
     "gnv_flow_create", "gnv_flow_destroy", "gnv_flow_workspace_bytes", "gnv_flow_decode", "gnv_flow_launches",
+    "gnv_flow_profile",
 ]
 
 
@@ -80,6 +81,9 @@ def load():
     lib.gnv_flow_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     lib.gnv_flow_decode.argtypes = [vp, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, vp,
                                     C.c_size_t, vp]
+    lib.gnv_flow_profile.argtypes = [vp, f32p, f32p, f32p, f32p, i32p, C.c_int, C.c_int, C.c_int, C.c_float, f32p, vp,
+                                     C.c_size_t, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_int)]
     lib.gnv_flow_launches.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_chain_trace.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_cluster_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]

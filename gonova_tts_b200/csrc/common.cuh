@@ -72,6 +72,20 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// GELU (erf form) for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 /
+// tf32 rounding of the stored operand), e^{-z^2} through MUFU.EX2 and 1 / (1 + p z) through MUFU.RCP: ~16 instructions
+// against ~85 of erff (which made the feed-forward GEMM of the flow estimator epilogue-bound).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * exp2f(-1.4426950408889634f * z * z);   // (1 - erf(z)) / 2
+  return x >= 0.f ? fmaf(-x, h, x) : x * h;
+}
+
 __device__ __forceinline__ float act_apply(int kind, float x, float alpha, float slope) {
   switch (kind) {
     case ACT_SNAKE: {

@@ -296,7 +296,12 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
       const float4* al = reinterpret_cast<const float4*>(c.tab + (1 + 2 * a) * c.c_tab + c0);
       const float4* iv = reinterpret_cast<const float4*>(c.tab + (2 + 2 * a) * c.c_tab + c0);
       float y[32];
-      if (kind == ACT_SNAKE_FAST) {
+      if (kind == ACT_NONE) {
+        // (first, and a real branch: with the plain copy as the chain's last `else` ptxas if-converted it together with
+        // the GELU arm, and the q/k/v projection of the flow estimator evaluated an erff per element it then threw away)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = v[i];
+      } else if (kind == ACT_SNAKE_FAST) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 a4 = al[j], i4 = iv[j];
@@ -310,6 +315,14 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
         const float slope = c.ep->act_slope[a];
 #pragma unroll
         for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+      } else if (kind == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = gelu_erf_fast(v[i]);
+      } else if (kind == ACT_ELU_FAST) {
+        // (the f0 predictor's five conv layers: with the out-of-line expm1f they were EPILOGUE-bound — ncu: tensor pipe
+        // active 22 %, ~50 instructions per element — at 0.11 ms per layer against 0.04 ms of MMA time)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.0f;
       } else if (kind == ACT_SNAKE) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -319,20 +332,9 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
           y[4 * j + 2] = snake_precise(v[4 * j + 2], a4.z, i4.z);
           y[4 * j + 3] = snake_precise(v[4 * j + 3], a4.w, i4.w);
         }
-      } else if (kind == ACT_ELU_FAST) {
-        // (the f0 predictor's five conv layers: with the out-of-line expm1f they were EPILOGUE-bound — ncu: tensor pipe
-        // active 22 %, ~50 instructions per element — at 0.11 ms per layer against 0.04 ms of MMA time)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = v[i] > 0.f ? v[i] : __expf(v[i]) - 1.0f;
-      } else if (kind == ACT_GELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
-      } else if (kind == ACT_ELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = v[i];
+        for (int i = 0; i < 32; ++i) y[i] = elu_precise(v[i]);
       }
       if constexpr (sizeof(E) == 2) {
 #pragma unroll

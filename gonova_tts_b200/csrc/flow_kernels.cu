@@ -16,8 +16,12 @@ namespace gnv {
 
 __device__ __forceinline__ float mish_f(float x) {
   // x * tanh(softplus(x)); softplus with torch's threshold 20
-  const float sp = x > 20.f ? x : log1pf(expf(x));
-  return x * tanhf(sp);
+  // tanh(log(1 + e^x)) = ((1 + e^x)^2 - 1) / ((1 + e^x)^2 + 1) = n / (n + 2) with n = e^x (e^x + 2): one MUFU.EX2 and one
+  // MUFU.RCP instead of expf + log1pf + tanhf (the LayerNorm + Mish kernel was bound by them); x > 20 returns x like torch
+  if (x > 20.f) return x;
+  const float e = __expf(x);
+  const float n = e * (e + 2.f);
+  return x * __fdividef(n, n + 2.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,58 +128,97 @@ cudaError_t launch_flow_pack(const float* z, const float* mu, const float* spks,
 // LayerNorm over the 256 channels of a row (eps 1e-5), optional Mish, optional per-channel bias (the ResNet block's time
 // embedding), mask; writes the conv / GEMM operand (E) and / or fp32.  One warp per row, 8 channels per lane.
 // ------------------------------------------------------------------------------------------------
+// A warp takes kLnRows rows per trip and has all their loads in flight before the first reduction (one row per warp and
+// one block per eight rows ran at 1.8 TB/s: 4000 short blocks whose load -> reduce -> reduce -> store chains did not overlap).
+constexpr int kLnRows = 4;
+
 template <typename E>
 __global__ void __launch_bounds__(256) flow_ln_kernel(const float* __restrict__ in, int rows, int T,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ tb, const int* __restrict__ lengths,
                                                       int mish, int round_tf32v, E* __restrict__ out_e, float* __restrict__ out_f) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int b = row / T, t = row - b * T;
-  const bool live = !lengths || t < lengths[b];
-  float v[8];
-  if (live) {
-    const float4* p = reinterpret_cast<const float4*>(in + (size_t)row * 256 + lane * 8);
-    const float4 a = p[0], c = p[1];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.f / 256.f);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * (1.f / 256.f) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c0 = lane * 8 + i;
-      float y = (v[i] - mean) * rstd * gamma[c0] + beta[c0];
-      if (mish) y = mish_f(y);
-      if (tb) y += tb[c0];
-      v[i] = y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float g[8], bt[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    bt[0] = b0.x; bt[1] = b0.y; bt[2] = b0.z; bt[3] = b0.w; bt[4] = b1.x; bt[5] = b1.y; bt[6] = b1.z; bt[7] = b1.w;
   }
-  if (out_f) {
-    float4* o = reinterpret_cast<float4*>(out_f + (size_t)row * 256 + lane * 8);
-    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
-  }
-  if (out_e) {
-    if constexpr (sizeof(E) == 4) {
-      if (round_tf32v) {
+  float tbv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = round_tf32(v[i]);
+  for (int i = 0; i < 8; ++i) tbv[i] = tb ? tb[lane * 8 + i] : 0.f;
+  for (int row0 = gw * kLnRows; row0 < rows; row0 += warps * kLnRows) {
+    float v[kLnRows][8];
+    bool live[kLnRows];
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      const int row = row0 + r;
+      live[r] = row < rows;
+      if (live[r] && lengths) { const int b = row / T; live[r] = row - b * T < lengths[b]; }
+      if (live[r]) {
+        const float4* p = reinterpret_cast<const float4*>(in + (size_t)row * 256 + lane * 8);
+        const float4 a = p[0], c = p[1];
+        v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w; v[r][4] = c.x; v[r][5] = c.y; v[r][6] = c.z; v[r][7] = c.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
       }
     }
-    ElemIO<E>::template store_vec<8>(out_e + (size_t)row * 256 + lane * 8, v);
+    float s[kLnRows], q[kLnRows];
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      s[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[r] += v[r][i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRows; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      s[r] *= (1.f / 256.f);
+      q[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[r][i] - s[r]; q[r] = fmaf(d, d, q[r]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kLnRows; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kLnRows; ++r) {
+      const int row = row0 + r;
+      if (row >= rows) break;
+      if (live[r]) {
+        const float rstd = rsqrtf(q[r] * (1.f / 256.f) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = (v[r][i] - s[r]) * rstd * g[i] + bt[i];
+          if (mish) y = mish_f(y);
+          v[r][i] = y + tbv[i];
+        }
+      }
+      if (out_f) {
+        float4* o = reinterpret_cast<float4*>(out_f + (size_t)row * 256 + lane * 8);
+        o[0] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        o[1] = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+      }
+      if (out_e) {
+        if constexpr (sizeof(E) == 4) {
+          if (round_tf32v) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[r][i] = round_tf32(v[r][i]);
+          }
+        }
+        ElemIO<E>::template store_vec<8>(out_e + (size_t)row * 256 + lane * 8, v[r]);
+      }
+    }
   }
 }
 
@@ -183,7 +226,8 @@ cudaError_t launch_flow_ln(const float* in, int rows, int T, const float* gamma,
                            const int* lengths, int mish, int round_tf32v, void* out_e, int elem_bytes, float* out_f,
                            cudaStream_t st) {
   const int wpb = 8;
-  dim3 grid((rows + wpb - 1) / wpb);
+  const int need = (rows + wpb * kLnRows - 1) / (wpb * kLnRows);
+  dim3 grid(need < 148 * 8 ? need : 148 * 8);
   if (elem_bytes == 2)
     flow_ln_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>(in, rows, T, gamma, beta, tb, lengths, mish, 0,
                                                              (__nv_bfloat16*)out_e, out_f);
@@ -302,12 +346,15 @@ __global__ void __launch_bounds__(kAttQ * 32) flow_attn_kernel(const E* __restri
 
 // ------------------------------------------------------------------------------------------------
 // The bf16 path: flash-attention on the warp-level tensor-core instruction (mma.sync m16n8k16, fp32 accumulate).
-// Block = 4 warps = 64 queries of one (utterance, head); K / V tiles of 64 keys in shared memory (rows padded to 144 B: the
-// fragment loads are conflict-free); S = Q K^T stays in registers, its accumulator layout IS the A-fragment layout of P V
-// (two adjacent 8-key tiles make one 16-key k-step), V fragments come through ldmatrix.trans; online softmax in fp32 with
-// exp2.  28x faster than the CUDA-core kernel above at B2 = 16, T = 500 — and the next candidate for tcgen05 (S in TMEM).
+// Block = 8 warps = 128 queries of one (utterance, head); K / V tiles of 64 keys arrive by cp.async into a two-stage ring
+// (rows padded to 144 B: every ldmatrix phase is conflict-free), so tile i + 1 loads under tile i's math.  S = Q K^T stays in
+// registers — its accumulator layout IS the A-fragment layout of P V (two adjacent 8-key tiles make one 16-key k-step); K
+// fragments come through ldmatrix.x4, V fragments through ldmatrix.x4.trans; online softmax in fp32 with ex2.approx, the
+// key mask only on an utterance's last tile.
+// History (B2 = 64, T = 500, one call): CUDA cores 5.6 ms -> 64-query blocks, synchronous tiles, 32-bit fragment loads
+// 0.200 ms -> this version (see profiles/).
 // ------------------------------------------------------------------------------------------------
-constexpr int kAmQ = 64, kAmK = 64, kAmPitch = 72;
+constexpr int kAmQ = 128, kAmK = 64, kAmPitch = 72, kAmWarps = kAmQ / 16;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -319,18 +366,46 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool live) {
+  const int n = live ? 16 : 0;                               // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
 
-__global__ void __launch_bounds__(128) flow_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int T,
-                                                            const int* __restrict__ lengths, float scale,
-                                                            __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) __nv_bfloat16 Ks[kAmK][kAmPitch];
-  __shared__ __align__(16) __nv_bfloat16 Vs[kAmK][kAmPitch];
+__global__ void __launch_bounds__(kAmWarps * 32, 2) flow_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int T,
+                                                                      const int* __restrict__ lengths, float scale,
+                                                                      __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[2][kAmK][kAmPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vs[2][kAmK][kAmPitch];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAmQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int len = lengths ? min(T, max(0, lengths[b])) : T;
   const __nv_bfloat16* base = qkv + (size_t)b * T * 1536 + h * 64;
   const int r0 = q0 + 16 * warp + g, r1 = r0 + 8;          // this thread's two query rows
+  const int n_tiles = (len + kAmK - 1) / kAmK;
+  const uint32_t ks_u = (uint32_t)__cvta_generic_to_shared(&Ks[0][0][0]);
+  const uint32_t vs_u = (uint32_t)__cvta_generic_to_shared(&Vs[0][0][0]);
+  constexpr uint32_t kStage = kAmK * kAmPitch * 2;
+  auto load_tile = [&](int tile, int stage) {
+    const int k0 = tile * kAmK;
+#pragma unroll
+    for (int i = threadIdx.x; i < kAmK * 8; i += kAmWarps * 32) {     // 64 rows x 8 sixteen-byte words, K and V
+      const int kk = i >> 3, w = i & 7;
+      const int tk = k0 + kk;
+      const bool live = tk < len;
+      const __nv_bfloat16* kp = base + (size_t)(live ? tk : 0) * 1536 + 512 + 8 * w;
+      const uint32_t off = stage * kStage + (uint32_t)(kk * kAmPitch + 8 * w) * 2u;
+      cp_async16(ks_u + off, kp, live);
+      cp_async16(vs_u + off, kp + 512, live);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_tiles > 0) load_tile(0, 0);
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -345,53 +420,55 @@ __global__ void __launch_bounds__(128) flow_attn_mma_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  for (int k0 = 0; k0 < len; k0 += kAmK) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kAmK * 8; i += 128) {     // 64 rows x 8 sixteen-byte words, K and V
-      const int kk = i >> 3, w = i & 7;
-      const int tk = k0 + kk;
-      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-      if (tk < len) {
-        const __nv_bfloat16* kp = base + (size_t)tk * 1536 + 512 + 8 * w;
-        kv = *reinterpret_cast<const uint4*>(kp);
-        vv = *reinterpret_cast<const uint4*>(kp + 512);
-      }
-      *reinterpret_cast<uint4*>(&Ks[kk][8 * w]) = kv;
-      *reinterpret_cast<uint4*>(&Vs[kk][8 * w]) = vv;
-    }
-    __syncthreads();
+  // ldmatrix lane addresses inside a stage: K (non-transposed, two k-steps per x4) and V (transposed, two d-tiles per x4)
+  const uint32_t k_lane = (uint32_t)((lane & 7) * kAmPitch + 8 * (lane >> 3)) * 2u;
+  const uint32_t v_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kAmPitch + 8 * (lane >> 4)) * 2u;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int stage = tile & 1, k0 = tile * kAmK;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                         // tile `tile` has landed; every warp is done with tile - 1
+    if (tile + 1 < n_tiles) load_tile(tile + 1, stage ^ 1);
+    const uint32_t kb = ks_u + stage * kStage + k_lane, vb = vs_u + stage * kStage + v_lane;
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {                      // k-steps 2 kp, 2 kp + 1
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(kb + (uint32_t)(8 * j * kAmPitch + 32 * kp) * 2u));
+        mma_bf16_16816(s[j], qa[2 * kp], b0, b1);
+        mma_bf16_16816(s[j], qa[2 * kp + 1], b2, b3);
+      }
+    }
+    if (k0 + kAmK > len) {                                   // the utterance's last tile: keys past its length
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[8 * j + g][16 * ks + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[8 * j + g][16 * ks + 2 * t + 8]);
-        mma_bf16_16816(s[j], qa[ks], b0, b1);
+        const int key = k0 + 8 * j + 2 * t;
+        if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
       }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int key = k0 + 8 * j + 2 * t;
-      if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-      if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0 * sc2), mn1 = fmaxf(m1, mx1 * sc2);      // finite: the tile holds at least one valid key
-    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
     m0 = mn0; m1 = mn1;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
-      s[j][0] = exp2f(fmaf(s[j][0], sc2, -mn0)); s[j][1] = exp2f(fmaf(s[j][1], sc2, -mn0));
-      s[j][2] = exp2f(fmaf(s[j][2], sc2, -mn1)); s[j][3] = exp2f(fmaf(s[j][3], sc2, -mn1));
+      s[j][0] = ex2_approx(fmaf(s[j][0], sc2, -mn0)); s[j][1] = ex2_approx(fmaf(s[j][1], sc2, -mn0));
+      s[j][2] = ex2_approx(fmaf(s[j][2], sc2, -mn1)); s[j][3] = ex2_approx(fmaf(s[j][3], sc2, -mn1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
@@ -402,12 +479,14 @@ __global__ void __launch_bounds__(128) flow_attn_mma_kernel(const __nv_bfloat16*
       pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
       pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      const uint32_t vrow = (uint32_t)__cvta_generic_to_shared(&Vs[16 * kk + (lane & 15)][0]);
 #pragma unroll
-      for (int dj = 0; dj < 8; ++dj) {
-        uint32_t b0, b1;
-        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(vrow + 16u * dj));
-        mma_bf16_16816(o[dj], pa, b0, b1);
+      for (int dp = 0; dp < 4; ++dp) {                      // d tiles 2 dp, 2 dp + 1
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vb + (uint32_t)(16 * kk * kAmPitch + 16 * dp) * 2u));
+        mma_bf16_16816(o[2 * dp], pa, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], pa, b2, b3);
       }
     }
   }
@@ -428,7 +507,7 @@ cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths,
   static const bool use_mma = [] { const char* v = getenv("GONOVA_FLOW_ATTN_MMA"); return !(v && atoi(v) == 0); }();
   if (elem_bytes == 2 && use_mma) {
     dim3 gm((T + kAmQ - 1) / kAmQ, 8, B2);
-    flow_attn_mma_kernel<<<gm, 128, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, (__nv_bfloat16*)out);
+    flow_attn_mma_kernel<<<gm, kAmWarps * 32, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, (__nv_bfloat16*)out);
     return cudaGetLastError();
   }
   if (elem_bytes == 2)

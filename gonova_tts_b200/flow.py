@@ -178,6 +178,34 @@ class B200Flow(torch.nn.Module):
         lengths = mask.reshape(B, T).sum(dim=1).to(torch.int32)
         return self.decode(z, mu, spks, cond, lengths=lengths, n_timesteps=n_timesteps), None
 
+    @torch.no_grad()
+    def profile(self, z, mu, spks, cond, n_timesteps: int = 1, cfg_rate: float = CFG_RATE):
+        """One decode with per-launch device times (gnv_flow_profile) -> [(name, kind, ms, algorithmic_flops), ...]."""
+        B, _, T = mu.shape
+        z = self._f32(z, "z", (B, 80, T)); mu = self._f32(mu, "mu", (B, 80, T))
+        cond = self._f32(cond, "cond", (B, 80, T)); spks = self._f32(spks, "spks", (B, 80))
+        mel = torch.empty(B, 80, T, dtype=torch.float32, device=self.device)
+        cap = 640 * n_timesteps
+        ms = (C.c_float * cap)(); kinds = (C.c_int32 * cap)(); flops = (C.c_double * cap)()
+        names = C.create_string_buffer(cap * _cabi.LAUNCH_NAME_LEN)
+        n = C.c_int()
+        with self._lock:
+            ws = self._workspace(B, T)
+            base = ws.data_ptr()
+            off = (-base) % 1024
+            rc = self._lib.gnv_flow_profile(self._h, C.c_void_p(z.data_ptr()), C.c_void_p(mu.data_ptr()),
+                                            C.c_void_p(spks.data_ptr()), C.c_void_p(cond.data_ptr()), None, B, T,
+                                            int(n_timesteps), C.c_float(cfg_rate), C.c_void_p(mel.data_ptr()),
+                                            C.c_void_p(base + off), ws.numel() - off,
+                                            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), cap, ms, kinds, flops,
+                                            names, C.byref(n))
+            _cabi.check(rc, None, "gnv_flow_profile")
+        rows = []
+        for i in range(n.value):
+            raw = names.raw[i * _cabi.LAUNCH_NAME_LEN:(i + 1) * _cabi.LAUNCH_NAME_LEN]
+            rows.append((raw.split(b"\0", 1)[0].decode(), int(kinds[i]), float(ms[i]), float(flops[i])))
+        return rows
+
     def launches(self, n_timesteps: int = N_TIMESTEPS) -> int:
         n = C.c_int()
         _cabi.check(self._lib.gnv_flow_launches(self._h, n_timesteps, C.byref(n)), None, "gnv_flow_launches")

@@ -220,6 +220,12 @@ int gnv_flow_workspace_bytes(gnv_flow_handle f, int B, int T, size_t* out_bytes)
 int gnv_flow_decode(gnv_flow_handle f, const float* z, const float* mu, const float* spks, const float* cond,
                     const int32_t* lengths, int B, int T, int n_timesteps, float cfg_rate, float* mel,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* Measurement hook (bench.py's flow roofline), like gnv_inference_profile: one gnv_flow_decode with a CUDA event after every
+ * launch of the Euler loop; synchronises the stream before returning.  Arrays are HOST memory with `capacity` entries. */
+int gnv_flow_profile(gnv_flow_handle f, const float* z, const float* mu, const float* spks, const float* cond,
+                     const int32_t* lengths, int B, int T, int n_timesteps, float cfg_rate, float* mel, void* workspace,
+                     size_t workspace_bytes, void* stream, int capacity, float* ms_out, int32_t* kind_out, double* flops_out,
+                     char* names_out, int* n_out);
 /* kernel launches of one gnv_flow_decode with the plan last built (bench bookkeeping) */
 int gnv_flow_launches(gnv_flow_handle f, int n_timesteps, int* out);
 
