@@ -23,7 +23,7 @@ SYMBOLS = [
     "gnv_plan_stats", "gnv_source_stream", "gnv_inference_dseed",
     "gnv_debug_chain_trace",
     "gnv_flow_create", "gnv_flow_destroy", "gnv_flow_workspace_bytes", "gnv_flow_decode", "gnv_flow_launches",
-    "gnv_flow_profile",
+    "gnv_flow_profile", "gnv_debug_flow_trace",
 ]
 
 

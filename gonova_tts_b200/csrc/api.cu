@@ -37,6 +37,7 @@
 #include "conv_tc2.cuh"
 #include "conv_pair.cuh"
 #include "conv_chain.cuh"
+#include "flow_blk.cuh"
 #include "kernels.h"
 #include "flow_kernels.h"
 
@@ -108,6 +109,7 @@ struct ConvOp {
   ConvTc2Launch tc2l;
   ConvPairLaunch pairl;
   ConvChainLaunch chainl;
+  FlowBlkLaunch blkl;    // tcv 5: flow_blk_kernel (a fused transformer-block step of the flow estimator)
   ConvGeom g;
   EpiParams ep;
   const void* A = nullptr;
@@ -202,6 +204,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 2) bytes += sizeof(ConvTc2Maps);
     if (op->tc && op->tcv == 3) bytes += sizeof(ConvPairMaps);
     if (op->tc && op->tcv == 4) bytes += sizeof(ConvChainMaps);
+    if (op->tc && op->tcv == 5) bytes += sizeof(FlowBlkMaps);
   }
   if (!bytes) return "";
   MapsSlot sl;
@@ -245,6 +248,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 2) { memcpy(sl.staging + off, &op->tc2l.maps, sizeof(ConvTc2Maps)); off += sizeof(ConvTc2Maps); }
     if (op->tc && op->tcv == 3) { memcpy(sl.staging + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
     if (op->tc && op->tcv == 4) { memcpy(sl.staging + off, &op->chainl.maps, sizeof(ConvChainMaps)); off += sizeof(ConvChainMaps); }
+    if (op->tc && op->tcv == 5) { memcpy(sl.staging + off, &op->blkl.maps, sizeof(FlowBlkMaps)); off += sizeof(FlowBlkMaps); }
   }
   cudaError_t e = cudaMemcpyAsync(sl.d, sl.staging, bytes, cudaMemcpyHostToDevice, st);
   // `st` is the handle's own upload stream (or the test hook's stream): the copy is complete before the plan is
@@ -258,6 +262,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 2) { op->tc2l.d_maps = reinterpret_cast<const ConvTc2Maps*>((char*)sl.d + off); off += sizeof(ConvTc2Maps); }
     if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)sl.d + off); off += sizeof(ConvPairMaps); }
     if (op->tc && op->tcv == 4) { op->chainl.d_maps = reinterpret_cast<const ConvChainMaps*>((char*)sl.d + off); off += sizeof(ConvChainMaps); }
+    if (op->tc && op->tcv == 5) { op->blkl.d_maps = reinterpret_cast<const FlowBlkMaps*>((char*)sl.d + off); off += sizeof(FlowBlkMaps); }
   }
   *slot = sl;
   return "";
@@ -620,6 +625,7 @@ std::string make_epi_only(const gnv_decoder* h, const ConvLayer& L, int B, int L
 
 cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   if (op.tc) {
+    if (op.tcv == 5) return launch_flow_blk(op.blkl, lengths, st);
     if (op.tcv == 4) return launch_conv_chain(op.chainl, lengths, st);
     if (op.tcv == 3) return launch_conv_pair(op.pairl, lengths, st);
     if (op.tcv == 2) return launch_conv_tc2(op.tc2l, lengths, st);

@@ -1,0 +1,149 @@
+// Host side of flow_blk_kernel (flow_blk.cuh): tensor maps, shared-memory carve-up, launch.
+#include "flow_blk.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace gnv {
+
+static constexpr size_t kFbMaxDynSmem = 227 * 1024;
+
+cudaError_t flow_blk_init() {
+  uint32_t* dptr = nullptr;
+  cudaError_t e = tc_debug_device_ptr(&dptr);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
+  if (e != cudaSuccess) return e;
+  const auto set = [](auto kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbMaxDynSmem);
+  };
+  if ((e = set(flow_blk_kernel<FB_FF>)) != cudaSuccess) return e;
+  if ((e = set(flow_blk_kernel<FB_OUT>)) != cudaSuccess) return e;
+  return set(flow_blk_kernel<FB_WIDE>);
+}
+
+int flow_blk_read_trace(unsigned long long* out, int cap) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  static unsigned long long host[kFbTraceCap];
+  if (cudaMemcpyFromSymbol(host, g_fb_trace, sizeof(host)) != cudaSuccess) return -1;
+  int n = 0;
+  for (int i = 0; i < kFbTraceCap && n < cap; ++i)
+    if (host[i]) out[n++] = host[i];
+  memset(host, 0, sizeof(host));
+  cudaMemcpyToSymbol(g_fb_trace, host, sizeof(host));
+  return n;
+}
+
+namespace {
+
+const char* encode_2d(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int elem_bytes, bool is_float, long long cols,
+                      long long rows, long long pitch_elems, int box_cols, int box_rows, CUtensorMapSwizzle sw,
+                      CUtensorMapL2promotion l2) {
+  if (!base) return "flow_blk: tensor is NULL";
+  if (((uintptr_t)base & 15) || (pitch_elems * elem_bytes) % 16) return "flow_blk: tensor is not 16-byte aligned";
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? "" : "flow_blk: cuTensorMapEncodeTiled failed";
+}
+
+}  // namespace
+
+const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, int K, const void* w1, const float* b1,
+                                 const void* w2, const float* b2, float* r, const float* gamma, const float* beta,
+                                 int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
+  if (mode != FB_FF && mode != FB_OUT && mode != FB_WIDE) return "flow_blk: bad mode";
+  if (M <= 0 || T <= 0 || K <= 0 || K % 64) return "flow_blk: bad shape";
+  if (mode == FB_FF && (K != 256 || N != 256)) return "flow_blk: the feed-forward is 256 -> 1024 -> 256";
+  if (mode == FB_OUT && N != 256) return "flow_blk: the output projection has 256 columns";
+  if (mode == FB_WIDE && (N % 256 || N > 1536 || K != 256)) return "flow_blk: wide GEMM: K = 256, N a multiple of 256 up to 1536";
+  memset(&out->maps, 0, sizeof(out->maps));
+  memset(&out->p, 0, sizeof(out->p));
+  out->d_maps = nullptr;
+  out->mode = mode;
+  FlowBlkParams& p = out->p;
+  p.M = M; p.T = T; p.tiles = (M + 255) / 256;
+  p.kb_a = K / 64;
+  p.n_tiles = mode == FB_WIDE ? N / 256 : 1;
+  p.n_bias1 = mode == FB_FF ? 1024 : (mode == FB_WIDE && b1 ? N : 0);
+  p.ln = ln;
+  {
+    static const int dbg = [] { const char* v = getenv("GONOVA_FB_DBG"); return v ? atoi(v) : 0; }();
+    static const int dbg_mode = [] { const char* v = getenv("GONOVA_FB_TRACE_MODE"); return v ? atoi(v) : 0; }();
+    p.dbg = (dbg & 8) ? ((mode == dbg_mode ? 8 : 0) | (dbg & ~8)) : dbg;
+  }
+  p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta;
+  p.r = r; p.n_out = (__nv_bfloat16*)n_out; p.n_pitch = n_pitch;
+  if (mode != FB_WIDE && (!r || !n_out || ((uintptr_t)r & 31) || ((uintptr_t)n_out & 31) || n_pitch % 16))
+    return "flow_blk: residual / output rows must be 32-byte aligned";
+  // WIDE: n tiles per work unit — the unit's A tile stays resident; fewer per unit when there are not enough m tiles to
+  // give every CTA pair work
+  p.npu = 1;
+  if (mode == FB_WIDE) {
+    const int pairs_avail = std::max(1, max_ctas / 2);
+    for (int cand : {6, 3, 2, 1})
+      if (p.n_tiles % cand == 0 && (long)p.tiles * (p.n_tiles / cand) >= pairs_avail) { p.npu = cand; break; }
+  }
+  const uint32_t fmt = 1u;   // bf16
+  const auto idesc = [&](uint32_t n) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24); };
+  p.idesc128 = idesc(128);
+  p.idesc256 = idesc(256);
+  p.sw = 4;
+  p.off_x = 0;
+  p.off_h = 4 * kFbSlot;
+  p.off_w = p.off_h + 4 * kFbSlot;
+  p.off_sc = p.off_w + (uint32_t)p.sw * kFbSlot;
+  p.off_tab = p.off_sc + 4 * 4096;
+  p.off_bar = p.off_tab + (((uint32_t)kFbTab * 4u + 1023u) & ~1023u);
+  out->smem_bytes = (size_t)p.off_bar + 1024 + 1024;
+  if (out->smem_bytes > kFbMaxDynSmem) return "flow_blk: shared memory budget exceeded";
+
+  const CUtensorMapL2promotion l2a = CU_TENSOR_MAP_L2_PROMOTION_L2_128B, l2w = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  const char* e = encode_2d(enc, &out->maps.A, a, 2, false, K, M, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, l2a);
+  if (*e) return e;
+  if (mode == FB_FF) {
+    e = encode_2d(enc, &out->maps.W1, w1, 2, false, 256, 1024, 256, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B, l2w);
+    if (*e) return e;
+    e = encode_2d(enc, &out->maps.W2, w2, 2, false, 1024, 256, 1024, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, l2w);
+    if (*e) return e;
+  } else if (mode == FB_OUT) {
+    e = encode_2d(enc, &out->maps.W2, w2, 2, false, K, 256, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, l2w);
+    if (*e) return e;
+    out->maps.W1 = out->maps.W2;
+  } else {
+    e = encode_2d(enc, &out->maps.W1, w1, 2, false, K, N, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, l2w);
+    if (*e) return e;
+    out->maps.W2 = out->maps.W1;
+  }
+  if (mode == FB_WIDE) {
+    e = encode_2d(enc, &out->maps.Nout, n_out, 2, false, N, M, n_pitch, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, l2a);
+    if (*e) return e;
+  } else {
+    out->maps.Nout = out->maps.A;
+  }
+  const int items = p.tiles * (p.n_tiles / p.npu);
+  const int pairs = std::max(1, std::min(items, std::max(1, max_ctas / 2)));
+  out->grid = 2 * pairs;
+  return "";
+}
+
+cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st) {
+  if (!L.d_maps) return cudaErrorInvalidValue;
+  FlowBlkParams p = L.p;
+  p.lengths = lengths;
+  const FlowBlkMaps* dm = L.d_maps;
+  switch (L.mode) {
+    case FB_FF:  return launch_persistent(flow_blk_kernel<FB_FF>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
+    case FB_OUT: return launch_persistent(flow_blk_kernel<FB_OUT>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
+    default:     return launch_persistent(flow_blk_kernel<FB_WIDE>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
+  }
+}
+
+}  // namespace gnv

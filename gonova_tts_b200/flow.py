@@ -185,7 +185,7 @@ class B200Flow(torch.nn.Module):
         z = self._f32(z, "z", (B, 80, T)); mu = self._f32(mu, "mu", (B, 80, T))
         cond = self._f32(cond, "cond", (B, 80, T)); spks = self._f32(spks, "spks", (B, 80))
         mel = torch.empty(B, 80, T, dtype=torch.float32, device=self.device)
-        cap = 640 * n_timesteps
+        cap = 4096 * n_timesteps
         ms = (C.c_float * cap)(); kinds = (C.c_int32 * cap)(); flops = (C.c_double * cap)()
         names = C.create_string_buffer(cap * _cabi.LAUNCH_NAME_LEN)
         n = C.c_int()

@@ -226,6 +226,9 @@ int gnv_flow_profile(gnv_flow_handle f, const float* z, const float* mu, const f
                      const int32_t* lengths, int B, int T, int n_timesteps, float cfg_rate, float* mel, void* workspace,
                      size_t workspace_bytes, void* stream, int capacity, float* ms_out, int32_t* kind_out, double* flops_out,
                      char* names_out, int* n_out);
+/* Tuning hook: CTA 0's event timeline of the last flow_blk_kernel launch traced (GONOVA_FB_DBG=8, GONOVA_FB_TRACE_MODE =
+ * 0 feed-forward / 1 output projection / 2 q,k,v); words (role + 1) << 56 | a << 48 | b << 40 | event << 32 | clock32. */
+int gnv_debug_flow_trace(unsigned long long* out, int cap, int* n_out);
 /* kernel launches of one gnv_flow_decode with the plan last built (bench bookkeeping) */
 int gnv_flow_launches(gnv_flow_handle f, int n_timesteps, int* out);
 
