@@ -38,6 +38,7 @@
 #include "conv_pair.cuh"
 #include "conv_chain.cuh"
 #include "flow_blk.cuh"
+#include "flow_attn.cuh"
 #include "kernels.h"
 #include "flow_kernels.h"
 
@@ -110,6 +111,7 @@ struct ConvOp {
   ConvPairLaunch pairl;
   ConvChainLaunch chainl;
   FlowBlkLaunch blkl;    // tcv 5: flow_blk_kernel (a fused transformer-block step of the flow estimator)
+  FlowAttnLaunch attnl;  // tcv 6: flow_attn_tc_kernel (self-attention of the flow estimator)
   ConvGeom g;
   EpiParams ep;
   const void* A = nullptr;
@@ -205,6 +207,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 3) bytes += sizeof(ConvPairMaps);
     if (op->tc && op->tcv == 4) bytes += sizeof(ConvChainMaps);
     if (op->tc && op->tcv == 5) bytes += sizeof(FlowBlkMaps);
+    if (op->tc && op->tcv == 6) bytes += sizeof(FlowAttnMaps);
   }
   if (!bytes) return "";
   MapsSlot sl;
@@ -249,6 +252,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 3) { memcpy(sl.staging + off, &op->pairl.maps, sizeof(ConvPairMaps)); off += sizeof(ConvPairMaps); }
     if (op->tc && op->tcv == 4) { memcpy(sl.staging + off, &op->chainl.maps, sizeof(ConvChainMaps)); off += sizeof(ConvChainMaps); }
     if (op->tc && op->tcv == 5) { memcpy(sl.staging + off, &op->blkl.maps, sizeof(FlowBlkMaps)); off += sizeof(FlowBlkMaps); }
+    if (op->tc && op->tcv == 6) { memcpy(sl.staging + off, &op->attnl.maps, sizeof(FlowAttnMaps)); off += sizeof(FlowAttnMaps); }
   }
   cudaError_t e = cudaMemcpyAsync(sl.d, sl.staging, bytes, cudaMemcpyHostToDevice, st);
   // `st` is the handle's own upload stream (or the test hook's stream): the copy is complete before the plan is
@@ -263,6 +267,7 @@ std::string upload_maps(std::vector<ConvOp*>& ops, std::vector<MapsSlot>& free_s
     if (op->tc && op->tcv == 3) { op->pairl.d_maps = reinterpret_cast<const ConvPairMaps*>((char*)sl.d + off); off += sizeof(ConvPairMaps); }
     if (op->tc && op->tcv == 4) { op->chainl.d_maps = reinterpret_cast<const ConvChainMaps*>((char*)sl.d + off); off += sizeof(ConvChainMaps); }
     if (op->tc && op->tcv == 5) { op->blkl.d_maps = reinterpret_cast<const FlowBlkMaps*>((char*)sl.d + off); off += sizeof(FlowBlkMaps); }
+    if (op->tc && op->tcv == 6) { op->attnl.d_maps = reinterpret_cast<const FlowAttnMaps*>((char*)sl.d + off); off += sizeof(FlowAttnMaps); }
   }
   *slot = sl;
   return "";
@@ -625,6 +630,7 @@ std::string make_epi_only(const gnv_decoder* h, const ConvLayer& L, int B, int L
 
 cudaError_t run_op(const ConvOp& op, const int* lengths, cudaStream_t st) {
   if (op.tc) {
+    if (op.tcv == 6) return launch_flow_attn_tc(op.attnl, lengths, st);
     if (op.tcv == 5) return launch_flow_blk(op.blkl, lengths, st);
     if (op.tcv == 4) return launch_conv_chain(op.chainl, lengths, st);
     if (op.tcv == 3) return launch_conv_pair(op.pairl, lengths, st);

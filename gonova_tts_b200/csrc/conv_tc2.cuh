@@ -162,8 +162,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive on a barrier of the pair's other CTA.  Default (.release.cta) semantics: the `.release.cluster` form compiles to
+// MEMBAR.ALL.CTA + ERRBAR and cost 2.6 k cycles per use on the timeline of flow_blk_kernel.  What these arrivals publish
+// is either a drained TMEM buffer (ordered by tcgen05.fence::before_thread_sync) or shared memory of the arriving CTA
+// itself that its own tensor core will read (ordered by fence.proxy.async) — nothing the other CTA's threads load.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1,
                                                 int c2) {

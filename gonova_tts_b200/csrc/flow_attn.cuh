@@ -1,0 +1,322 @@
+// Self-attention of the CFM flow estimator (8 heads x 64, full attention over the valid keys of an utterance) on tcgen05.
+//
+// Work item = (utterance b, head h, 256 queries): two 128-query tiles side by side, one per softmax warpgroup, sharing
+// every K / V tile.  Per 128-key tile j and warpgroup g:
+//     S_g = Q_g K_j^T            tcgen05.mma, M = 128, N = 128, K = 64: S in TMEM (128 columns)
+//     softmax warpgroup g        thread = query row: row max and row sum are thread-local (no shuffles); the running
+//                                output O_g (TMEM, 64 columns) is rescaled in place; P = 2^(s - m) goes to shared memory as
+//                                bf16 in the K-major SWIZZLE_128B operand layout
+//     O_g += P_g V_j             tcgen05.mma, M = 128, N = 64, K = 128
+// While warpgroup 0 runs its softmax, the tensor core works for warpgroup 1 and vice versa (the two never share a
+// barrier).  K comes straight from the fused q/k/v buffer [2B, T, 1536]; V is read from Vt [2B * 8, 64, Tp] — the q/k/v
+// GEMM's epilogue writes its V columns TRANSPOSED (keys contiguous), which makes V^T a plain K-major B operand.
+// Bound: one MUFU.EX2 per score (16 per clock per SM).  Replaces the mma.sync kernel (flow_kernels.cu) on the bf16 path.
+// Warp roles (352 threads): 0..3 softmax warpgroup 0, 4..7 warpgroup 1, 8 TMEM + barriers, 9 TMA producer, 10 MMA issuer.
+#pragma once
+#include "conv_tc2.cuh"
+
+namespace gnv {
+
+constexpr int kFaStages = 3;             // K / V ring depth (32 KB per stage)
+constexpr int kFaThreads = 352;
+
+struct FlowAttnParams {
+  int B2, T, nqp, items;                 // utterances, frames, 256-query groups per (b, h), work items
+  const int* lengths;
+  __nv_bfloat16* o;                      // [B2, T, 512] (plain stores for the rows of an empty utterance)
+  float sc2;                             // softmax scale * log2(e)
+  uint32_t idesc_s, idesc_pv;
+  uint32_t off_q, off_kv, off_p, off_bar;
+};
+
+struct FlowAttnMaps { CUtensorMap QK, Vt, O; };
+
+#ifdef __CUDACC__
+namespace tc2 {
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+}  // namespace tc2
+
+template <int kVariant>
+__global__ void __launch_bounds__(kFaThreads, 1)
+flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_constant__ FlowAttnParams p) {
+  using namespace tc2;
+  typedef __nv_bfloat16 E;
+  const FlowAttnMaps& maps = *maps_g;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base + p.off_q, sKV = smem_base + p.off_kv, sP = smem_base + p.off_p;
+  const uint32_t bar0 = smem_base + p.off_bar;
+  const uint32_t b_q_full = bar0, b_q_empty = bar0 + 16u;     // [2] each: the Q tiles of the next item load under this one
+  const uint32_t b_kv_full = bar0 + 32u, b_kv_empty = b_kv_full + 8u * kFaStages;
+  const uint32_t b_s_full = b_kv_empty + 8u * kFaStages;       // [2]
+  const uint32_t b_p_ready = b_s_full + 16u, b_pv_done = b_p_ready + 16u;
+  const uint32_t tmem_slot = b_pv_done + 16u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 9 && lane == 0) {
+    prefetch_tmap(&maps.QK);
+    prefetch_tmap(&maps.Vt);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) { mbar_init(b_q_full + 8u * s, 1); mbar_init(b_q_empty + 8u * s, 1); }
+      for (int s = 0; s < kFaStages; ++s) { mbar_init(b_kv_full + 8u * s, 1); mbar_init(b_kv_empty + 8u * s, 1); }
+      for (int g = 0; g < 2; ++g) {
+        mbar_init(b_s_full + 8u * g, 1);
+        mbar_init(b_p_ready + 8u * g, 4);
+        mbar_init(b_pv_done + 8u * g, 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait_then_release();
+
+  // item -> (b, h, qp); n_kv = 128-key tiles of the utterance
+  auto decode = [&](int item, int& b, int& h, int& qp, int& len) {
+    qp = item % p.nqp;
+    const int bh = item / p.nqp;
+    h = bh & 7; b = bh >> 3;
+    len = p.lengths ? min(p.T, max(0, p.lengths[b])) : p.T;
+  };
+
+  if (warp == 9) {
+    // ===== TMA producer =====
+    Ring rkv;
+    uint32_t nq = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, h, qp, len;
+      decode(item, b, h, qp, len);
+      const int n_kv = (len + 127) >> 7;
+      if (n_kv == 0) continue;
+      const uint32_t qb = nq & 1u;
+      mbar_wait(b_q_empty + 8u * qb, ((nq >> 1) & 1u) ^ 1u, 1);
+      if (elect_one()) {
+        mbar_expect_tx(b_q_full + 8u * qb, 2u * 16384u);
+        tma_load_3d(&maps.QK, b_q_full + 8u * qb, sQ + qb * 32768u, h * 64, qp * 256, b);
+        tma_load_3d(&maps.QK, b_q_full + 8u * qb, sQ + qb * 32768u + 16384u, h * 64, qp * 256 + 128, b);
+      }
+      __syncwarp();
+      ++nq;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(b_kv_empty + 8u * rkv.slot, rkv.phase ^ 1u, 1);
+        if (elect_one()) {
+          const uint32_t dst = sKV + rkv.slot * 32768u;
+          mbar_expect_tx(b_kv_full + 8u * rkv.slot, 32768u);
+          tma_load_3d(&maps.QK, b_kv_full + 8u * rkv.slot, dst, 512 + h * 64, j * 128, b);
+          tma_load_3d(&maps.Vt, b_kv_full + 8u * rkv.slot, dst + 16384u, j * 128, 0, b * 8 + h);
+          tma_load_3d(&maps.Vt, b_kv_full + 8u * rkv.slot, dst + 16384u + 8192u, j * 128 + 64, 0, b * 8 + h);
+        }
+        __syncwarp();
+        rkv.advance(kFaStages);
+      }
+    }
+  } else if (warp == 10) {
+    // ===== MMA issuer =====
+    const uint64_t q_desc0 = umma_desc_sw128(sQ), kv_desc0 = umma_desc_sw128(sKV), p_desc0 = umma_desc_sw128(sP);
+    Ring rkv;
+    uint32_t np = 0;                                     // p_ready completions consumed so far (same for both warpgroups)
+    uint32_t nq = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, h, qp, len;
+      decode(item, b, h, qp, len);
+      const int n_kv = (len + 127) >> 7;
+      if (n_kv == 0) continue;
+      const uint32_t qb = nq & 1u;
+      auto issue_s = [&](int g, int slot) {
+        if (elect_one()) {
+          const uint64_t ad = q_desc0 + (uint64_t)(qb * 2u + (uint32_t)g) * (16384u >> 4), bd = kv_desc0 + (uint64_t)slot * (32768u >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma<E>(tmem_base + (uint32_t)g * 192u, ad + 2u * kk, bd + 2u * kk, p.idesc_s, kk ? 1u : 0u);
+          umma_commit(b_s_full + 8u * g);
+        }
+        __syncwarp();
+      };
+      mbar_wait(b_q_full + 8u * qb, (nq >> 1) & 1u, 2);
+      ++nq;
+      mbar_wait(b_kv_full + 8u * rkv.slot, rkv.phase, 2);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_s(0, rkv.slot);
+      issue_s(1, rkv.slot);
+      for (int j = 0; j < n_kv; ++j) {
+        const int slot = rkv.slot;
+        Ring nxt = rkv;
+        nxt.advance(kFaStages);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(b_p_ready + 8u * g, np & 1u, 2);     // P_g(j) is in shared memory, O_g rescaled, S_g read
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t ad = p_desc0 + (uint64_t)(g * 2 + kb) * (16384u >> 4);
+              const uint64_t bd = kv_desc0 + (uint64_t)slot * (32768u >> 4) + (uint64_t)((16384u + kb * 8192u) >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma<E>(tmem_base + (uint32_t)g * 192u + 128u, ad + 2u * kk, bd + 2u * kk, p.idesc_pv, (j | kb | kk) ? 1u : 0u);
+            }
+            umma_commit(b_pv_done + 8u * g);
+          }
+          __syncwarp();
+          if (j + 1 < n_kv) {
+            if (g == 0) {
+              mbar_wait(b_kv_full + 8u * nxt.slot, nxt.phase, 2);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            issue_s(g, nxt.slot);
+          }
+        }
+        if (elect_one()) {
+          umma_commit(b_kv_empty + 8u * slot);
+          if (j + 1 == n_kv) umma_commit(b_q_empty + 8u * qb);
+        }
+        __syncwarp();
+        rkv = nxt;
+        ++np;
+      }
+    }
+  } else if (warp < 8) {
+    // ===== softmax warpgroups =====
+    const int g = warp >> 2, q = warp & 3;
+    const int erow = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 192u;
+    const uint32_t sPg = sP + (uint32_t)g * 32768u;
+    const uint32_t p_row = sPg + (uint32_t)erow * 128u;
+    uint32_t ns = 0;                                     // S tiles consumed so far by this warpgroup
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int b, h, qp, len;
+      decode(item, b, h, qp, len);
+      const int n_kv = (len + 127) >> 7;
+      const int t_row = qp * 256 + g * 128 + erow;       // this thread's query
+      if (n_kv == 0) {
+        // an empty utterance: its rows of O are zero
+        if (t_row < p.T) {
+          uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.T + t_row) * 512 + h * 64);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        continue;
+      }
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++ns) {
+        mbar_wait(b_s_full + 8u * g, ns & 1u, 4);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int kmax = len - j * 128;                  // keys of this tile that exist (>= 1)
+        // pass A: row maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(lane_base + (uint32_t)(c * 32), v);
+          if (kmax < 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) v[i] = -INFINITY;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+        }
+        const float m_new = fmaxf(m, mx * p.sc2);
+        const float corr = ex2_fast(m - m_new);          // 0 on the first tile (m = -inf)
+        if (j > 0) {
+          // the previous tile's P V has landed in O: rescale it to the new maximum
+          mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= corr;
+            tmem_st32(lane_base + 128u + (uint32_t)(c * 32), v);
+          }
+          l *= corr;
+        }
+        // pass B: P = 2^(s sc2 - m_new) -> bf16 -> shared memory (K block = 64 keys; 16-byte chunks XOR row & 7)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(lane_base + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], p.sc2, -m_new));
+          if (kmax < 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) l += v[i];
+          const uint32_t rowa = p_row + (uint32_t)(c >> 1) * 16384u;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            sts128u(rowa + ((((uint32_t)((c & 1) * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
+                    ElemIO<E>::pack2(v[8 * k4 + 2], v[8 * k4 + 3]), ElemIO<E>::pack2(v[8 * k4 + 4], v[8 * k4 + 5]),
+                    ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
+        }
+        m = m_new;
+        if (j > 0) tmem_wait_st();
+        fence_async_smem();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (elect_one()) mbar_arrive(b_p_ready + 8u * g);
+      }
+      // ---- output: O / l -> bf16 -> this warp's 32 x 64 box (staged in the warpgroup's P buffer) -> TMA store ----
+      mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const float inv = (t_row < len && l > 0.f) ? 1.f / l : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= inv;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          sts128u(p_row + ((((uint32_t)(c * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
+                  ElemIO<E>::pack2(v[8 * k4 + 2], v[8 * k4 + 3]), ElemIO<E>::pack2(v[8 * k4 + 4], v[8 * k4 + 5]),
+                  ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
+      }
+      fence_async_smem();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_3d(&maps.O, sPg + (uint32_t)q * 4096u, h * 64, qp * 256 + g * 128 + q * 32, b);
+        bulk_commit();
+        bulk_wait_read<0>();                              // the box has left shared memory before the next item's P lands there
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+#endif  // __CUDACC__
+
+struct FlowAttnLaunch {
+  FlowAttnMaps maps;
+  const FlowAttnMaps* d_maps = nullptr;
+  FlowAttnParams p;
+  int grid = 0;
+  size_t smem_bytes = 0;
+};
+
+// qkv: [B2, T, 1536] bf16 (q | k | unused); vt: [B2 * 8, 64, Tp] bf16 (V transposed, Tp = T rounded up to 8);
+// out: [B2, T, 512] bf16
+const char* make_flow_attn_launch(FlowAttnLaunch* out, const void* qkv, const void* vt, int Tp, void* o, int B2, int T,
+                                  float scale, int max_ctas);
+cudaError_t launch_flow_attn_tc(const FlowAttnLaunch& L, const int* lengths, cudaStream_t st);
+cudaError_t flow_attn_init();
+
+}  // namespace gnv

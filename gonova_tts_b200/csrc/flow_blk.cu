@@ -56,7 +56,8 @@ const char* encode_2d(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int
 
 const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, int K, const void* w1, const float* b1,
                                  const void* w2, const float* b2, float* r, const float* gamma, const float* beta,
-                                 int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas) {
+                                 int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas, void* vt, int vt_col0,
+                                 int vt_tp) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
   if (mode != FB_FF && mode != FB_OUT && mode != FB_WIDE) return "flow_blk: bad mode";
@@ -81,6 +82,8 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
   }
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta;
   p.r = r; p.n_out = (__nv_bfloat16*)n_out; p.n_pitch = n_pitch;
+  p.vt = mode == FB_WIDE ? (__nv_bfloat16*)vt : nullptr; p.vt_col0 = vt_col0; p.vt_tp = vt_tp;
+  if (p.vt && (vt_col0 % 256 || vt_tp < T)) return "flow_blk: bad transposed-V geometry";
   if (mode != FB_WIDE && (!r || !n_out || ((uintptr_t)r & 31) || ((uintptr_t)n_out & 31) || n_pitch % 16))
     return "flow_blk: residual / output rows must be 32-byte aligned";
   // WIDE: n tiles per work unit — the unit's A tile stays resident; fewer per unit when there are not enough m tiles to

@@ -42,6 +42,10 @@ struct FlowBlkParams {
   float* r;                 // FF / OUT: the residual stream [M, 256] fp32, updated in place
   __nv_bfloat16* n_out;     // FF / OUT: bf16 output rows, pitch n_pitch elements
   int n_pitch;
+  // WIDE: columns at or beyond vt_col0 (the V third of q | k | v) are written TRANSPOSED into vt [M / T * 8, 64, vt_tp]
+  // (keys contiguous: the K-major B operand of P V in flow_attn_tc_kernel) instead of the row-major output
+  __nv_bfloat16* vt;
+  int vt_col0, vt_tp;
   uint32_t idesc128, idesc256;
   uint32_t off_x, off_h, off_w, off_sc, off_tab, off_bar;   // off_sc: the row warps' scratch (4 x 4 KB)
 };
@@ -509,6 +513,17 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
+            if (p.vt && n * 256 + col >= p.vt_col0) {
+              // a warp = 32 consecutive rows = (mostly) 32 consecutive keys of one utterance: one 64-byte run per channel
+              if (row < p.M) {
+                const int b = row / p.T, t = row - b * p.T;
+                const int c = n * 256 + col - p.vt_col0;              // channel of v[0] inside the V third: head c / 64
+                __nv_bfloat16* dst = p.vt + ((size_t)(b * 8 + (c >> 6)) * 64 + (c & 63)) * p.vt_tp + t;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(size_t)j * p.vt_tp] = __float2bfloat16_rn(v[j]);
+              }
+              continue;
+            }
             const uint32_t sbuf = sH + (uint32_t)warp * 4096u + (uint32_t)i2 * 2048u;
             if (elect_one()) bulk_wait_read<1>();
             __syncwarp();
@@ -741,7 +756,8 @@ struct FlowBlkLaunch {
 // (FF / OUT: 256 columns at n_out; WIDE: N columns).  Returns "" or an error text.
 const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, int K, const void* w1, const float* b1,
                                  const void* w2, const float* b2, float* r, const float* gamma, const float* beta,
-                                 int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas);
+                                 int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas,
+                                 void* vt = nullptr, int vt_col0 = 0, int vt_tp = 0);
 cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st);
 cudaError_t flow_blk_init();
 int flow_blk_read_trace(unsigned long long* out, int cap);   // tuning: CTA 0's timeline of the last traced launch
