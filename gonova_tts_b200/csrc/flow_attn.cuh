@@ -38,6 +38,27 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// after tcgen05.wait::ld: names the registers as in-out operands of an (empty) volatile asm, so that nothing that reads
+// them is scheduled before the wait
+__device__ __forceinline__ void tmem_ld_pin32(uint32_t (&r)[32]) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace tc2
 
 template <int kVariant>
@@ -213,48 +234,43 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         mbar_wait(b_s_full + 8u * g, ns & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int kmax = len - j * 128;                  // keys of this tile that exist (>= 1)
-        // pass A: row maximum
-        float mx = -INFINITY;
-#pragma unroll 1
+        // the whole S row (128 scores) into registers with ONE wait: a tcgen05.ld round trip is several hundred cycles and a
+        // warpgroup has one warp per scheduler (chunk by chunk, twice over, the loads were most of the tile's time)
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32_issue(lane_base + (uint32_t)(c * 32), sr[c]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_pin32(sr[c]);
+        if (kmax < 128) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) sr[c][i] = 0xff800000u;    // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i])); mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i])); mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // Lazy rescale: the reference maximum moves only when some row of the warp would otherwise see P > 2^8 (bf16 / fp32
+        // have the headroom); then the O tile in TMEM is left alone — its load / scale / store round trip was a quarter of
+        // a tile's critical path, and after the first tiles of an utterance the running maximum rarely grows that much.
+        const float m_cand = fmaxf(m, mx * p.sc2);
+        const bool move = (j == 0) || __any_sync(0xffffffffu, m_cand - m > 8.0f);
+        const float m_new = move ? m_cand : m;
+        const float corr = move ? ex2_fast(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
+        // P = 2^(s sc2 - m_new) -> bf16 -> shared memory (K block = 64 keys; 16-byte chunks XOR row & 7); masked keys: 2^-inf = 0
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
           float v[32];
-          tmem_ld32(lane_base + (uint32_t)(c * 32), v);
-          if (kmax < 128) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) v[i] = -INFINITY;
-          }
+          for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(__uint_as_float(sr[c][i]), p.sc2, -m_new));
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
-        }
-        const float m_new = fmaxf(m, mx * p.sc2);
-        const float corr = ex2_fast(m - m_new);          // 0 on the first tile (m = -inf)
-        if (j > 0) {
-          // the previous tile's P V has landed in O: rescale it to the new maximum
-          mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            float v[32];
-            tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= corr;
-            tmem_st32(lane_base + 128u + (uint32_t)(c * 32), v);
-          }
-          l *= corr;
-        }
-        // pass B: P = 2^(s sc2 - m_new) -> bf16 -> shared memory (K block = 64 keys; 16-byte chunks XOR row & 7)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32(lane_base + (uint32_t)(c * 32), v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(v[i], p.sc2, -m_new));
-          if (kmax < 128) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) v[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) l += v[i];
+          for (int i = 0; i < 32; i += 2) { l0 += v[i]; l1 += v[i + 1]; }
           const uint32_t rowa = p_row + (uint32_t)(c >> 1) * 16384u;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
@@ -262,8 +278,27 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
                     ElemIO<E>::pack2(v[8 * k4 + 2], v[8 * k4 + 3]), ElemIO<E>::pack2(v[8 * k4 + 4], v[8 * k4 + 5]),
                     ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
         }
+        l = fmaf(l, corr, l0 + l1);
+        if (j > 0 && move) {
+          // the previous tile's P V has landed in O: rescale it to the new maximum (both halves in flight, one wait)
+          mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t orr[2][32];
+          tmem_ld32_issue(lane_base + 128u, orr[0]);
+          tmem_ld32_issue(lane_base + 160u, orr[1]);
+          tmem_wait_ld();
+          tmem_ld_pin32(orr[0]);
+          tmem_ld_pin32(orr[1]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(orr[c][i]) * corr;
+            tmem_st32(lane_base + 128u + (uint32_t)(c * 32), v);
+          }
+        }
         m = m_new;
-        if (j > 0) tmem_wait_st();
+        if (j > 0 && move) tmem_wait_st();
         fence_async_smem();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
