@@ -641,11 +641,94 @@ def main():
                 torch.cuda.synchronize(dev)
                 fms = fe0.elapsed_time(fe1) / 3
                 gemm_flops = 2.0 * 65.1e6 * 2 * fB * fT * 10 + 10 * 56 * 2 * fB * 8 * 4.0 * fT * fT * 64
+                # per-kernel-class device times of ONE estimator evaluation (gnv_flow_profile: an event after every launch)
+                import collections
+                import re as _re
+                flow.profile(fz, fmu, fsp, fcond, n_timesteps=1)
+                acc = collections.OrderedDict()
+                n_fp = 3
+                for _ in range(n_fp):
+                    for name, kind, ms_i, fl_i in flow.profile(fz, fmu, fsp, fcond, n_timesteps=1):
+                        cls = _re.sub(r"^(down_blocks\.0|mid_blocks\.\d+|up_blocks\.0)\.", "L.", name)
+                        cls = _re.sub(r"^L\.1\.\d+\.", "L.1.j.", cls)
+                        a_ = acc.setdefault(cls, [0, 0.0, 0.0])
+                        a_[0] += 1; a_[1] += ms_i / n_fp; a_[2] += fl_i / n_fp
+                eval_ms = sum(v[1] for v in acc.values())
+                f_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) if flow.dtype == "bf16" else None
+                fk = []
+                for cls, (n_l, ms_c, fl_c) in sorted(acc.items(), key=lambda kv: -kv[1][1]):
+                    ent = {"kernel": cls, "launches": n_l // n_fp, "ms": ms_c, "share": ms_c / eval_ms if eval_ms else 0.0}
+                    if fl_c > 0:
+                        ent.update({"bound": "tensor", "achieved": fl_c / (ms_c / 1e3) / 1e12, "unit": "TFLOP/s"})
+                        if f_peak:
+                            ent.update({"peak": f_peak, "frac": ent["achieved"] / f_peak})
+                    fk.append(ent)
+                tens_ms = sum(v[1] for v in acc.values() if v[2] > 0)
+                tens_fl = sum(v[2] for v in acc.values())
+                # end to end: pinned host inputs -> device, decode, mel back to pinned host memory, inside the timed region
+                hz, hmu, hcond, hsp = (t.cpu().pin_memory() for t in (fz, fmu, fcond, fsp))
+                hmel = torch.empty(fB, 80, fT, dtype=torch.float32).pin_memory()
+                dz, dmu, dcond, dsp = (torch.empty_like(t) for t in (fz, fmu, fcond, fsp))
+
+                def flow_e2e():
+                    dz.copy_(hz, non_blocking=True); dmu.copy_(hmu, non_blocking=True)
+                    dcond.copy_(hcond, non_blocking=True); dsp.copy_(hsp, non_blocking=True)
+                    hmel.copy_(flow.decode(dz, dmu, dsp, dcond), non_blocking=True)
+
+                flow_e2e()
+                torch.cuda.synchronize(dev)
+                fe0.record(stream)
+                for _ in range(3):
+                    flow_e2e()
+                fe1.record(stream)
+                torch.cuda.synchronize(dev)
+                fms_e2e = fe0.elapsed_time(fe1) / 3
+                # one utterance alone (the service's case: one sentence per request)
+                z1, mu1, sp1, c1 = fz[:1].contiguous(), fmu[:1].contiguous(), fsp[:1].contiguous(), fcond[:1].contiguous()
+                for _ in range(2):
+                    flow.decode(z1, mu1, sp1, c1)
+                torch.cuda.synchronize(dev)
+                fe0.record(stream)
+                for _ in range(5):
+                    flow.decode(z1, mu1, sp1, c1)
+                fe1.record(stream)
+                torch.cuda.synchronize(dev)
+                fms_b1 = fe0.elapsed_time(fe1) / 5
+                flow_cpu = None
+                if not args.no_cpu_baseline:
+                    # the oracle (fp32 torch CPU restatement) on all host cores, bounded sample: 1 utterance x 100 frames, 2 Euler steps
+                    from oracle import flow_ref as FR
+                    torch.set_num_threads(os.cpu_count() or 1)
+                    est = FR.load_estimator(FR.random_state_dict(0))
+                    cz, cmu, cmask, csp, ccond = FR.synthetic_inputs(1, 100, seed=1)
+                    with torch.inference_mode():
+                        FR.solve_euler(est, cz, cmu, cmask, csp, ccond, n_timesteps=1)
+                        t0c = time.perf_counter()
+                        FR.solve_euler(est, cz, cmu, cmask, csp, ccond, n_timesteps=2)
+                        dtc = time.perf_counter() - t0c
+                    flow_cpu = {"value": 100 / 50.0 / (dtc * 5.0), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"1 utterance x 100 frames, 2 of the 10 Euler steps in {dtc:.2f} s (x5 for the full "
+                                          "solve), fp32 torch CPU oracle (oracle/flow_ref.py)"}
                 flow_block = {"value": fB * fT / 50.0 / (fms / 1e3), "unit": UNIT, "ms_per_decode": fms, "batch": fB, "frames": fT,
-                              "n_timesteps": 10, "cfg_rate": 0.7, "gpu_launches": flow.launches(10),
+                              "dtype": flow.dtype, "n_timesteps": 10, "cfg_rate": 0.7, "gpu_launches": flow.launches(10),
                               "algorithmic_tflops": gemm_flops / (fms / 1e3) / 1e12,
+                              "e2e": {"value": fB * fT / 50.0 / (fms_e2e / 1e3), "unit": UNIT, "ms_per_decode": fms_e2e,
+                                      "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in (hz, hmu, hcond, hsp))),
+                                      "d2h_bytes_per_step": int(hmel.numel() * 4)},
+                              "one_utterance": {"ms_per_decode": fms_b1, "value": fT / 50.0 / (fms_b1 / 1e3), "unit": UNIT},
+                              "estimator_eval_ms_profiled": eval_ms,
+                              "roofline": {"kernel": "flow_blk_kernel + flow_attn_tc_kernel + conv_tc2_kernel (every tensor-core "
+                                                     "launch of one estimator evaluation)", "bound": "tensor",
+                                           "achieved": tens_fl / (tens_ms / 1e3) / 1e12 if tens_ms else 0.0, "peak": f_peak,
+                                           "unit": "TFLOP/s",
+                                           "frac": (tens_fl / (tens_ms / 1e3) / 1e12 / f_peak) if (f_peak and tens_ms) else None,
+                                           "traffic": None,
+                                           "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
+                                                  "per-launch CUDA-event time of those launches in one evaluation"},
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
-                                      "(classifier-free guidance); estimator GEMMs on the tcgen05 conv kernel, attention on mma.sync"}
+                                      "(classifier-free guidance); bf16: transformer blocks on flow_blk_kernel (fused q/k/v, "
+                                      "out-proj + residual + LayerNorm, whole feed-forward) and flow_attn_tc_kernel (tcgen05)"}
                 del flow
                 torch.cuda.empty_cache()
             except Exception as e:

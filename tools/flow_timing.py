@@ -4,13 +4,15 @@ import torch
 
 sys.path.insert(0, ".")
 from gonova_tts_b200 import B200Flow  # noqa: E402
-from oracle import flow_ref as FR  # noqa: E402  (weights / inputs only)
+from gonova_tts_b200.flow import random_flow_state_dict  # noqa: E402
 
 dev = torch.device("cuda:0")
 dtype = sys.argv[1] if len(sys.argv) > 1 else "bf16"
-flow = B200Flow(FR.random_state_dict(0), device=dev, dtype=dtype)
+flow = B200Flow(random_flow_state_dict(0), device=dev, dtype=dtype)
 for B, T in ((1, 100), (1, 500), (8, 500), (32, 500)):
-    z, mu, mask, spks, cond = [t.to(dev) for t in FR.synthetic_inputs(B, T, seed=1)]
+    g = torch.Generator().manual_seed(1)
+    z, mu, cond = (torch.randn(B, 80, T, generator=g).to(dev) for _ in range(3))
+    spks = torch.randn(B, 80, generator=g).to(dev)
     for _ in range(2):
         flow.decode(z, mu, spks, cond)
     torch.cuda.synchronize()
