@@ -98,12 +98,12 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
   const auto idesc = [&](uint32_t n) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24); };
   p.idesc128 = idesc(128);
   p.idesc256 = idesc(256);
-  p.sw = 4;
+  p.sw = 5;
   p.off_x = 0;
   p.off_h = 4 * kFbSlot;
   p.off_w = p.off_h + 4 * kFbSlot;
-  p.off_sc = p.off_w + (uint32_t)p.sw * kFbSlot;
-  p.off_tab = p.off_sc + 4 * 4096;
+  p.off_sc = p.off_w + (uint32_t)p.sw * kFbSlot;     // (no separate scratch any more: the epilogue's scratch is the H region)
+  p.off_tab = p.off_sc;
   p.off_bar = p.off_tab + (((uint32_t)kFbTab * 4u + 1023u) & ~1023u);
   out->smem_bytes = (size_t)p.off_bar + 1024 + 1024;
   if (out->smem_bytes > kFbMaxDynSmem) return "flow_blk: shared memory budget exceeded";

@@ -10,16 +10,17 @@
 //   FB_OUT  : R' = R + A W^T + b  (the attention output projection, K = 512 streamed), same epilogue
 //   FB_WIDE : Y = A W^T (+ b) as bf16, N in tiles of 256 (the fused q / k / v projection, N = 1536)
 //
-// The residual + LayerNorm epilogue belongs to four "row" warps (thread = one row of the tile, all 256 columns): the R row
-// is fetched while the MMAs run, x = acc + b2 + R goes back into TMEM with its shifted sums, and the second pass writes
-// LayerNorm(x) — no exchange between threads, no shared-memory staging.  They run beside the sixteen "column" warps (the
-// GELU epilogue of the NEXT tile's first chunks), so a tile's tail overlaps the next tile's head.
+// The residual + LayerNorm epilogue (E2) runs on the same sixteen warps once a tile's last MMA has retired: a warp owns 32
+// rows x 64 columns, x = acc + b2 + R goes back into TMEM with the thread's mean / M2, the four warps of a lane quarter
+// combine them through shared memory, and the second pass writes LayerNorm(x).
 //
 // CTA pair (cluster of 2, tcgen05.mma.cta_group::2, M = 256): each CTA owns 128 rows and stages HALF of every weight
 // tile; the leader's MMA warp issues for both.  TMEM (512 columns): acc1 x 2 at 0 / 128, acc2 at 256 (OUT / WIDE: two
 // 256-column buffers).  Shared memory: x 64 KB (FF / WIDE: resident A tile; OUT: A ring) | H 64 KB (WIDE: output staging) |
-// weight ring sw x 16 KB.  768 threads: 16 column warps, 4 row warps, TMEM allocator, barrier init, TMA producer, MMA issuer.
+// weight ring sw x 16 KB.  640 threads: 16 epilogue warps, TMEM allocator, barrier init, TMA producer, MMA issuer.
 #pragma once
+#include <type_traits>
+
 #include "conv_tc2.cuh"
 
 namespace gnv {
@@ -27,7 +28,7 @@ namespace gnv {
 enum { FB_FF = 0, FB_OUT = 1, FB_WIDE = 2 };
 constexpr int kFbSlot = 16384;     // one K block (64 bf16) of 128 rows: A tile of a CTA / weight ring slot
 constexpr int kFbMaxSw = 6;
-constexpr int kFbTab = 1536 + 3 * 256;     // floats: b1 | b2 | gamma | beta
+constexpr int kFbTab = 1536 + 3 * 256 + 16 * 32 * 2;     // floats: b1 | b2 | gamma | beta | LayerNorm exchange
 
 struct FlowBlkParams {
   int M, T, tiles;          // rows, rows per utterance, pair tiles of 256 rows
@@ -52,11 +53,11 @@ struct FlowBlkParams {
 
 struct FlowBlkMaps { CUtensorMap A, W1, W2, Nout; };
 
-constexpr int kFbThreads = 768;
-// warps 0..15 "column" warps (TMEM lane quarter w % 4, column block w / 4): the GELU epilogue of FF, the output of WIDE;
-// warps 16..19 "row" warps (thread = row): residual + LayerNorm epilogue of FF / OUT, straight to global memory;
-// the single-lane control warps last (highest ids: favoured by the warp arbiter)
-constexpr int kFbWarpTmem = 20, kFbWarpInit = 21, kFbWarpProducer = 22, kFbWarpMma = 23;
+constexpr int kFbThreads = 640;
+// warps 0..15 epilogue warps (TMEM lane quarter w % 4, column block w / 4): the GELU epilogue of FF, the residual +
+// LayerNorm epilogue of FF / OUT, the output of WIDE; the single-lane control warps last (highest ids: favoured by the
+// warp arbiter)
+constexpr int kFbWarpTmem = 16, kFbWarpInit = 17, kFbWarpProducer = 18, kFbWarpMma = 19;
 
 #ifdef __CUDACC__
 namespace tc2 {
@@ -199,7 +200,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       mbar_init(b_e1_done + 8u * s, 32);                               // 16 column warps of both CTAs arrive on the leader
       mbar_init(b_h_empty + 8u * s, 1);
       mbar_init(b_acc2_full + 8u * s, 1);
-      mbar_init(b_acc2_free + 8u * s, MODE == FB_WIDE ? 32 : 8);       // WIDE: column warps; FF / OUT: the four row warps
+      mbar_init(b_acc2_free + 8u * s, 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -441,11 +442,242 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       }
     }
   } else if (warp < 16) {
-    // ===== column warps =====
+    // ===== the sixteen epilogue warps: TMEM lane quarter q = warp % 4 (32 rows), column block cb = warp / 4 =====
     const int q = warp & 3, cb = warp >> 2;
     const int erow = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int tre = tr && warp == 0;
+
+    // ---- E2 (FF / OUT): x = acc + b2 + R  ->  R' (fp32, in place)  and  N' = LayerNorm(x) gamma + beta  (or bf16(x)) ----
+    // A warp owns 32 rows x 64 columns (four 16-column steps).  TMEM gives a thread one ROW; global memory wants a warp
+    // instruction to cover whole 64-byte row segments: every step passes through a 2 KB scratch of the warp (in the H region,
+    // idle between a tile's last G2 and the next tile's first E1): the R segment arrives there by cp.async (lane -> row
+    // 8 i + lane / 4, 16-byte piece lane % 4), the thread reads its row, writes x back in place, and the warp stores the
+    // scratch with the same coalesced mapping.  LayerNorm: each thread's mean / M2 over its 64 columns, combined across the
+    // four warps of the lane quarter through shared memory (Chan's formula), x parked in TMEM for the second pass.
+    // (History: four dedicated "row" warps with a whole row per thread ran this at one warp per scheduler — every
+    // instruction's latency exposed, 25 k cycles per tile; these sixteen warps do it in ~5 k.)
+    const uint32_t sc0 = sH + (uint32_t)warp * 4096u;
+    const uint32_t my_row = (uint32_t)lane * 64u, my_sw = ((uint32_t)lane >> 1) & 3u;
+    uint32_t co_off[4];                                 // coalesced mapping, fp32: instruction i -> row 8 i + lane / 4
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t r = 8u * i + ((uint32_t)lane >> 2), pc = (uint32_t)lane & 3u;
+      co_off[i] = r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
+    }
+    uint32_t cbo[2];                                    // coalesced mapping, bf16 (rows of 32 B): i -> row 16 i + lane / 2
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t r = 16u * i + ((uint32_t)lane >> 1), pc = (uint32_t)lane & 1u;
+      cbo[i] = r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
+    }
+    float* red = tab + 1536 + 768;                      // [16 warps][32 lanes][2]: mean, M2 of a thread's 64 columns
+    auto e2_tile = [&](int t, uint32_t acc_col, uint32_t full_bar, uint32_t full_par, uint32_t free_bar) {
+      const int wrow0 = t * 256 + crank * 128 + q * 32;   // first row of this warp
+      const int row = wrow0 + lane;
+      bool live = row < p.M;
+      if (live && p.lengths) { const int b = row / p.T; live = row - b * p.T < p.lengths[b]; }
+      const uint32_t acc = lane_base + acc_col + (uint32_t)(cb * 64);
+      const float* rsrc[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = wrow0 + 8 * i + (lane >> 2);
+        rok[i] = r < p.M;
+        rsrc[i] = p.r + (size_t)(rok[i] ? r : 0) * 256 + cb * 64 + (lane & 3) * 4;
+      }
+      __nv_bfloat16* ndst[2];
+      bool nok[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = wrow0 + 16 * i + (lane >> 1);
+        nok[i] = r < p.M;
+        ndst[i] = p.n_out + (size_t)(nok[i] ? r : 0) * p.n_pitch + cb * 64 + (lane & 1) * 8;
+      }
+      auto issue_load = [&](int st) {
+        const uint32_t sc = sc0 + (uint32_t)(st & 1) * 2048u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int nb = rok[i] ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sc + co_off[i]), "l"(rsrc[i] + st * 16), "r"(nb) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      if constexpr (MODE == FB_OUT) {                     // (OUT: the H region is never an operand: the R segments load under the MMAs)
+        issue_load(0);
+        issue_load(1);
+      }
+      mbar_wait(full_bar, full_par, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      fb_trace(tre, 3, t, 0, 4, tri);
+      if constexpr (MODE == FB_FF) {
+        issue_load(0);
+        issue_load(1);
+      }
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      uint32_t tv0[16], tv1[16];
+      tmem_ld16_issue(acc, tv0);
+      // (instruction count matters here: sixteen warps run this pass issue-bound.  Everything that moves by a constant per
+      // step is a pointer bumped once per loop trip plus a compile-time offset, and the row-in-range predicates exist
+      // only in the instantiation for a tensor's last, partial tile.)
+      const bool full = wrow0 + 32 <= p.M;                 // warp-uniform
+      auto pass1 = [&](auto FULLC) {
+        constexpr bool FULL = decltype(FULLC)::value;
+        const float* rp[4] = {rsrc[0], rsrc[1], rsrc[2], rsrc[3]};
+        __nv_bfloat16* np[2] = {ndst[0], ndst[1]};
+        const float* btp = tb2 + cb * 64;
+        uint32_t accp = acc;
+        auto step1 = [&](auto ODD, bool more, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
+          constexpr int odd = decltype(ODD)::value;
+          const uint32_t sc = sc0 + (uint32_t)odd * 2048u;
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();
+          tmem_ld_wait16(tcur);
+          if (odd == 0 || more) tmem_ld16_issue(accp + (uint32_t)(odd * 16 + 16), tnext);
+          float v[16];
+          const float4* bt = reinterpret_cast<const float4*>(btp + odd * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = bt[j];
+            const float4 r4 = lds128(sc + my_row + (((uint32_t)j ^ my_sw) << 4));
+            v[4 * j] = __uint_as_float(tcur[4 * j]) + b4.x + r4.x;
+            v[4 * j + 1] = __uint_as_float(tcur[4 * j + 1]) + b4.y + r4.y;
+            v[4 * j + 2] = __uint_as_float(tcur[4 * j + 2]) + b4.z + r4.z;
+            v[4 * j + 3] = __uint_as_float(tcur[4 * j + 3]) + b4.w + r4.w;
+          }
+          if (!live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(sc + my_row + (((uint32_t)j ^ my_sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 o = lds128(sc + co_off[i]);
+            if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + odd * 16) = o;
+          }
+          if (p.ln) {
+            if (odd == 0 && more) shift = v[0];           // (first step: sums relative to a value of the row itself)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float d = v[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+            tmem_st16(accp + (uint32_t)(odd * 16), v);
+          } else {
+            __syncwarp();                                 // the fp32 rows have been read: the scratch takes the bf16 rows
+            sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
+                    ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
+            sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
+                    ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 o = lds128(sc + cbo[i]);
+              if (FULL || nok[i]) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
+            }
+          }
+          __syncwarp();                                   // this scratch buffer is free again
+          if (more) {                                     // the segment two steps on, into the buffer just freed
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int nb = (FULL || rok[i]) ? 16 : 0;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sc + co_off[i]), "l"(rp[i] + odd * 16 + 32), "r"(nb) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty: keeps the wait count uniform)
+        };
+#pragma unroll 1
+        for (int sp = 0; sp < 2; ++sp) {
+          const bool more = sp == 0;
+          step1(std::integral_constant<int, 0>{}, more, tv0, tv1);
+          step1(std::integral_constant<int, 1>{}, more, tv1, tv0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rp[i] += 32;
+          np[0] += 32; np[1] += 32;
+          btp += 32;
+          accp += 32u;
+        }
+      };
+      if (full) pass1(std::true_type{}); else pass1(std::false_type{});
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (p.ln) {
+        tmem_wait_st();
+        // this thread: 64 columns -> (mean, M2); the row's other three quarters sit in warps q + 4 k
+        const float m1 = s1 * (1.f / 64.f);
+        red[(warp * 32 + lane) * 2] = shift + m1;
+        red[(warp * 32 + lane) * 2 + 1] = fmaxf(s2 - s1 * m1, 0.f);
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+        float mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mean += red[((q + 4 * k) * 32 + lane) * 2];
+        mean *= 0.25f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d = red[((q + 4 * k) * 32 + lane) * 2] - mean;
+          m2 += red[((q + 4 * k) * 32 + lane) * 2 + 1] + 64.f * d * d;
+        }
+        const float rstd = rsqrtf(m2 * (1.f / 256.f) + 1e-5f);
+        const float nmr = -mean * rstd;
+        fb_trace(tre, 3, t, 0, 5, tri);
+        tmem_ld16_issue(acc, tv0);
+        auto pass2 = [&](auto FULLC) {
+          constexpr bool FULL = decltype(FULLC)::value;
+          __nv_bfloat16* np[2] = {ndst[0], ndst[1]};
+          const float* gp = tg + cb * 64;
+          const float* bp = tbt + cb * 64;
+          uint32_t accp = acc;
+          auto step2 = [&](auto ODD, bool more, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
+            constexpr int odd = decltype(ODD)::value;
+            const uint32_t sc = sc0 + (uint32_t)odd * 2048u;
+            tmem_ld_wait16(tcur);
+            if (odd == 0 || more) tmem_ld16_issue(accp + (uint32_t)(odd * 16 + 16), tnext);
+            float v[16];
+            const float4* g4 = reinterpret_cast<const float4*>(gp + odd * 16);
+            const float4* b4p = reinterpret_cast<const float4*>(bp + odd * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 gg = g4[j], bb = b4p[j];
+              v[4 * j] = fmaf(fmaf(__uint_as_float(tcur[4 * j]), rstd, nmr), gg.x, bb.x);
+              v[4 * j + 1] = fmaf(fmaf(__uint_as_float(tcur[4 * j + 1]), rstd, nmr), gg.y, bb.y);
+              v[4 * j + 2] = fmaf(fmaf(__uint_as_float(tcur[4 * j + 2]), rstd, nmr), gg.z, bb.z);
+              v[4 * j + 3] = fmaf(fmaf(__uint_as_float(tcur[4 * j + 3]), rstd, nmr), gg.w, bb.w);
+            }
+            if (!live) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
+                    ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
+            sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
+                    ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float4 o = lds128(sc + cbo[i]);
+              if (FULL || nok[i]) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
+            }
+            // (the next step writes the OTHER scratch buffer; this one is rewritten two steps on, after two more __syncwarp)
+          };
+#pragma unroll 1
+          for (int sp = 0; sp < 2; ++sp) {
+            const bool more = sp == 0;
+            step2(std::integral_constant<int, 0>{}, more, tv0, tv1);
+            step2(std::integral_constant<int, 1>{}, more, tv1, tv0);
+            np[0] += 32; np[1] += 32;
+            gp += 32; bp += 32;
+            accp += 32u;
+          }
+        };
+        if (full) pass2(std::true_type{}); else pass2(std::false_type{});
+        // the next tile rewrites the exchange words and the scratch: every warp of the quarter is done reading both
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (elect_one()) mbar_arrive_leader(free_bar);
+      fb_trace(tre, 3, t, 0, 6, tri);
+    };
+
     if constexpr (MODE == FB_FF) {
       // E1(c): gelu(acc1 + b1_c) -> bf16 -> H[c & 1] in the K-major SWIZZLE_128B operand layout; this warp: 32 of the 128 columns
       int it = 0;
@@ -481,8 +713,18 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           if (elect_one()) mbar_arrive_leader(b_e1_done + 8u * buf);
           fb_trace(tre, 0, t, c, 3, tri);
         }
+        // the tile's rows are complete once the last G2 has retired (which also frees the H region for the scratch)
+        e2_tile(t, 256u, b_acc2_full, (uint32_t)(it & 1), b_acc2_free);
+        // every warp's generic-proxy writes to the H region are done before the next tile's E1 hands it to the tensor core
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
-    } else if constexpr (MODE == FB_WIDE) {
+    } else if constexpr (MODE == FB_OUT) {
+      int it = 0;
+      for (int t = pair0; t < p.tiles; t += G, ++it) {
+        const uint32_t buf = (uint32_t)(it & 1);
+        e2_tile(t, buf * 256u, b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), b_acc2_free + 8u * buf);
+      }
+    } else {
       // plain output: this warp's 32 rows x 64 columns of every 256-column tile, staged and stored by TMA
       int cnt = 0;
       for (int u = pair0; u < n_units; u += G) {
@@ -546,191 +788,6 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         }
       }
       if (elect_one()) bulk_wait_read<0>();
-    }
-  } else if (warp < 20) {
-    // ===== row warps (FF / OUT): a warp owns 32 rows of the tile, all 256 columns, in sixteen 16-column steps =====
-    //   x = acc + b2 + R  ->  R' (fp32, in place)  and  N' = LayerNorm(x) gamma + beta  (or bf16(x)).
-    // TMEM gives a thread one ROW; global memory wants a warp instruction to cover whole 64-byte row segments.  (Each
-    // thread moving its own row — even as full 32-byte sectors — cost 16 k cycles per pass: 32 lines per instruction.)  So
-    // every step passes through a 2 KB shared-memory scratch of the warp: the R segment arrives there by cp.async (lane ->
-    // row 8 i + lane / 4, 16-byte piece lane % 4: eight rows x 64 contiguous bytes per instruction), the thread reads its
-    // row, writes x back in place, and the warp stores the scratch with the same coalesced mapping.  Two scratch buffers:
-    // the segment of step st + 2 is in flight while step st is computed; the tcgen05.ld of step st + 1 as well.
-    if constexpr (MODE != FB_WIDE) {
-      const int q = warp & 3;
-      const int erow = q * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      const int tre = tr && warp == 16;
-      const uint32_t sc0 = smem_base + p.off_sc + (uint32_t)(warp - 16) * 4096u;
-      // scratch addressing (rows of 64 B, 16-byte pieces XOR-swizzled like TMA's SWIZZLE_64B): conflict-free both ways
-      const uint32_t my_row = (uint32_t)lane * 64u, my_sw = ((uint32_t)lane >> 1) & 3u;
-      uint32_t co_off[4];                                 // coalesced mapping, fp32: instruction i -> row 8 i + lane / 4
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t r = 8u * i + ((uint32_t)lane >> 2), pc = (uint32_t)lane & 3u;
-        co_off[i] = r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
-      }
-      uint32_t cb_off[2];                                 // coalesced mapping, bf16 (rows of 32 B): i -> row 16 i + lane / 2
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t r = 16u * i + ((uint32_t)lane >> 1), pc = (uint32_t)lane & 1u;
-        cb_off[i] = r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
-      }
-      int it = 0;
-      for (int t = pair0; t < p.tiles; t += G, ++it) {
-        const int wrow0 = t * 256 + crank * 128 + q * 32;   // first row of this warp
-        const int row = wrow0 + lane;
-        bool live = row < p.M;
-        if (live && p.lengths) { const int b = row / p.T; live = row - b * p.T < p.lengths[b]; }
-        const uint32_t buf = MODE == FB_OUT ? (uint32_t)(it & 1) : 0u;
-        const uint32_t acc = lane_base + (MODE == FB_OUT ? buf * 256u : 256u);
-        // per-instruction global pointers of the coalesced mappings (rows past M are never touched)
-        const float* rsrc[4];
-        bool rok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = wrow0 + 8 * i + (lane >> 2);
-          rok[i] = r < p.M;
-          rsrc[i] = p.r + (size_t)(rok[i] ? r : 0) * 256 + (lane & 3) * 4;
-        }
-        __nv_bfloat16* ndst[2];
-        bool nok[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int r = wrow0 + 16 * i + (lane >> 1);
-          nok[i] = r < p.M;
-          ndst[i] = p.n_out + (size_t)(nok[i] ? r : 0) * p.n_pitch + (lane & 1) * 8;
-        }
-        auto issue_load = [&](int st) {
-          const uint32_t sc = sc0 + (uint32_t)(st & 1) * 2048u;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int nb = rok[i] ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sc + co_off[i]), "l"(rsrc[i] + st * 16), "r"(nb) : "memory");
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        // the residual rows do not depend on this tile's MMAs: pull them into L2 and start the first two steps now
-        if (row < p.M && lane == 0) {
-          const int nrows = min(32, p.M - row);
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.r + (size_t)row * 256), "r"(nrows * 1024) : "memory");
-        }
-        issue_load(0);
-        issue_load(1);
-        if constexpr (MODE == FB_OUT) mbar_wait(b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), 4);
-        else mbar_wait(b_acc2_full, (uint32_t)(it & 1), 4);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        fb_trace(tre, 3, t, 0, 4, tri);
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
-        uint32_t tv0[16], tv1[16];
-        tmem_ld16_issue(acc, tv0);
-        // (a real loop, two steps per trip: fully unrolled, the two passes were ~100 KB of code that every tile fetched
-        // from L2 once — the row warps ran at four cycles per instruction and a pass took 20 k cycles)
-        auto step1 = [&](int st, uint32_t (&tcur)[16], uint32_t (&tnext)[16], uint32_t sc) {
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-          __syncwarp();
-          tmem_ld_wait16(tcur);
-          if (st + 1 < 16) tmem_ld16_issue(acc + (uint32_t)((st + 1) * 16), tnext);
-          float v[16];
-          const float4* bt = reinterpret_cast<const float4*>(tb2 + st * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b4 = bt[j];
-            const float4 r4 = lds128(sc + my_row + (((uint32_t)j ^ my_sw) << 4));
-            v[4 * j] = __uint_as_float(tcur[4 * j]) + b4.x + r4.x;
-            v[4 * j + 1] = __uint_as_float(tcur[4 * j + 1]) + b4.y + r4.y;
-            v[4 * j + 2] = __uint_as_float(tcur[4 * j + 2]) + b4.z + r4.z;
-            v[4 * j + 3] = __uint_as_float(tcur[4 * j + 3]) + b4.w + r4.w;
-          }
-          if (!live) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(sc + my_row + (((uint32_t)j ^ my_sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 o = lds128(sc + co_off[i]);
-            if (rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rsrc[i]) + st * 16) = o;
-          }
-          if (p.ln) {
-            if (st == 0) shift = v[0];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const float d = v[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
-            tmem_st16(acc + (uint32_t)(st * 16), v);
-          } else {
-            __syncwarp();                                 // the fp32 rows have been read: the scratch takes the bf16 rows
-            sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
-                    ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
-            sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
-                    ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 o = lds128(sc + cb_off[i]);
-              if (nok[i]) *reinterpret_cast<float4*>(ndst[i] + st * 16) = o;
-            }
-          }
-          __syncwarp();                                   // this scratch buffer is free again
-          if (st + 2 < 16) issue_load(st + 2);
-          else asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the wait count uniform)
-        };
-#pragma unroll 1
-        for (int sp = 0; sp < 8; ++sp) {
-          step1(2 * sp, tv0, tv1, sc0);
-          step1(2 * sp + 1, tv1, tv0, sc0 + 2048u);
-        }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (p.ln) {
-          tmem_wait_st();
-          const float m1 = s1 * (1.f / 256.f);
-          const float mean = shift + m1;
-          const float rstd = rsqrtf(fmaxf(s2 * (1.f / 256.f) - m1 * m1, 0.f) + 1e-5f);
-          fb_trace(tre, 3, t, 0, 5, tri);
-          tmem_ld16_issue(acc, tv0);
-          auto step2 = [&](int st, uint32_t (&tcur)[16], uint32_t (&tnext)[16], uint32_t sc) {
-            tmem_ld_wait16(tcur);
-            if (st + 1 < 16) tmem_ld16_issue(acc + (uint32_t)((st + 1) * 16), tnext);
-            float v[16];
-            const float4* g4 = reinterpret_cast<const float4*>(tg + st * 16);
-            const float4* b4p = reinterpret_cast<const float4*>(tbt + st * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 gg = g4[j], bb = b4p[j];
-              v[4 * j] = fmaf((__uint_as_float(tcur[4 * j]) - mean) * rstd, gg.x, bb.x);
-              v[4 * j + 1] = fmaf((__uint_as_float(tcur[4 * j + 1]) - mean) * rstd, gg.y, bb.y);
-              v[4 * j + 2] = fmaf((__uint_as_float(tcur[4 * j + 2]) - mean) * rstd, gg.z, bb.z);
-              v[4 * j + 3] = fmaf((__uint_as_float(tcur[4 * j + 3]) - mean) * rstd, gg.w, bb.w);
-            }
-            if (!live) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            }
-            sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
-                    ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
-            sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
-                    ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 o = lds128(sc + cb_off[i]);
-              if (nok[i]) *reinterpret_cast<float4*>(ndst[i] + st * 16) = o;
-            }
-            // (the next step writes the OTHER scratch buffer; this one is rewritten two steps on, after two more __syncwarp)
-          };
-#pragma unroll 1
-          for (int sp = 0; sp < 8; ++sp) {
-            step2(2 * sp, tv0, tv1, sc0);
-            step2(2 * sp + 1, tv1, tv0, sc0 + 2048u);
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (elect_one()) mbar_arrive_leader(b_acc2_free + 8u * buf);
-        fb_trace(tre, 3, t, 0, 6, tri);
-      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
