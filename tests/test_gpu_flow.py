@@ -86,3 +86,70 @@ def test_upstream_call_shape_and_determinism(flows, cuda_device):
     assert flow.launches(10) > 1000
     with pytest.raises(ValueError, match="shape"):
         flow.decode(torch.zeros(1, 80, 7, device=dev), mu.to(dev), spks.to(dev), cond.to(dev))
+
+
+def test_large_batch_walks_every_tile_path(flows, oracle, cuda_device):
+    """2 B T = 19 000 rows: 75 pair tiles of flow_blk_kernel on 74 CTA pairs (one pair takes a second tile: accumulator
+    hand-over, scratch reuse), six q/k/v tiles per resident A tile, attention over four 128-key tiles and two 256-query
+    groups, ragged lengths across tile boundaries.  One Euler step against the oracle, row by row."""
+    B, T = 19, 500
+    lengths = [500, 500, 257, 256, 255, 3, 500, 129, 400, 500, 500, 13, 500, 385, 500, 500, 64, 500, 500]
+    z, mu, mask, spks, cond = FR.synthetic_inputs(B, T, seed=11, lengths=lengths)
+    want = FR.solve_euler(oracle, z * mask, mu, mask, spks, cond, n_timesteps=1).numpy()
+    dev = cuda_device
+    got = flows("bf16").decode(z.to(dev), mu.to(dev), spks.to(dev), cond.to(dev), lengths=lengths, n_timesteps=1).cpu().numpy()
+    zn = (z * mask).numpy()
+    worst = 1e9
+    for b, n in enumerate(lengths):
+        assert np.all(got[b, :, n:] == 0)
+        snr = snr_db(got[b, :, :n] - zn[b, :, :n], want[b, :, :n] - zn[b, :, :n])
+        worst = min(worst, snr)
+        assert np.abs(got[b, :, :n] - want[b, :, :n]).max() <= TOL["bf16"][0] and snr >= TOL["bf16"][1], (b, n, snr)
+    print(f"[parity] flow 1 step bf16, 19 x 500 ragged: worst row SNR of the velocity {worst:.1f} dB")
+
+
+def test_empty_utterance_in_a_batch(flows, cuda_device):
+    """lengths[b] = 0: that row comes back as zeros (the attention kernel has no key tile to visit) and its neighbours are
+    what they are without it."""
+    B, T = 3, 40
+    z, mu, mask, spks, cond = FR.synthetic_inputs(B, T, seed=13, lengths=[40, 40, 40])
+    dev = cuda_device
+    flow = flows("bf16")
+    full = flow.decode(z.to(dev), mu.to(dev), spks.to(dev), cond.to(dev), lengths=[40, 40, 40], n_timesteps=2).cpu().numpy()
+    got = flow.decode(z.to(dev), mu.to(dev), spks.to(dev), cond.to(dev), lengths=[40, 0, 40], n_timesteps=2).cpu().numpy()
+    assert np.all(got[1] == 0) and np.isfinite(got).all()
+    assert np.array_equal(got[0], full[0]) and np.array_equal(got[2], full[2])
+
+
+def test_fused_blocks_equal_one_launch_per_projection(flows, cuda_device, tmp_path):
+    """GONOVA_FLOW_FUSED=0 (read once per process, hence a child process) runs the bf16 estimator with one conv_tc2 launch per
+    projection, separate LayerNorm launches and the mma.sync attention: the same arithmetic up to bf16 rounding of different
+    intermediates (the fused path never rounds the feed-forward's hidden activation through HBM differently: both round it to
+    bf16 once).  The two must agree far inside the tolerance against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    B, T = 2, 100
+    z, mu, mask, spks, cond = FR.synthetic_inputs(B, T, seed=17)
+    dev = cuda_device
+    got = flows("bf16").decode(z.to(dev), mu.to(dev), spks.to(dev), cond.to(dev), n_timesteps=3).cpu().numpy()
+    out = tmp_path / "unfused.npy"
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from oracle import flow_ref as FR\n"
+        "from gonova_tts_b200 import B200Flow\n"
+        f"z, mu, mask, spks, cond = FR.synthetic_inputs({B}, {T}, seed=17)\n"
+        "f = B200Flow(FR.random_state_dict(0), device='cuda:0', dtype='bf16')\n"
+        "d = 'cuda:0'\n"
+        "y = f.decode(z.to(d), mu.to(d), spks.to(d), cond.to(d), n_timesteps=3).cpu().numpy()\n"
+        f"np.save({str(out)!r}, y)\n"
+    )
+    env = dict(os.environ, GONOVA_FLOW_FUSED="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(out)
+    snr = snr_db(got, ref)
+    print(f"[parity] flow 3 steps bf16: fused blocks vs one launch per projection: max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
+    assert snr >= 38.0
