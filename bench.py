@@ -694,6 +694,33 @@ def main():
                 fe1.record(stream)
                 torch.cuda.synchronize(dev)
                 fms_b1 = fe0.elapsed_time(fe1) / 5
+                # the two drop-ins chained, as S3Gen.inference chains them: flow decoder -> mel -> vocoder -> int16 PCM in
+                # pinned host memory (mu / spks / cond resident: the encoder in front stays the engine's)
+                chain = None
+                try:
+                    pcm_host = torch.empty(fB, fT * 480, dtype=torch.int16).pin_memory()
+                    pcm_dev = torch.empty(fB, fT * 480, dtype=torch.int16, device=dev)
+                    no_cache = torch.zeros(fB, 1, 0, device=dev)
+
+                    def flow_then_vocoder():
+                        mel_f = flow.decode(fz, fmu, fsp, fcond)
+                        wav_f, _ = dec.inference(mel_f, cache_source=no_cache)
+                        pcm_tail(wav_f, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm_dev)
+                        pcm_host.copy_(pcm_dev, non_blocking=True)
+
+                    flow_then_vocoder()
+                    torch.cuda.synchronize(dev)
+                    fe0.record(stream)
+                    for _ in range(3):
+                        flow_then_vocoder()
+                    fe1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    cms = fe0.elapsed_time(fe1) / 3
+                    chain = {"value": fB * fT / 50.0 / (cms / 1e3), "unit": UNIT, "ms_per_batch": cms, "batch": fB,
+                             "what": "mu -> flow decoder (10 Euler steps, CFG) -> mel -> f0 / source / HiFT decode -> int16 PCM in "
+                                     "pinned host memory, both on this repo's kernels"}
+                except Exception as ce:
+                    chain = {"error": str(ce)}
                 flow_cpu = None
                 if not args.no_cpu_baseline:
                     # the oracle (fp32 torch CPU restatement) on all host cores, bounded sample: 1 utterance x 100 frames, 2 Euler steps
@@ -725,7 +752,7 @@ def main():
                                            "traffic": None,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
-                              "roofline_kernels": fk, "cpu_baseline": flow_cpu,
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
                                       "(classifier-free guidance); bf16: transformer blocks on flow_blk_kernel (fused q/k/v, "
                                       "out-proj + residual + LayerNorm, whole feed-forward) and flow_attn_tc_kernel (tcgen05)"}

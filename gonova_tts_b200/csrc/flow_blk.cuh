@@ -738,11 +738,19 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           mbar_wait(b_acc2_full + 8u * buf, (uint32_t)((cnt >> 1) & 1), 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           fb_trace(tre, 0, u, n, 4, tri);
+          // both 32-column halves of this warp's block in flight behind one wait (a tcgen05.ld round trip is ~400 cycles)
+          uint32_t tw[2][32];
+          tmem_ld32_issue(lane_base + buf * 256u + (uint32_t)(cb * 64), tw[0]);
+          tmem_ld32_issue(lane_base + buf * 256u + (uint32_t)(cb * 64 + 32), tw[1]);
+          tmem_wait_ld();
+          tmem_ld_pin32(tw[0]);
+          tmem_ld_pin32(tw[1]);
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2) {
             const int col = cb * 64 + i2 * 32;
             float v[32];
-            tmem_ld32(lane_base + buf * 256u + (uint32_t)col, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(tw[i2][j]);
             if (p.n_bias1) {
               const float4* bt = reinterpret_cast<const float4*>(tb1 + n * 256 + col);
 #pragma unroll
