@@ -2,6 +2,7 @@
 #include "flow_attn.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace gnv {
@@ -15,6 +16,18 @@ cudaError_t flow_attn_init() {
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(flow_attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFaMaxDynSmem);
+}
+
+int flow_attn_read_trace(unsigned long long* out, int cap) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  static unsigned long long host[kFaTraceCap];
+  if (cudaMemcpyFromSymbol(host, g_fa_trace, sizeof(host)) != cudaSuccess) return -1;
+  int n = 0;
+  for (int i = 0; i < kFaTraceCap && n < cap; ++i)
+    if (host[i]) out[n++] = host[i];
+  memset(host, 0, sizeof(host));
+  cudaMemcpyToSymbol(g_fa_trace, host, sizeof(host));
+  return n;
 }
 
 namespace {
@@ -47,6 +60,11 @@ const char* make_flow_attn_launch(FlowAttnLaunch* out, const void* qkv, const vo
   p.items = B2 * 8 * p.nqp;
   p.o = (__nv_bfloat16*)o;
   p.sc2 = scale * 1.4426950408889634f;
+  {
+    const char* v = getenv("GONOVA_FB_DBG");
+    const char* m = getenv("GONOVA_FB_TRACE_MODE");
+    p.dbg = (v && (atoi(v) & 8) && m && atoi(m) == 3) ? 8 : 0;
+  }
   const auto idesc = [&](uint32_t n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); };
   p.idesc_s = idesc(128);
   p.idesc_pv = idesc(64);

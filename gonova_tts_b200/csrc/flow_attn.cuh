@@ -25,6 +25,7 @@ struct FlowAttnParams {
   const int* lengths;
   __nv_bfloat16* o;                      // [B2, T, 512] (plain stores for the rows of an empty utterance)
   float sc2;                             // softmax scale * log2(e)
+  int dbg;                               // GONOVA_FB_DBG = 8 with GONOVA_FB_TRACE_MODE = 3: CTA 0's timeline
   uint32_t idesc_s, idesc_pv;
   uint32_t off_q, off_kv, off_p, off_bar;
 };
@@ -39,6 +40,18 @@ __device__ __forceinline__ float ex2_fast(float x) {
   return y;
 }
 }  // namespace tc2
+
+constexpr int kFaTraceCap = 4 * 2048;
+static __device__ unsigned long long g_fa_trace[kFaTraceCap];
+__device__ __forceinline__ void fa_trace(int on, int role, int a, int b, int ev, unsigned int& idx) {
+  if (!on) return;
+  unsigned int c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  if (idx < 2048u)
+    g_fa_trace[role * 2048 + idx] = ((unsigned long long)(role + 1) << 56) | ((unsigned long long)(a & 255) << 48) |
+                                    ((unsigned long long)(b & 255) << 40) | ((unsigned long long)ev << 32) | c;
+  ++idx;
+}
 
 template <int kVariant>
 __global__ void __launch_bounds__(kFaThreads, 1)
@@ -58,6 +71,8 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
   const uint32_t tmem_slot = b_pv_done + 16u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tr = ((p.dbg & 8) && blockIdx.x == 0 && lane == 0) ? 1 : 0;
+  unsigned int tri = 0;
 
   if (warp == 9 && lane == 0) {
     prefetch_tmap(&maps.QK);
@@ -157,6 +172,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         for (int g = 0; g < 2; ++g) {
           mbar_wait(b_p_ready + 8u * g, np & 1u, 2);     // P_g(j) is in shared memory, O_g rescaled, S_g read
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          fa_trace(tr, 2, j, g, 1, tri);
           if (elect_one()) {
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
@@ -176,6 +192,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
             }
             issue_s(g, nxt.slot);
           }
+          fa_trace(tr, 2, j, g, 3, tri);
         }
         if (elect_one()) {
           umma_commit(b_kv_empty + 8u * slot);
@@ -194,6 +211,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
     const uint32_t sPg = sP + (uint32_t)g * 32768u;
     const uint32_t p_row = sPg + (uint32_t)erow * 128u;
     uint32_t ns = 0;                                     // S tiles consumed so far by this warpgroup
+    if (g == 1) asm volatile("bar.arrive %0, 256;" ::"r"(2) : "memory");   // warpgroup 0 goes first
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, qp, len;
       decode(item, b, h, qp, len);
@@ -212,6 +230,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
       for (int j = 0; j < n_kv; ++j, ++ns) {
         mbar_wait(b_s_full + 8u * g, ns & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        fa_trace(tr && q == 0, g, j, 0, 1, tri);
         const int kmax = len - j * 128;                  // keys of this tile that exist (>= 1)
         // the whole S row (128 scores) into registers with ONE wait: a tcgen05.ld round trip is several hundred cycles and a
         // warpgroup has one warp per scheduler (chunk by chunk, twice over, the loads were most of the tile's time)
@@ -241,6 +260,13 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         const bool move = (j == 0) || __any_sync(0xffffffffu, m_cand - m > 8.0f);
         const float m_new = move ? m_cand : m;
         const float corr = move ? ex2_fast(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
+        // The exponentials of the two warpgroups take turns (named barriers 2 + g): a warpgroup has one warp per scheduler
+        // and that warp alone saturates the scheduler's MUFU unit, so two exp sections side by side just run at half
+        // speed IN PHASE — and then both wait for their MMAs together.  Alternating, one warpgroup's TMEM loads, maximum,
+        // P stores and MMAs run under the other's exponentials.
+        fa_trace(tr && q == 0, g, j, 0, 2, tri);
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+        fa_trace(tr && q == 0, g, j, 0, 3, tri);
         // P = 2^(s sc2 - m_new) -> bf16 -> shared memory (K block = 64 keys; 16-byte chunks XOR row & 7); masked keys: 2^-inf = 0
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
@@ -258,6 +284,8 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
                     ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
         }
         l = fmaf(l, corr, l0 + l1);
+        asm volatile("bar.arrive %0, 256;" ::"r"(3 - g) : "memory");      // the other warpgroup's turn
+        fa_trace(tr && q == 0, g, j, 0, 4, tri);
         if (j > 0 && move) {
           // the previous tile's P V has landed in O: rescale it to the new maximum (both halves in flight, one wait)
           mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
@@ -282,6 +310,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (elect_one()) mbar_arrive(b_p_ready + 8u * g);
+        fa_trace(tr && q == 0, g, j, 0, 5, tri);
       }
       // ---- output: O / l -> bf16 -> this warp's 32 x 64 box (staged in the warpgroup's P buffer) -> TMA store ----
       mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
@@ -332,5 +361,6 @@ const char* make_flow_attn_launch(FlowAttnLaunch* out, const void* qkv, const vo
                                   float scale, int max_ctas);
 cudaError_t launch_flow_attn_tc(const FlowAttnLaunch& L, const int* lengths, cudaStream_t st);
 cudaError_t flow_attn_init();
+int flow_attn_read_trace(unsigned long long* out, int cap);
 
 }  // namespace gnv

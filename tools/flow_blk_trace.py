@@ -1,4 +1,4 @@
-"""Timeline of CTA 0 of flow_blk_kernel: python tools/flow_blk_trace.py <mode 0 ff | 1 out | 2 qkv> [B] [T]"""
+"""Timeline of CTA 0 of flow_blk_kernel: python tools/flow_blk_trace.py <mode 0 ff | 1 out | 2 qkv | 3 attention> [B] [T]"""
 import ctypes as C
 import os
 import sys
@@ -32,7 +32,7 @@ for i in range(n.value):
     ev.append((w & 0xFFFFFFFF, ((w >> 56) & 0xFF) - 1, (w >> 48) & 0xFF, (w >> 40) & 0xFF, (w >> 32) & 0xFF))
 ev.sort()
 t0 = ev[0][0] if ev else 0
-names = {0: "COL", 1: "MMA", 2: "PRD", 3: "ROW"}
+names = {0: "COL", 1: "MMA", 2: "PRD", 3: "ROW"} if mode != "3" else {0: "SM0", 1: "SM1", 2: "MMA"}
 for c, role, a, b, e in ev[: int(os.environ.get("TRACE_LINES", "400"))]:
     print(f"{c - t0:9d} {names.get(role, role)} item{a} sub{b} ev{e}")
 print("events", n.value)
