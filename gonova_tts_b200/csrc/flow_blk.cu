@@ -20,6 +20,7 @@ cudaError_t flow_blk_init() {
   };
   if ((e = set(flow_blk_kernel<FB_FF>)) != cudaSuccess) return e;
   if ((e = set(flow_blk_kernel<FB_OUT>)) != cudaSuccess) return e;
+  if ((e = set(flow_blk_kernel<FB_CONV>)) != cudaSuccess) return e;
   return set(flow_blk_kernel<FB_WIDE>);
 }
 
@@ -57,7 +58,7 @@ const char* encode_2d(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int
 const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, int K, const void* w1, const float* b1,
                                  const void* w2, const float* b2, float* r, const float* gamma, const float* beta,
                                  int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas, void* vt, int vt_col0,
-                                 int vt_tp) {
+                                 int vt_tp, const float* r_in) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
   if (mode != FB_FF && mode != FB_OUT && mode != FB_WIDE) return "flow_blk: bad mode";
@@ -81,7 +82,8 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
     p.dbg = (dbg & 8) ? ((mode == dbg_mode ? 8 : 0) | (dbg & ~8)) : dbg;
   }
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta;
-  p.r = r; p.n_out = (__nv_bfloat16*)n_out; p.n_pitch = n_pitch;
+  p.r = r; p.r_in = r_in ? r_in : r; p.n_out = (__nv_bfloat16*)n_out; p.n_pitch = n_pitch;
+  if (r_in && ((uintptr_t)r_in & 15)) return "flow_blk: residual input must be 16-byte aligned";
   p.vt = mode == FB_WIDE ? (__nv_bfloat16*)vt : nullptr; p.vt_col0 = vt_col0; p.vt_tp = vt_tp;
   if (p.vt && (vt_col0 % 256 || vt_tp < T)) return "flow_blk: bad transposed-V geometry";
   if (mode != FB_WIDE && (!r || !n_out || ((uintptr_t)r & 31) || ((uintptr_t)n_out & 31) || n_pitch % 16))
@@ -137,14 +139,74 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
   return "";
 }
 
-cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st) {
+const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, const void* w, const float* bias,
+                                  const float* gamma, const float* beta, void* out_bf16, float* out_f32, int B2, int T,
+                                  int max_ctas) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
+  if (B2 <= 0 || T <= 0 || C_in <= 0 || C_in % 64) return "flow_conv: bad shape";
+  if (!a || !w || (!out_bf16 && !out_f32)) return "flow_conv: NULL tensor";
+  memset(&out->maps, 0, sizeof(out->maps));
+  memset(&out->p, 0, sizeof(out->p));
+  out->d_maps = nullptr;
+  out->mode = FB_CONV;
+  FlowBlkParams& p = out->p;
+  p.M = B2 * T; p.T = T;
+  p.conv_tpb = (T + 255) / 256;
+  p.tiles = B2 * p.conv_tpb;
+  p.conv_nch = C_in / 64;
+  p.kb_a = 3 * p.conv_nch;
+  p.n_tiles = 1; p.npu = 1; p.n_bias1 = 0; p.ln = 1;
+  p.b1 = nullptr; p.b2 = bias; p.gamma = gamma; p.beta = beta;
+  p.r = out_f32; p.r_in = out_f32; p.n_out = (__nv_bfloat16*)out_bf16; p.n_pitch = 256;
+  p.out_f32 = out_bf16 ? 0 : 1;
+  if (((uintptr_t)a & 15) || (out_bf16 && ((uintptr_t)out_bf16 & 15)) || (out_f32 && ((uintptr_t)out_f32 & 15)))
+    return "flow_conv: tensors must be 16-byte aligned";
+  const auto idesc = [&](uint32_t n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24); };
+  p.idesc128 = idesc(128);
+  p.idesc256 = idesc(256);
+  p.sw = 5;
+  p.off_x = 0;
+  p.off_h = 4 * kFbSlot;
+  p.off_w = p.off_h + 4 * kFbSlot;
+  p.off_sc = p.off_w + (uint32_t)p.sw * kFbSlot;
+  p.off_tab = p.off_sc;
+  p.off_bar = p.off_tab + (((uint32_t)kFbTab * 4u + 1023u) & ~1023u);
+  out->smem_bytes = (size_t)p.off_bar + 1024 + 1024;
+  if (out->smem_bytes > kFbMaxDynSmem) return "flow_conv: shared memory budget exceeded";
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C_in, (cuuint64_t)T, (cuuint64_t)B2};
+    cuuint64_t strides[2] = {(cuuint64_t)C_in * 2, (cuuint64_t)T * C_in * 2};
+    cuuint32_t box[3] = {64u, 128u, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&out->maps.A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "flow_conv: cuTensorMapEncodeTiled failed";
+  }
+  const char* e = encode_2d(enc, &out->maps.W2, w, 2, false, 3LL * C_in, 256, 3LL * C_in, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (*e) return e;
+  out->maps.W1 = out->maps.W2;
+  out->maps.Nout = out->maps.W2;
+  const int pairs = std::max(1, std::min(p.tiles, std::max(1, max_ctas / 2)));
+  out->grid = 2 * pairs;
+  return "";
+}
+
+cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias) {
   if (!L.d_maps) return cudaErrorInvalidValue;
   FlowBlkParams p = L.p;
   p.lengths = lengths;
+  if (L.mode == FB_CONV) {
+    p.b1 = tbias;                      // the kernel's b1 table holds the ResNet block's time bias (zeros when NULL)
+    p.n_bias1 = tbias ? 256 : 0;
+  }
   const FlowBlkMaps* dm = L.d_maps;
   switch (L.mode) {
     case FB_FF:  return launch_persistent(flow_blk_kernel<FB_FF>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
     case FB_OUT: return launch_persistent(flow_blk_kernel<FB_OUT>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
+    case FB_CONV: return launch_persistent(flow_blk_kernel<FB_CONV>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
     default:     return launch_persistent(flow_blk_kernel<FB_WIDE>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
   }
 }

@@ -9,6 +9,9 @@
 //             exists in HBM (it was written and read back: 131 MB per block), and there is one launch instead of three.
 //   FB_OUT  : R' = R + A W^T + b  (the attention output projection, K = 512 streamed), same epilogue
 //   FB_WIDE : Y = A W^T (+ b) as bf16, N in tiles of 256 (the fused q / k / v projection, N = 1536)
+//   FB_CONV : Y = Mish(LayerNorm(causal 3-tap conv(A) + b)) (+ time bias), the two convs of a ResNet block with the
+//             LayerNorm / Mish kernel that followed each folded into the epilogue; tiles per utterance (the taps are
+//             row-shifted TMA loads of a [C, T, 2B] map: rows before an utterance's first frame read as zero)
 //
 // The residual + LayerNorm epilogue (E2) runs on the same sixteen warps once a tile's last MMA has retired: a warp owns 32
 // rows x 64 columns, x = acc + b2 + R goes back into TMEM with the thread's mean / M2, the four warps of a lane quarter
@@ -25,7 +28,7 @@
 
 namespace gnv {
 
-enum { FB_FF = 0, FB_OUT = 1, FB_WIDE = 2 };
+enum { FB_FF = 0, FB_OUT = 1, FB_WIDE = 2, FB_CONV = 3 };
 constexpr int kFbSlot = 16384;     // one K block (64 bf16) of 128 rows: A tile of a CTA / weight ring slot
 constexpr int kFbMaxSw = 6;
 constexpr int kFbTab = 1536 + 3 * 256 + 16 * 32 * 2;     // floats: b1 | b2 | gamma | beta | LayerNorm exchange
@@ -40,7 +43,10 @@ struct FlowBlkParams {
   int dbg;                  // GONOVA_FB_DBG: 8 = record CTA 0's timeline (tools/flow_blk_trace.py)
   const int* lengths;       // [M / T] valid rows per utterance, or NULL
   const float *b1, *b2, *gamma, *beta;
-  float* r;                 // FF / OUT: the residual stream [M, 256] fp32, updated in place
+  float* r;                 // FF / OUT: the residual stream [M, 256] fp32 (output); CONV with out_f32: the fp32 output
+  const float* r_in;        // FF / OUT: the residual input (== r when updated in place)
+  int conv_nch, conv_tpb;   // CONV: K blocks per tap (C_in / 64), pair tiles per utterance
+  int out_f32;              // CONV: 1 = fp32 output rows at r, 0 = bf16 at n_out
   __nv_bfloat16* n_out;     // FF / OUT: bf16 output rows, pitch n_pitch elements
   int n_pitch;
   // WIDE: columns at or beyond vt_col0 (the V third of q | k | v) are written TRANSPOSED into vt [M / T * 8, 64, vt_tp]
@@ -139,6 +145,12 @@ __device__ __forceinline__ float gelu_poly(float x) {
   float h;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(g));
   return fmaf(-a, h, fmaxf(x, 0.f));
+}
+// Mish = x tanh(softplus x) = x n / (n + 2) with n = e^x (e^x + 2): one MUFU.EX2 and one MUFU.RCP; x > 20 returns x like torch
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = __expf(fminf(x, 20.f));
+  const float n = e * (e + 2.f);
+  return x > 20.f ? x : x * __fdividef(n, n + 2.f);
 }
 }  // namespace tc2
 
@@ -273,6 +285,26 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           fb_trace(tr, 2, t, c, 3, tri);
         }
       }
+    } else if constexpr (MODE == FB_CONV) {
+      for (int t = pair0; t < p.tiles; t += G) {
+        const int b = t / p.conv_tpb, t0 = (t - b * p.conv_tpb) * 256 + crank * 128;
+        for (int kb = 0; kb < p.kb_a; ++kb) {
+          const int tap = kb / p.conv_nch, ch = kb - tap * p.conv_nch;
+          mbar_wait(b_a_empty + 8u * ra.slot, ra.phase ^ 1u, 1);
+          if (elect_one()) {
+            if (crank == 0) mbar_expect_tx(b_a_full + 8u * ra.slot, 2u * kFbSlot);
+            // causal: tap j reads frame t - 2 + j; frames before 0 (and past T) arrive as zeros
+            tma_load_3d_2sm(&maps.A, (b_a_full + 8u * ra.slot) & kPeerBitMask, sX + ra.slot * kFbSlot, ch * 64, t0 - 2 + tap, b);
+          }
+          __syncwarp();
+          ra.advance(4);
+          const uint32_t sl = w_slot();
+          if (elect_one())
+            tma_load_2d_2sm(&maps.W2, (b_w_full + 8u * sl) & kPeerBitMask, sW + sl * kFbSlot, kb * 64, 128 * crank);
+          __syncwarp();
+          rw.advance(p.sw);
+        }
+      }
     } else if constexpr (MODE == FB_OUT) {
       for (int t = pair0; t < p.tiles; t += G) {
         const int row0 = t * 256 + crank * 128;
@@ -380,7 +412,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           if (elect_one()) umma_commit_2sm(b_acc2_full);
           __syncwarp();
         }
-      } else if constexpr (MODE == FB_OUT) {
+      } else if constexpr (MODE == FB_OUT || MODE == FB_CONV) {
         Ring ra;
         int it = 0;
         for (int t = pair0; t < p.tiles; t += G, ++it) {
@@ -484,7 +516,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       for (int i = 0; i < 4; ++i) {
         const int r = wrow0 + 8 * i + (lane >> 2);
         rok[i] = r < p.M;
-        rsrc[i] = p.r + (size_t)(rok[i] ? r : 0) * 256 + cb * 64 + (lane & 3) * 4;
+        rsrc[i] = p.r_in + (size_t)(rok[i] ? r : 0) * 256 + cb * 64 + (lane & 3) * 4;
       }
       __nv_bfloat16* ndst[2];
       bool nok[2];
@@ -517,6 +549,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
       uint32_t tv0[16], tv1[16];
       tmem_ld16_issue(acc, tv0);
+      const ptrdiff_t rdelta = p.r - p.r_in;               // R' goes to r (== r_in when the stream is updated in place)
       // (instruction count matters here: sixteen warps run this pass issue-bound.  Everything that moves by a constant per
       // step is a pointer bumped once per loop trip plus a compile-time offset, and the row-in-range predicates exist
       // only in the instantiation for a tensor's last, partial tile.)
@@ -556,7 +589,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 o = lds128(sc + co_off[i]);
-            if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + odd * 16) = o;
+            if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + rdelta + odd * 16) = o;
           }
           if (p.ln) {
             if (odd == 0 && more) shift = v[0];           // (first step: sums relative to a value of the row itself)
@@ -678,7 +711,115 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       fb_trace(tre, 3, t, 0, 6, tri);
     };
 
-    if constexpr (MODE == FB_FF) {
+    // ---- CONV epilogue: y = Mish(LayerNorm(acc + b)) (+ time bias) -> bf16 rows (the next conv's operand) or fp32 rows ----
+    auto e2_conv = [&](int b, int t0w, uint32_t acc_col, uint32_t full_bar, uint32_t full_par, uint32_t free_bar) {
+      const int nvalid = min(32, max(0, p.T - t0w));       // rows of this warp inside the utterance
+      bool live = lane < nvalid;
+      if (live && p.lengths) live = t0w + lane < p.lengths[b];
+      const size_t grow0 = (size_t)b * p.T + t0w;
+      const uint32_t acc = lane_base + acc_col + (uint32_t)(cb * 64);
+      mbar_wait(full_bar, full_par, 4);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      uint32_t tv0[16], tv1[16];
+      tmem_ld16_issue(acc, tv0);
+      auto c1 = [&](int st, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
+        tmem_ld_wait16(tcur);
+        if (st + 1 < 4) tmem_ld16_issue(acc + (uint32_t)((st + 1) * 16), tnext);
+        float v[16];
+        const float4* bt = reinterpret_cast<const float4*>(tb2 + cb * 64 + st * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = bt[j];
+          v[4 * j] = __uint_as_float(tcur[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(tcur[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(tcur[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(tcur[4 * j + 3]) + b4.w;
+        }
+        if (st == 0) shift = v[0];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float d = v[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
+        tmem_st16(acc + (uint32_t)(st * 16), v);
+      };
+#pragma unroll 1
+      for (int sp = 0; sp < 2; ++sp) { c1(2 * sp, tv0, tv1); c1(2 * sp + 1, tv1, tv0); }
+      tmem_wait_st();
+      const float m1 = s1 * (1.f / 64.f);
+      red[(warp * 32 + lane) * 2] = shift + m1;
+      red[(warp * 32 + lane) * 2 + 1] = fmaxf(s2 - s1 * m1, 0.f);
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+      float mean = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mean += red[((q + 4 * k) * 32 + lane) * 2];
+      mean *= 0.25f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d = red[((q + 4 * k) * 32 + lane) * 2] - mean;
+        m2 += red[((q + 4 * k) * 32 + lane) * 2 + 1] + 64.f * d * d;
+      }
+      const float rstd = rsqrtf(m2 * (1.f / 256.f) + 1e-5f);
+      const float nmr = -mean * rstd;
+      tmem_ld16_issue(acc, tv0);
+      auto c2 = [&](int st, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
+        const uint32_t sc = sc0 + (uint32_t)(st & 1) * 2048u;
+        tmem_ld_wait16(tcur);
+        if (st + 1 < 4) tmem_ld16_issue(acc + (uint32_t)((st + 1) * 16), tnext);
+        float v[16];
+        const int c0 = cb * 64 + st * 16;
+        const float4* g4 = reinterpret_cast<const float4*>(tg + c0);
+        const float4* b4p = reinterpret_cast<const float4*>(tbt + c0);
+        const float4* t4 = reinterpret_cast<const float4*>(tb1 + c0);     // the ResNet block's time bias (zeros when absent)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 gg = g4[j], bb = b4p[j], tt = t4[j];
+          v[4 * j] = mish_fast(fmaf(fmaf(__uint_as_float(tcur[4 * j]), rstd, nmr), gg.x, bb.x)) + tt.x;
+          v[4 * j + 1] = mish_fast(fmaf(fmaf(__uint_as_float(tcur[4 * j + 1]), rstd, nmr), gg.y, bb.y)) + tt.y;
+          v[4 * j + 2] = mish_fast(fmaf(fmaf(__uint_as_float(tcur[4 * j + 2]), rstd, nmr), gg.z, bb.z)) + tt.z;
+          v[4 * j + 3] = mish_fast(fmaf(fmaf(__uint_as_float(tcur[4 * j + 3]), rstd, nmr), gg.w, bb.w)) + tt.w;
+        }
+        if (!live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (p.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(sc + my_row + (((uint32_t)j ^ my_sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
+            const float4 o = lds128(sc + co_off[i]);
+            if (r < nvalid) *reinterpret_cast<float4*>(p.r + (grow0 + r) * 256 + c0 + (lane & 3) * 4) = o;
+          }
+        } else {
+          sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
+                  ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
+          sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
+                  ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = 16 * i + (lane >> 1);
+            const float4 o = lds128(sc + cbo[i]);
+            if (r < nvalid) *reinterpret_cast<float4*>(p.n_out + (grow0 + r) * p.n_pitch + c0 + (lane & 1) * 8) = o;
+          }
+        }
+      };
+#pragma unroll 1
+      for (int sp = 0; sp < 2; ++sp) { c2(2 * sp, tv0, tv1); c2(2 * sp + 1, tv1, tv0); }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");    // exchange words and scratch are free for the next tile
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (elect_one()) mbar_arrive_leader(free_bar);
+    };
+
+    if constexpr (MODE == FB_CONV) {
+      int it = 0;
+      for (int t = pair0; t < p.tiles; t += G, ++it) {
+        const uint32_t buf = (uint32_t)(it & 1);
+        const int b = t / p.conv_tpb, t0w = (t - b * p.conv_tpb) * 256 + crank * 128 + q * 32;
+        e2_conv(b, t0w, buf * 256u, b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), b_acc2_free + 8u * buf);
+      }
+    } else if constexpr (MODE == FB_FF) {
       // E1(c): gelu(acc1 + b1_c) -> bf16 -> H[c & 1] in the K-major SWIZZLE_128B operand layout; this warp: 32 of the 128 columns
       int it = 0;
       const uint32_t row_off = (uint32_t)(cb >> 1) * kFbSlot + (uint32_t)erow * 128u;
@@ -822,8 +963,13 @@ struct FlowBlkLaunch {
 const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, int K, const void* w1, const float* b1,
                                  const void* w2, const float* b2, float* r, const float* gamma, const float* beta,
                                  int ln, void* n_out, int n_pitch, int N, int M, int T, int max_ctas,
-                                 void* vt = nullptr, int vt_col0 = 0, int vt_tp = 0);
-cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st);
+                                 void* vt = nullptr, int vt_col0 = 0, int vt_tp = 0, const float* r_in = nullptr);
+// the two causal 3-tap convs of a ResNet block with LayerNorm + Mish (+ the block's time bias, given per launch):
+// a: [B2, T, C_in] bf16, w: packed [256, 3 * C_in] bf16 (tap-major K); output bf16 [B2 * T, 256] or fp32 [B2 * T, 256]
+const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, const void* w, const float* bias,
+                                  const float* gamma, const float* beta, void* out_bf16, float* out_f32, int B2, int T,
+                                  int max_ctas);
+cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias = nullptr);
 cudaError_t flow_blk_init();
 int flow_blk_read_trace(unsigned long long* out, int cap);   // tuning: CTA 0's timeline of the last traced launch
 
