@@ -21,6 +21,7 @@ cudaError_t flow_blk_init() {
   if ((e = set(flow_blk_kernel<FB_FF>)) != cudaSuccess) return e;
   if ((e = set(flow_blk_kernel<FB_OUT>)) != cudaSuccess) return e;
   if ((e = set(flow_blk_kernel<FB_CONV>)) != cudaSuccess) return e;
+  if ((e = set(flow_blk_kernel<FB_OUTFF>)) != cudaSuccess) return e;
   return set(flow_blk_kernel<FB_WIDE>);
 }
 
@@ -79,7 +80,7 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
   {
     static const int dbg = [] { const char* v = getenv("GONOVA_FB_DBG"); return v ? atoi(v) : 0; }();
     static const int dbg_mode = [] { const char* v = getenv("GONOVA_FB_TRACE_MODE"); return v ? atoi(v) : 0; }();
-    p.dbg = (dbg & 8) ? ((mode == dbg_mode ? 8 : 0) | (dbg & ~8)) : dbg;
+    p.dbg = (dbg & 8) ? ((mode == dbg_mode ? 8 : 0) | (dbg & ~8)) : dbg;   // (FB_OUTFF is built as FB_FF: trace mode 0)
   }
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta;
   p.r = r; p.r_in = r_in ? r_in : r; p.n_out = (__nv_bfloat16*)n_out; p.n_pitch = n_pitch;
@@ -194,6 +195,27 @@ const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, c
   return "";
 }
 
+const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
+                                   const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
+                                   const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
+                                   int max_ctas) {
+  // the feed-forward's launch, then the out-projection's operands on top of it
+  const char* e = make_flow_blk_launch(out, FB_FF, o, 256, w1, b1, w2, b2, r, gamma, beta, ln, n_out, n_pitch, 256, M, T, max_ctas,
+                                       nullptr, 0, 0, nullptr);
+  if (*e) return e;
+  if (K <= 0 || K % 64 || !w3) return "flow_outff: bad out-projection";
+  PFN_encodeTiled enc = get_encode_tiled();
+  out->mode = FB_OUTFF;
+  FlowBlkParams& p = out->p;
+  p.kb_a = K / 64;
+  p.b3 = b3; p.g3 = g3; p.be3 = be3;
+  e = encode_2d(enc, &out->maps.A, o, 2, false, K, M, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (*e) return e;
+  e = encode_2d(enc, &out->maps.W3, w3, 2, false, K, 256, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (*e) return e;
+  return "";
+}
+
 cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias) {
   if (!L.d_maps) return cudaErrorInvalidValue;
   FlowBlkParams p = L.p;
@@ -207,6 +229,7 @@ cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStre
     case FB_FF:  return launch_persistent(flow_blk_kernel<FB_FF>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
     case FB_OUT: return launch_persistent(flow_blk_kernel<FB_OUT>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
     case FB_CONV: return launch_persistent(flow_blk_kernel<FB_CONV>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
+    case FB_OUTFF: return launch_persistent(flow_blk_kernel<FB_OUTFF>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
     default:     return launch_persistent(flow_blk_kernel<FB_WIDE>, L.grid, L.smem_bytes, st, true, kFbThreads, dm, p);
   }
 }

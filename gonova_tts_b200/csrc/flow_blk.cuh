@@ -9,6 +9,9 @@
 //             exists in HBM (it was written and read back: 131 MB per block), and there is one launch instead of three.
 //   FB_OUT  : R' = R + A W^T + b  (the attention output projection, K = 512 streamed), same epilogue
 //   FB_WIDE : Y = A W^T (+ b) as bf16, N in tiles of 256 (the fused q / k / v projection, N = 1536)
+//   FB_OUTFF: FB_OUT and FB_FF of one transformer block chained in ONE launch: the out-projection's rows (x = R + O W^T + b)
+//             stay in TMEM as the accumulator the feed-forward adds onto, LayerNorm(x) goes straight into shared memory
+//             as the feed-forward's A operand; R is read once and written once per block, N never touches HBM between them
 //   FB_CONV : Y = Mish(LayerNorm(causal 3-tap conv(A) + b)) (+ time bias), the two convs of a ResNet block with the
 //             LayerNorm / Mish kernel that followed each folded into the epilogue; tiles per utterance (the taps are
 //             row-shifted TMA loads of a [C, T, 2B] map: rows before an utterance's first frame read as zero)
@@ -28,10 +31,10 @@
 
 namespace gnv {
 
-enum { FB_FF = 0, FB_OUT = 1, FB_WIDE = 2, FB_CONV = 3 };
+enum { FB_FF = 0, FB_OUT = 1, FB_WIDE = 2, FB_CONV = 3, FB_OUTFF = 4 };
 constexpr int kFbSlot = 16384;     // one K block (64 bf16) of 128 rows: A tile of a CTA / weight ring slot
 constexpr int kFbMaxSw = 6;
-constexpr int kFbTab = 1536 + 3 * 256 + 16 * 32 * 2;     // floats: b1 | b2 | gamma | beta | LayerNorm exchange
+constexpr int kFbTab = 1536 + 3 * 256 + 16 * 32 * 2 + 256;     // floats: b1 (| b3 | g3) | b2 | gamma | beta | LayerNorm exchange | be3
 
 struct FlowBlkParams {
   int M, T, tiles;          // rows, rows per utterance, pair tiles of 256 rows
@@ -43,6 +46,7 @@ struct FlowBlkParams {
   int dbg;                  // GONOVA_FB_DBG: 8 = record CTA 0's timeline (tools/flow_blk_trace.py)
   const int* lengths;       // [M / T] valid rows per utterance, or NULL
   const float *b1, *b2, *gamma, *beta;
+  const float *b3, *g3, *be3;   // OUTFF: the out-projection's bias and the LayerNorm between it and the feed-forward
   float* r;                 // FF / OUT: the residual stream [M, 256] fp32 (output); CONV with out_f32: the fp32 output
   const float* r_in;        // FF / OUT: the residual input (== r when updated in place)
   int conv_nch, conv_tpb;   // CONV: K blocks per tap (C_in / 64), pair tiles per utterance
@@ -57,7 +61,7 @@ struct FlowBlkParams {
   uint32_t off_x, off_h, off_w, off_sc, off_tab, off_bar;   // off_sc: the row warps' scratch (4 x 4 KB)
 };
 
-struct FlowBlkMaps { CUtensorMap A, W1, W2, Nout; };
+struct FlowBlkMaps { CUtensorMap A, W1, W2, Nout, W3; };
 
 constexpr int kFbThreads = 640;
 // warps 0..15 epilogue warps (TMEM lane quarter w % 4, column block w / 4): the GELU epilogue of FF, the residual +
@@ -188,7 +192,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
   const uint32_t b_acc1_full = b_w_empty + 8u * kFbMaxSw;
   const uint32_t b_e1_done = b_acc1_full + 16u, b_h_empty = b_e1_done + 16u;
   const uint32_t b_acc2_full = b_h_empty + 16u, b_acc2_free = b_acc2_full + 16u;
-  const uint32_t tmem_slot = b_acc2_free + 16u;
+  const uint32_t b_x_ready = b_acc2_free + 16u, b_x_free = b_x_ready + 8u;   // OUTFF
+  const uint32_t tmem_slot = b_x_free + 8u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,6 +208,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
     prefetch_tmap(&maps.A);
     prefetch_tmap(&maps.W1);
     prefetch_tmap(&maps.W2);
+    if constexpr (MODE == FB_OUTFF) prefetch_tmap(&maps.W3);
   }
   if (warp == kFbWarpInit && lane == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(b_a_full + 8u * s, 1); mbar_init(b_a_empty + 8u * s, 1); }
@@ -214,17 +220,24 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       mbar_init(b_acc2_full + 8u * s, 1);
       mbar_init(b_acc2_free + 8u * s, 32);
     }
+    mbar_init(b_x_ready, 32);
+    mbar_init(b_x_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kFbWarpTmem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  for (int c = threadIdx.x; c < 1536; c += blockDim.x) tb1[c] = (p.b1 && c < p.n_bias1) ? p.b1[c] : 0.f;
+  for (int c = threadIdx.x; c < (MODE == FB_OUTFF ? 1024 : 1536); c += blockDim.x) tb1[c] = (p.b1 && c < p.n_bias1) ? p.b1[c] : 0.f;
   for (int c = threadIdx.x; c < 256; c += blockDim.x) {
     tb2[c] = p.b2 ? p.b2[c] : 0.f;
     tg[c] = p.gamma ? p.gamma[c] : 1.f;
     tbt[c] = p.beta ? p.beta[c] : 0.f;
+    if constexpr (MODE == FB_OUTFF) {
+      tb1[1024 + c] = p.b3 ? p.b3[c] : 0.f;
+      tb1[1280 + c] = p.g3 ? p.g3[c] : 1.f;
+      tab[1536 + 768 + 1024 + c] = p.be3 ? p.be3[c] : 0.f;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -251,7 +264,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       __syncwarp();
       return (uint32_t)rw.slot;
     };
-    if constexpr (MODE == FB_FF) {
+    if constexpr (MODE == FB_FF || MODE == FB_OUTFF) {
       auto load_w1 = [&](int c) {                       // W1 rows [128 c, 128 c + 128): this CTA's 64, K blocks 2 s, 2 s + 1
         for (int s = 0; s < 2; ++s) {
           const uint32_t sl = w_slot();
@@ -273,10 +286,25 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           rw.advance(p.sw);
         }
       };
-      for (int t = pair0; t < p.tiles; t += G) {
+      int itp = 0;
+      for (int t = pair0; t < p.tiles; t += G, ++itp) {
         const int row0 = t * 256 + crank * 128;
         fb_trace(tr, 2, t, 0, 0, tri);
-        for (int kb = 0; kb < 4; ++kb) load_a(kb, row0);
+        if constexpr (MODE == FB_OUTFF) {
+          // the x region is the out-projection's A ring now and the feed-forward's operand afterwards: the next tile's
+          // attention-output blocks may land only when this CTA's last G1 of the previous tile has read it
+          if (itp > 0) mbar_wait(b_x_free, (uint32_t)((itp - 1) & 1), 1);
+          for (int kb = 0; kb < p.kb_a; ++kb) {
+            load_a(kb, row0);
+            const uint32_t sl = w_slot();
+            if (elect_one())
+              tma_load_2d_2sm(&maps.W3, (b_w_full + 8u * sl) & kPeerBitMask, sW + sl * kFbSlot, kb * 64, 128 * crank);
+            __syncwarp();
+            rw.advance(p.sw);
+          }
+        } else {
+          for (int kb = 0; kb < 4; ++kb) load_a(kb, row0);
+        }
         load_w1(0);
         load_w1(1);
         for (int c = 0; c < 8; ++c) {
@@ -341,8 +369,9 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       const uint64_t x_desc0 = umma_desc_sw128(sX), w_desc0 = umma_desc_sw128(sW), h_desc0 = umma_desc_sw128(sH);
       constexpr uint64_t kSlotUnits = kFbSlot >> 4;
       Ring rw;
-      if constexpr (MODE == FB_FF) {
+      if constexpr (MODE == FB_FF || MODE == FB_OUTFF) {
         int it = 0;
+        Ring ra;
         for (int t = pair0; t < p.tiles; t += G, ++it) {
           auto g1 = [&](int c, bool first) {
             const uint32_t acc = tmem_base + (uint32_t)(((it * 8 + c) & 1) * 128);
@@ -380,7 +409,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
                 const uint64_t ad = h_desc0 + (uint64_t)(buf * 2 + s) * kSlotUnits;
                 const uint64_t bd = w_desc0 + (uint64_t)rw.slot * kSlotUnits;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc256, (c | s | kk) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_2sm<E>(acc, ad + 2u * kk, bd + 2u * kk, p.idesc256, (MODE == FB_OUTFF || (c | s | kk)) ? 1u : 0u);
                 umma_commit_2sm(b_w_empty + 8u * rw.slot);
               }
               __syncwarp();
@@ -390,12 +420,36 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             __syncwarp();
           };
           fb_trace(tr, 1, t, 0, 0, tri);
-          g1(0, true);
+          if constexpr (MODE == FB_OUTFF) {
+            // ---- the out-projection: acc2 = O W3^T (K streamed through the x ring) ----
+            mbar_wait(b_acc2_free, (uint32_t)(it & 1) ^ 1u, 2);                     // the previous tile's rows have left acc2
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < p.kb_a; ++kb) {
+              mbar_wait(b_a_full + 8u * ra.slot, ra.phase, 2);
+              mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              if (elect_one()) {
+                const uint64_t ad = x_desc0 + (uint64_t)ra.slot * kSlotUnits, bd = w_desc0 + (uint64_t)rw.slot * kSlotUnits;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_2sm<E>(tmem_base + 256u, ad + 2u * kk, bd + 2u * kk, p.idesc256, (kb | kk) ? 1u : 0u);
+                umma_commit_2sm(b_a_empty + 8u * ra.slot);
+                umma_commit_2sm(b_w_empty + 8u * rw.slot);
+              }
+              __syncwarp();
+              ra.advance(4);
+              rw.advance(p.sw);
+            }
+            if (elect_one()) umma_commit_2sm(b_acc2_full);                          // (phase 0 of the tile: the projection is done)
+            __syncwarp();
+            mbar_wait(b_x_ready, (uint32_t)(it & 1), 2);                            // x is back in acc2, LayerNorm(x) in the x region
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          g1(0, MODE == FB_FF);
           g1(1, false);
           for (int c = 0; c < 8; ++c) {
             const int nn = it * 8 + c;
             mbar_wait(b_e1_done + 8u * (nn & 1), (uint32_t)((nn >> 1) & 1), 2);     // H[nn & 1] valid, acc1[nn & 1] free
-            if (c == 0) mbar_wait(b_acc2_free, (uint32_t)(it & 1) ^ 1u, 2);         // the previous tile's rows have left acc2
+            if (MODE == FB_FF && c == 0) mbar_wait(b_acc2_free, (uint32_t)(it & 1) ^ 1u, 2);   // the previous tile's rows have left acc2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             fb_trace(tr, 1, t, c, 3, tri);
             g2(c);
@@ -404,7 +458,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             fb_trace(tr, 1, t, c, 5, tri);
             if (c + 2 == 7) {                                                       // the tile's last read of x
               if (elect_one()) {
-                for (int s = 0; s < 4; ++s) umma_commit_2sm(b_a_empty + 8u * s);
+                if constexpr (MODE == FB_OUTFF) umma_commit_2sm(b_x_free);
+                else for (int s = 0; s < 4; ++s) umma_commit_2sm(b_a_empty + 8u * s);
               }
               __syncwarp();
             }
@@ -504,7 +559,11 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       cbo[i] = r * 64u + ((pc ^ ((r >> 1) & 3u)) << 4);
     }
     float* red = tab + 1536 + 768;                      // [16 warps][32 lanes][2]: mean, M2 of a thread's 64 columns
-    auto e2_tile = [&](int t, uint32_t acc_col, uint32_t full_bar, uint32_t full_par, uint32_t free_bar) {
+    // resin: x includes the residual rows (cp.async through the scratch); store_r: x is written to r (R'); to_x: the bf16
+    // output goes into the x region in the operand layout (OUTFF's first epilogue) instead of global memory; do_ln:
+    // LayerNorm with (gtab, betab) or the plain cast; btab: the GEMM's bias; free_bar = 0: no arrival (OUTFF's first epilogue)
+    auto e2_tile = [&](int t, uint32_t acc_col, uint32_t full_bar, uint32_t full_par, uint32_t free_bar, bool resin, bool store_r,
+                       bool to_x, bool do_ln, bool early_loads, const float* btab, const float* gtab, const float* betab) {
       const int wrow0 = t * 256 + crank * 128 + q * 32;   // first row of this warp
       const int row = wrow0 + lane;
       bool live = row < p.M;
@@ -535,14 +594,14 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      if constexpr (MODE == FB_OUT) {                     // (OUT: the H region is never an operand: the R segments load under the MMAs)
+      if (resin && early_loads) {                          // (the H region is idle: the R segments load under the MMAs)
         issue_load(0);
         issue_load(1);
       }
       mbar_wait(full_bar, full_par, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       fb_trace(tre, 3, t, 0, 4, tri);
-      if constexpr (MODE == FB_FF) {
+      if (resin && !early_loads) {
         issue_load(0);
         issue_load(1);
       }
@@ -558,13 +617,15 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         constexpr bool FULL = decltype(FULLC)::value;
         const float* rp[4] = {rsrc[0], rsrc[1], rsrc[2], rsrc[3]};
         __nv_bfloat16* np[2] = {ndst[0], ndst[1]};
-        const float* btp = tb2 + cb * 64;
+        const float* btp = btab + cb * 64;
         uint32_t accp = acc;
         auto step1 = [&](auto ODD, bool more, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
           constexpr int odd = decltype(ODD)::value;
           const uint32_t sc = sc0 + (uint32_t)odd * 2048u;
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-          __syncwarp();
+          if (resin) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+          }
           tmem_ld_wait16(tcur);
           if (odd == 0 || more) tmem_ld16_issue(accp + (uint32_t)(odd * 16 + 16), tnext);
           float v[16];
@@ -572,7 +633,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b4 = bt[j];
-            const float4 r4 = lds128(sc + my_row + (((uint32_t)j ^ my_sw) << 4));
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (resin) r4 = lds128(sc + my_row + (((uint32_t)j ^ my_sw) << 4));
             v[4 * j] = __uint_as_float(tcur[4 * j]) + b4.x + r4.x;
             v[4 * j + 1] = __uint_as_float(tcur[4 * j + 1]) + b4.y + r4.y;
             v[4 * j + 2] = __uint_as_float(tcur[4 * j + 2]) + b4.z + r4.z;
@@ -582,16 +644,18 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
+          if (store_r) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128(sc + my_row + (((uint32_t)j ^ my_sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          __syncwarp();
+            for (int j = 0; j < 4; ++j)
+              sts128(sc + my_row + (((uint32_t)j ^ my_sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 o = lds128(sc + co_off[i]);
-            if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + rdelta + odd * 16) = o;
+            for (int i = 0; i < 4; ++i) {
+              const float4 o = lds128(sc + co_off[i]);
+              if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + rdelta + odd * 16) = o;
+            }
           }
-          if (p.ln) {
+          if (do_ln) {
             if (odd == 0 && more) shift = v[0];           // (first step: sums relative to a value of the row itself)
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const float d = v[j] - shift; s1 += d; s2 = fmaf(d, d, s2); }
@@ -610,14 +674,16 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             }
           }
           __syncwarp();                                   // this scratch buffer is free again
-          if (more) {                                     // the segment two steps on, into the buffer just freed
+          if (resin) {
+            if (more) {                                   // the segment two steps on, into the buffer just freed
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int nb = (FULL || rok[i]) ? 16 : 0;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sc + co_off[i]), "l"(rp[i] + odd * 16 + 32), "r"(nb) : "memory");
+              for (int i = 0; i < 4; ++i) {
+                const int nb = (FULL || rok[i]) ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sc + co_off[i]), "l"(rp[i] + odd * 16 + 32), "r"(nb) : "memory");
+              }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty: keeps the wait count uniform)
           }
-          asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty: keeps the wait count uniform)
         };
 #pragma unroll 1
         for (int sp = 0; sp < 2; ++sp) {
@@ -633,7 +699,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       };
       if (full) pass1(std::true_type{}); else pass1(std::false_type{});
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      if (p.ln) {
+      if (do_ln) {
         tmem_wait_st();
         // this thread: 64 columns -> (mean, M2); the row's other three quarters sit in warps q + 4 k
         const float m1 = s1 * (1.f / 64.f);
@@ -656,9 +722,11 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         auto pass2 = [&](auto FULLC) {
           constexpr bool FULL = decltype(FULLC)::value;
           __nv_bfloat16* np[2] = {ndst[0], ndst[1]};
-          const float* gp = tg + cb * 64;
-          const float* bp = tbt + cb * 64;
+          const float* gp = gtab + cb * 64;
+          const float* bp = betab + cb * 64;
           uint32_t accp = acc;
+          uint32_t xrow = sX + (uint32_t)cb * kFbSlot + (uint32_t)erow * 128u;   // to_x: this row of K block cb of the x operand
+          uint32_t xch = 0;                                                      // 16-byte chunk of the step inside the row
           auto step2 = [&](auto ODD, bool more, uint32_t (&tcur)[16], uint32_t (&tnext)[16]) {
             constexpr int odd = decltype(ODD)::value;
             const uint32_t sc = sc0 + (uint32_t)odd * 2048u;
@@ -679,17 +747,25 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
-            sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
-                    ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
-            sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
-                    ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
-            __syncwarp();
+            if (to_x) {
+              const uint32_t c0 = xch + (uint32_t)odd * 2u;
+              sts128u(xrow + ((c0 ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
+                      ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
+              sts128u(xrow + (((c0 + 1u) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
+                      ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
+            } else {
+              sts128u(sc + my_row + ((0u ^ my_sw) << 4), ElemIO<E>::pack2(v[0], v[1]), ElemIO<E>::pack2(v[2], v[3]),
+                      ElemIO<E>::pack2(v[4], v[5]), ElemIO<E>::pack2(v[6], v[7]));
+              sts128u(sc + my_row + ((1u ^ my_sw) << 4), ElemIO<E>::pack2(v[8], v[9]), ElemIO<E>::pack2(v[10], v[11]),
+                      ElemIO<E>::pack2(v[12], v[13]), ElemIO<E>::pack2(v[14], v[15]));
+              __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float4 o = lds128(sc + cbo[i]);
-              if (FULL || nok[i]) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
+              for (int i = 0; i < 2; ++i) {
+                const float4 o = lds128(sc + cbo[i]);
+                if (FULL || nok[i]) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
+              }
+              // (the next step writes the OTHER scratch buffer; this one is rewritten two steps on, after two more __syncwarp)
             }
-            // (the next step writes the OTHER scratch buffer; this one is rewritten two steps on, after two more __syncwarp)
           };
 #pragma unroll 1
           for (int sp = 0; sp < 2; ++sp) {
@@ -699,12 +775,14 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             np[0] += 32; np[1] += 32;
             gp += 32; bp += 32;
             accp += 32u;
+            xch += 4u;
           }
         };
         if (full) pass2(std::true_type{}); else pass2(std::false_type{});
         // the next tile rewrites the exchange words and the scratch: every warp of the quarter is done reading both
         asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
       }
+      if (to_x) fence_async_smem();                        // the x operand was written through the generic proxy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (elect_one()) mbar_arrive_leader(free_bar);
@@ -819,11 +897,17 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         const int b = t / p.conv_tpb, t0w = (t - b * p.conv_tpb) * 256 + crank * 128 + q * 32;
         e2_conv(b, t0w, buf * 256u, b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), b_acc2_free + 8u * buf);
       }
-    } else if constexpr (MODE == FB_FF) {
+    } else if constexpr (MODE == FB_FF || MODE == FB_OUTFF) {
       // E1(c): gelu(acc1 + b1_c) -> bf16 -> H[c & 1] in the K-major SWIZZLE_128B operand layout; this warp: 32 of the 128 columns
       int it = 0;
       const uint32_t row_off = (uint32_t)(cb >> 1) * kFbSlot + (uint32_t)erow * 128u;
       for (int t = pair0; t < p.tiles; t += G, ++it) {
+        if constexpr (MODE == FB_OUTFF) {
+          // the out-projection's epilogue: x = acc + b3 + R stays in TMEM (the feed-forward accumulates onto it),
+          // LayerNorm(x) becomes the feed-forward's A operand in the x region; nothing goes to global memory
+          e2_tile(t, 256u, b_acc2_full, 0u, b_x_ready, true, false, true, true, true, tb1 + 1024, tb1 + 1280,
+                  tab + 1536 + 768 + 1024);
+        }
         for (int c = 0; c < 8; ++c) {
           const int nn = it * 8 + c;
           const uint32_t buf = (uint32_t)(nn & 1);
@@ -855,7 +939,10 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           fb_trace(tre, 0, t, c, 3, tri);
         }
         // the tile's rows are complete once the last G2 has retired (which also frees the H region for the scratch)
-        e2_tile(t, 256u, b_acc2_full, (uint32_t)(it & 1), b_acc2_free);
+        if constexpr (MODE == FB_OUTFF)
+          e2_tile(t, 256u, b_acc2_full, 1u, b_acc2_free, false, true, false, p.ln != 0, false, tb2, tg, tbt);
+        else
+          e2_tile(t, 256u, b_acc2_full, (uint32_t)(it & 1), b_acc2_free, true, true, false, p.ln != 0, false, tb2, tg, tbt);
         // every warp's generic-proxy writes to the H region are done before the next tile's E1 hands it to the tensor core
         asm volatile("bar.sync 1, 512;" ::: "memory");
       }
@@ -863,7 +950,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       int it = 0;
       for (int t = pair0; t < p.tiles; t += G, ++it) {
         const uint32_t buf = (uint32_t)(it & 1);
-        e2_tile(t, buf * 256u, b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), b_acc2_free + 8u * buf);
+        e2_tile(t, buf * 256u, b_acc2_full + 8u * buf, (uint32_t)((it >> 1) & 1), b_acc2_free + 8u * buf, true, true, false,
+                p.ln != 0, true, tb2, tg, tbt);
       }
     } else {
       // plain output: this warp's 32 rows x 64 columns of every 256-column tile, staged and stored by TMA
@@ -969,6 +1057,11 @@ const char* make_flow_blk_launch(FlowBlkLaunch* out, int mode, const void* a, in
 const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, const void* w, const float* bias,
                                   const float* gamma, const float* beta, void* out_bf16, float* out_f32, int B2, int T,
                                   int max_ctas);
+// FB_OUTFF: o [M, K] bf16 (attention output), w3 [256, K] + b3 and LayerNorm (g3, be3), then the feed-forward as in FB_FF
+const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
+                                   const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
+                                   const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
+                                   int max_ctas);
 cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias = nullptr);
 cudaError_t flow_blk_init();
 int flow_blk_read_trace(unsigned long long* out, int cap);   // tuning: CTA 0's timeline of the last traced launch
