@@ -198,7 +198,7 @@ const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, c
 const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
                                    const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
                                    const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
-                                   int max_ctas) {
+                                   int max_ctas, const void* w4, void* qkv_out, void* vt, int vt_tp) {
   // the feed-forward's launch, then the out-projection's operands on top of it
   const char* e = make_flow_blk_launch(out, FB_FF, o, 256, w1, b1, w2, b2, r, gamma, beta, ln, n_out, n_pitch, 256, M, T, max_ctas,
                                        nullptr, 0, 0, nullptr);
@@ -213,6 +213,18 @@ const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, con
   if (*e) return e;
   e = encode_2d(enc, &out->maps.W3, w3, 2, false, K, 256, K, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (*e) return e;
+  if (w4) {
+    if (!ln || !qkv_out || !vt || vt_tp < T) return "flow_outff: the q/k/v tail needs the LayerNorm and its outputs";
+    p.qkv = 1;
+    p.vt = (__nv_bfloat16*)vt; p.vt_col0 = 1024; p.vt_tp = vt_tp;
+    e = encode_2d(enc, &out->maps.W4, w4, 2, false, 256, 1536, 256, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (*e) return e;
+    e = encode_2d(enc, &out->maps.Nout, qkv_out, 2, false, 1536, M, 1536, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (*e) return e;
+  } else {
+    out->maps.W4 = out->maps.W3;
+  }
   return "";
 }
 

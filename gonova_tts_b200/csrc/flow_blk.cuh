@@ -47,6 +47,7 @@ struct FlowBlkParams {
   const int* lengths;       // [M / T] valid rows per utterance, or NULL
   const float *b1, *b2, *gamma, *beta;
   const float *b3, *g3, *be3;   // OUTFF: the out-projection's bias and the LayerNorm between it and the feed-forward
+  int qkv;                      // OUTFF: 1 = the NEXT block's q/k/v projection runs on the tile's LayerNorm output before it leaves
   float* r;                 // FF / OUT: the residual stream [M, 256] fp32 (output); CONV with out_f32: the fp32 output
   const float* r_in;        // FF / OUT: the residual input (== r when updated in place)
   int conv_nch, conv_tpb;   // CONV: K blocks per tap (C_in / 64), pair tiles per utterance
@@ -61,7 +62,7 @@ struct FlowBlkParams {
   uint32_t off_x, off_h, off_w, off_sc, off_tab, off_bar;   // off_sc: the row warps' scratch (4 x 4 KB)
 };
 
-struct FlowBlkMaps { CUtensorMap A, W1, W2, Nout, W3; };
+struct FlowBlkMaps { CUtensorMap A, W1, W2, Nout, W3, W4; };
 
 constexpr int kFbThreads = 640;
 // warps 0..15 epilogue warps (TMEM lane quarter w % 4, column block w / 4): the GELU epilogue of FF, the residual +
@@ -193,7 +194,8 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
   const uint32_t b_e1_done = b_acc1_full + 16u, b_h_empty = b_e1_done + 16u;
   const uint32_t b_acc2_full = b_h_empty + 16u, b_acc2_free = b_acc2_full + 16u;
   const uint32_t b_x_ready = b_acc2_free + 16u, b_x_free = b_x_ready + 8u;   // OUTFF
-  const uint32_t tmem_slot = b_x_free + 8u;
+  const uint32_t b_q_full = b_x_free + 8u, b_q_free = b_q_full + 16u;          // OUTFF with the q/k/v tail: two 256-column buffers
+  const uint32_t tmem_slot = b_q_free + 16u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,7 +210,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
     prefetch_tmap(&maps.A);
     prefetch_tmap(&maps.W1);
     prefetch_tmap(&maps.W2);
-    if constexpr (MODE == FB_OUTFF) prefetch_tmap(&maps.W3);
+    if constexpr (MODE == FB_OUTFF) { prefetch_tmap(&maps.W3); prefetch_tmap(&maps.W4); }
   }
   if (warp == kFbWarpInit && lane == 0) {
     for (int s = 0; s < 4; ++s) { mbar_init(b_a_full + 8u * s, 1); mbar_init(b_a_empty + 8u * s, 1); }
@@ -222,6 +224,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
     }
     mbar_init(b_x_ready, 32);
     mbar_init(b_x_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(b_q_full + 8u * s, 1); mbar_init(b_q_free + 8u * s, 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kFbWarpTmem) {
@@ -311,6 +314,18 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           load_w2(c);
           if (c + 2 < 8) load_w1(c + 2);
           fb_trace(tr, 2, t, c, 3, tri);
+        }
+        if constexpr (MODE == FB_OUTFF) {
+          if (p.qkv) {
+            for (int n = 0; n < 6; ++n)
+              for (int kb = 0; kb < 4; ++kb) {
+                const uint32_t sl = w_slot();
+                if (elect_one())
+                  tma_load_2d_2sm(&maps.W4, (b_w_full + 8u * sl) & kPeerBitMask, sW + sl * kFbSlot, kb * 64, n * 256 + 128 * crank);
+                __syncwarp();
+                rw.advance(p.sw);
+              }
+          }
         }
       }
     } else if constexpr (MODE == FB_CONV) {
@@ -441,7 +456,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             }
             if (elect_one()) umma_commit_2sm(b_acc2_full);                          // (phase 0 of the tile: the projection is done)
             __syncwarp();
-            mbar_wait(b_x_ready, (uint32_t)(it & 1), 2);                            // x is back in acc2, LayerNorm(x) in the x region
+            mbar_wait(b_x_ready, p.qkv ? 0u : (uint32_t)(it & 1), 2);               // x is back in acc2, LayerNorm(x) in the x region
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           g1(0, MODE == FB_FF);
@@ -458,7 +473,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             fb_trace(tr, 1, t, c, 5, tri);
             if (c + 2 == 7) {                                                       // the tile's last read of x
               if (elect_one()) {
-                if constexpr (MODE == FB_OUTFF) umma_commit_2sm(b_x_free);
+                if constexpr (MODE == FB_OUTFF) { if (!p.qkv) umma_commit_2sm(b_x_free); }
                 else for (int s = 0; s < 4; ++s) umma_commit_2sm(b_a_empty + 8u * s);
               }
               __syncwarp();
@@ -466,6 +481,36 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           }
           if (elect_one()) umma_commit_2sm(b_acc2_full);
           __syncwarp();
+          if constexpr (MODE == FB_OUTFF) {
+            if (p.qkv) {
+              // ---- the next block's q/k/v projection on the LayerNorm output the second epilogue left in the x region ----
+              mbar_wait(b_x_ready, 1u, 2);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              for (int n = 0; n < 6; ++n) {
+                const uint32_t buf = (uint32_t)(n & 1);
+                const uint32_t idx = (uint32_t)(3 * it + (n >> 1));
+                mbar_wait(b_q_free + 8u * buf, (idx & 1u) ^ 1u, 2);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < 4; ++kb) {
+                  mbar_wait(b_w_full + 8u * rw.slot, rw.phase, 2);
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                  if (elect_one()) {
+                    const uint64_t ad = x_desc0 + (uint64_t)kb * kSlotUnits, bd = w_desc0 + (uint64_t)rw.slot * kSlotUnits;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                      umma_2sm<E>(tmem_base + buf * 256u, ad + 2u * kk, bd + 2u * kk, p.idesc256, (kb | kk) ? 1u : 0u);
+                    umma_commit_2sm(b_w_empty + 8u * rw.slot);
+                  }
+                  __syncwarp();
+                  rw.advance(p.sw);
+                }
+                if (elect_one()) umma_commit_2sm(b_q_full + 8u * buf);
+                __syncwarp();
+              }
+              if (elect_one()) umma_commit_2sm(b_x_free);
+              __syncwarp();
+            }
+          }
         }
       } else if constexpr (MODE == FB_OUT || MODE == FB_CONV) {
         Ring ra;
@@ -789,6 +834,62 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
       fb_trace(tre, 3, t, 0, 6, tri);
     };
 
+    // one 256-column tile of a plain bf16 output (q | k | v): this warp's 32 rows x 64 columns, staged and stored by TMA; the
+    // V third leaves transposed (WIDE, and the q/k/v tail of OUTFF)
+    auto wide_item = [&](int n, uint32_t acc_col, int row0, int row, bool live) {
+      // both 32-column halves of this warp's block in flight behind one wait (a tcgen05.ld round trip is ~400 cycles)
+      uint32_t tw[2][32];
+      tmem_ld32_issue(lane_base + acc_col + (uint32_t)(cb * 64), tw[0]);
+      tmem_ld32_issue(lane_base + acc_col + (uint32_t)(cb * 64 + 32), tw[1]);
+      tmem_wait_ld();
+      tmem_ld_pin32(tw[0]);
+      tmem_ld_pin32(tw[1]);
+#pragma unroll
+      for (int i2 = 0; i2 < 2; ++i2) {
+        const int col = cb * 64 + i2 * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(tw[i2][j]);
+        if (MODE == FB_WIDE && p.n_bias1) {
+          const float4* bt = reinterpret_cast<const float4*>(tb1 + n * 256 + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bt[j];
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+        }
+        if (!live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (p.vt && n * 256 + col >= p.vt_col0) {
+          // a warp = 32 consecutive rows = (mostly) 32 consecutive keys of one utterance: one 64-byte run per channel
+          if (row < p.M) {
+            const int b = row / p.T, t = row - b * p.T;
+            const int c = n * 256 + col - p.vt_col0;              // channel of v[0] inside the V third: head c / 64
+            __nv_bfloat16* dst = p.vt + ((size_t)(b * 8 + (c >> 6)) * 64 + (c & 63)) * p.vt_tp + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(size_t)j * p.vt_tp] = __float2bfloat16_rn(v[j]);
+          }
+          continue;
+        }
+        const uint32_t sbuf = sH + (uint32_t)warp * 4096u + (uint32_t)i2 * 2048u;
+        if (elect_one()) bulk_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128u(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), ElemIO<E>::pack2(v[8 * j], v[8 * j + 1]),
+                  ElemIO<E>::pack2(v[8 * j + 2], v[8 * j + 3]), ElemIO<E>::pack2(v[8 * j + 4], v[8 * j + 5]),
+                  ElemIO<E>::pack2(v[8 * j + 6], v[8 * j + 7]));
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&maps.Nout, sbuf, n * 256 + col, row0 + q * 32);
+          bulk_commit();
+        }
+      }
+    };
+
     // ---- CONV epilogue: y = Mish(LayerNorm(acc + b)) (+ time bias) -> bf16 rows (the next conv's operand) or fp32 rows ----
     auto e2_conv = [&](int b, int t0w, uint32_t acc_col, uint32_t full_bar, uint32_t full_par, uint32_t free_bar) {
       const int nvalid = min(32, max(0, p.T - t0w));       // rows of this warp inside the utterance
@@ -940,9 +1041,31 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         }
         // the tile's rows are complete once the last G2 has retired (which also frees the H region for the scratch)
         if constexpr (MODE == FB_OUTFF)
-          e2_tile(t, 256u, b_acc2_full, 1u, b_acc2_free, false, true, false, p.ln != 0, false, tb2, tg, tbt);
+          e2_tile(t, 256u, b_acc2_full, 1u, p.qkv ? b_x_ready : b_acc2_free, false, true, p.qkv != 0, p.ln != 0, false, tb2, tg, tbt);
         else
           e2_tile(t, 256u, b_acc2_full, (uint32_t)(it & 1), b_acc2_free, true, true, false, p.ln != 0, false, tb2, tg, tbt);
+        if constexpr (MODE == FB_OUTFF) {
+          if (p.qkv) {
+            const int row0 = t * 256 + crank * 128;
+            const int row = row0 + erow;
+            bool live = row < p.M;
+            if (live && p.lengths) { const int b = row / p.T; live = row - b * p.T < p.lengths[b]; }
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // every warp is done with the E2 scratch: the H region stages the q/k/v stores
+            for (int n = 0; n < 6; ++n) {
+              const uint32_t buf = (uint32_t)(n & 1);
+              const uint32_t idx = (uint32_t)(3 * it + (n >> 1));
+              mbar_wait(b_q_full + 8u * buf, idx & 1u, 4);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              wide_item(n, buf * 256u, row0, row, live);
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (elect_one()) mbar_arrive_leader(b_q_free + 8u * buf);
+            }
+            if (elect_one()) bulk_wait_read<0>();            // the staged boxes have left the H region
+            __syncwarp();
+            if (elect_one()) mbar_arrive_leader(b_acc2_free);
+          }
+        }
         // every warp's generic-proxy writes to the H region are done before the next tile's E1 hands it to the tensor core
         asm volatile("bar.sync 1, 512;" ::: "memory");
       }
@@ -967,57 +1090,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           mbar_wait(b_acc2_full + 8u * buf, (uint32_t)((cnt >> 1) & 1), 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           fb_trace(tre, 0, u, n, 4, tri);
-          // both 32-column halves of this warp's block in flight behind one wait (a tcgen05.ld round trip is ~400 cycles)
-          uint32_t tw[2][32];
-          tmem_ld32_issue(lane_base + buf * 256u + (uint32_t)(cb * 64), tw[0]);
-          tmem_ld32_issue(lane_base + buf * 256u + (uint32_t)(cb * 64 + 32), tw[1]);
-          tmem_wait_ld();
-          tmem_ld_pin32(tw[0]);
-          tmem_ld_pin32(tw[1]);
-#pragma unroll
-          for (int i2 = 0; i2 < 2; ++i2) {
-            const int col = cb * 64 + i2 * 32;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(tw[i2][j]);
-            if (p.n_bias1) {
-              const float4* bt = reinterpret_cast<const float4*>(tb1 + n * 256 + col);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = bt[j];
-                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-              }
-            }
-            if (!live) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            }
-            if (p.vt && n * 256 + col >= p.vt_col0) {
-              // a warp = 32 consecutive rows = (mostly) 32 consecutive keys of one utterance: one 64-byte run per channel
-              if (row < p.M) {
-                const int b = row / p.T, t = row - b * p.T;
-                const int c = n * 256 + col - p.vt_col0;              // channel of v[0] inside the V third: head c / 64
-                __nv_bfloat16* dst = p.vt + ((size_t)(b * 8 + (c >> 6)) * 64 + (c & 63)) * p.vt_tp + t;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) dst[(size_t)j * p.vt_tp] = __float2bfloat16_rn(v[j]);
-              }
-              continue;
-            }
-            const uint32_t sbuf = sH + (uint32_t)warp * 4096u + (uint32_t)i2 * 2048u;
-            if (elect_one()) bulk_wait_read<1>();
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128u(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), ElemIO<E>::pack2(v[8 * j], v[8 * j + 1]),
-                      ElemIO<E>::pack2(v[8 * j + 2], v[8 * j + 3]), ElemIO<E>::pack2(v[8 * j + 4], v[8 * j + 5]),
-                      ElemIO<E>::pack2(v[8 * j + 6], v[8 * j + 7]));
-            fence_async_smem();
-            __syncwarp();
-            if (elect_one()) {
-              tma_store_2d(&maps.Nout, sbuf, n * 256 + col, row0 + q * 32);
-              bulk_commit();
-            }
-          }
+          wide_item(n, buf * 256u, row0, row, live);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (elect_one()) mbar_arrive_leader(b_acc2_free + 8u * buf);
@@ -1058,10 +1131,13 @@ const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, c
                                   const float* gamma, const float* beta, void* out_bf16, float* out_f32, int B2, int T,
                                   int max_ctas);
 // FB_OUTFF: o [M, K] bf16 (attention output), w3 [256, K] + b3 and LayerNorm (g3, be3), then the feed-forward as in FB_FF
+// w4 != NULL: the NEXT block's q/k/v projection [1536, 256] runs on the LayerNorm output (which then never leaves the SM):
+// qkv_out [M, 1536] bf16 (q | k), vt [M / T * 8, 64, vt_tp] (V transposed); n_out is not written in that case
 const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
                                    const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
                                    const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
-                                   int max_ctas);
+                                   int max_ctas, const void* w4 = nullptr, void* qkv_out = nullptr, void* vt = nullptr,
+                                   int vt_tp = 0);
 cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias = nullptr);
 cudaError_t flow_blk_init();
 int flow_blk_read_trace(unsigned long long* out, int cap);   // tuning: CTA 0's timeline of the last traced launch
