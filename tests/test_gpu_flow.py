@@ -146,10 +146,16 @@ def test_fused_blocks_equal_one_launch_per_projection(flows, cuda_device, tmp_pa
         "y = f.decode(z.to(d), mu.to(d), spks.to(d), cond.to(d), n_timesteps=3).cpu().numpy()\n"
         f"np.save({str(out)!r}, y)\n"
     )
-    env = dict(os.environ, GONOVA_FLOW_FUSED="0")
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    ref = np.load(out)
-    snr = snr_db(got, ref)
-    print(f"[parity] flow 3 steps bf16: fused blocks vs one launch per projection: max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
-    assert snr >= 38.0
+    # each switch takes one fusion away: everything / the chained out-projection + feed-forward / its q/k/v tail and the fused
+    # ResNet blocks / the tcgen05 attention (back to mma.sync)
+    for name, extra in (("one launch per projection", {"GONOVA_FLOW_FUSED": "0"}),
+                        ("out-proj and feed-forward as two launches", {"GONOVA_FLOW_OUTFF": "0"}),
+                        ("no q/k/v tail, ResNet convs unfused", {"GONOVA_FLOW_QKV_TAIL": "0", "GONOVA_FLOW_RESNET_FUSED": "0"}),
+                        ("mma.sync attention", {"GONOVA_FLOW_ATTN_TC": "0"})):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        ref = np.load(out)
+        snr = snr_db(got, ref)
+        print(f"[parity] flow 3 steps bf16: default against '{name}': max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
+        assert snr >= 38.0, name
