@@ -72,7 +72,7 @@ const char* make_flow_attn_launch(FlowAttnLaunch* out, const void* qkv, const vo
   p.off_kv = 2 * 32768;
   p.off_p = p.off_kv + kFaStages * 32768;
   p.off_bar = p.off_p + 2 * 32768;
-  out->smem_bytes = (size_t)p.off_bar + 1024 + 1024;
+  out->smem_bytes = (size_t)p.off_bar + 1024 + 2048 + 1024;      // barriers | row-maximum exchange | alignment slack
   if (out->smem_bytes > kFaMaxDynSmem) return "flow_attn: shared memory budget exceeded";
   const char* e = encode_3d(enc, &out->maps.QK, qkv, 1536, T, B2, 1536, (long long)T * 1536, 64, 128);
   if (*e) return e;

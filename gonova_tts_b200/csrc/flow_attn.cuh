@@ -11,14 +11,15 @@
 // barrier).  K comes straight from the fused q/k/v buffer [2B, T, 1536]; V is read from Vt [2B * 8, 64, Tp] — the q/k/v
 // GEMM's epilogue writes its V columns TRANSPOSED (keys contiguous), which makes V^T a plain K-major B operand.
 // Bound: one MUFU.EX2 per score (16 per clock per SM).  Replaces the mma.sync kernel (flow_kernels.cu) on the bf16 path.
-// Warp roles (352 threads): 0..3 softmax warpgroup 0, 4..7 warpgroup 1, 8 TMEM + barriers, 9 TMA producer, 10 MMA issuer.
+// Warp roles (608 threads): 0..7 softmax warpgroup 0, 8..15 warpgroup 1 (two warps per 32 query rows: one per key half),
+// 16 TMEM + barriers, 17 TMA producer, 18 MMA issuer.
 #pragma once
 #include "conv_tc2.cuh"
 
 namespace gnv {
 
-constexpr int kFaStages = 3;             // K / V ring depth (32 KB per stage)
-constexpr int kFaThreads = 352;
+constexpr int kFaStages = 2;             // K / V ring depth (32 KB per stage)
+constexpr int kFaThreads = 608;
 
 struct FlowAttnParams {
   int B2, T, nqp, items;                 // utterances, frames, 256-query groups per (b, h), work items
@@ -74,17 +75,17 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
   const int tr = ((p.dbg & 8) && blockIdx.x == 0 && lane == 0) ? 1 : 0;
   unsigned int tri = 0;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == 17 && lane == 0) {
     prefetch_tmap(&maps.QK);
     prefetch_tmap(&maps.Vt);
   }
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) { mbar_init(b_q_full + 8u * s, 1); mbar_init(b_q_empty + 8u * s, 1); }
       for (int s = 0; s < kFaStages; ++s) { mbar_init(b_kv_full + 8u * s, 1); mbar_init(b_kv_empty + 8u * s, 1); }
       for (int g = 0; g < 2; ++g) {
         mbar_init(b_s_full + 8u * g, 1);
-        mbar_init(b_p_ready + 8u * g, 4);
+        mbar_init(b_p_ready + 8u * g, 8);
         mbar_init(b_pv_done + 8u * g, 1);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -107,7 +108,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
     len = p.lengths ? min(p.T, max(0, p.lengths[b])) : p.T;
   };
 
-  if (warp == 9) {
+  if (warp == 17) {
     // ===== TMA producer =====
     Ring rkv;
     uint32_t nq = 0;
@@ -138,7 +139,7 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         rkv.advance(kFaStages);
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 18) {
     // ===== MMA issuer =====
     const uint64_t q_desc0 = umma_desc_sw128(sQ), kv_desc0 = umma_desc_sw128(sKV), p_desc0 = umma_desc_sw128(sP);
     Ring rkv;
@@ -203,15 +204,22 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
         ++np;
       }
     }
-  } else if (warp < 8) {
-    // ===== softmax warpgroups =====
-    const int g = warp >> 2, q = warp & 3;
+  } else if (warp < 16) {
+    // ===== softmax warpgroups: warpgroup g = warp / 8; inside it lane quarter q = warp % 4 and key half hh = (warp / 4) % 2 =====
+    // Two warps share each 32 query rows: warp hh takes keys [64 hh, 64 hh + 64) of a tile (= one K block of P) and 32 of O's 64
+    // columns.  (With ONE warp per scheduler and warpgroup the exp section ran at 1 450 cycles against its 1 024-cycle MUFU
+    // floor: nothing to issue while an EX2 result is on its way.)  The row maximum is exchanged through shared memory.
+    const int g = warp >> 3, q = warp & 3, hh = (warp >> 2) & 1;
     const int erow = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 192u;
     const uint32_t sPg = sP + (uint32_t)g * 32768u;
     const uint32_t p_row = sPg + (uint32_t)erow * 128u;
+    float* xch = reinterpret_cast<float*>(smem_gen + p.off_bar + 1024);       // [16 warps][32 lanes]
+    float* mine = xch + warp * 32 + lane;
+    const float* theirs = xch + (warp ^ 4) * 32 + lane;                       // the warp with the other key half of my rows
+    const int pair_bar = 4 + g * 4 + q;                                       // named barrier of the two warps (64 threads)
     uint32_t ns = 0;                                     // S tiles consumed so far by this warpgroup
-    if (g == 1) asm volatile("bar.arrive %0, 256;" ::"r"(2) : "memory");   // warpgroup 0 goes first
+    if (g == 1) asm volatile("bar.arrive %0, 512;" ::"r"(2) : "memory");   // warpgroup 0 goes first
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int b, h, qp, len;
       decode(item, b, h, qp, len);
@@ -220,9 +228,9 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
       if (n_kv == 0) {
         // an empty utterance: its rows of O are zero
         if (t_row < p.T) {
-          uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.T + t_row) * 512 + h * 64);
+          uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.T + t_row) * 512 + h * 64 + hh * 32);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
         }
         continue;
       }
@@ -230,118 +238,110 @@ flow_attn_tc_kernel(const FlowAttnMaps* __restrict__ maps_g, const __grid_consta
       for (int j = 0; j < n_kv; ++j, ++ns) {
         mbar_wait(b_s_full + 8u * g, ns & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        fa_trace(tr && q == 0, g, j, 0, 1, tri);
-        const int kmax = len - j * 128;                  // keys of this tile that exist (>= 1)
-        // the whole S row (128 scores) into registers with ONE wait: a tcgen05.ld round trip is several hundred cycles and a
-        // warpgroup has one warp per scheduler (chunk by chunk, twice over, the loads were most of the tile's time)
-        uint32_t sr[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32_issue(lane_base + (uint32_t)(c * 32), sr[c]);
+        fa_trace(tr && q == 0 && hh == 0, g, j, 0, 1, tri);
+        const int kmax = len - j * 128 - hh * 64;        // keys of my half that exist (may be <= 0 on the last tile)
+        uint32_t sr[2][32];
+        tmem_ld32_issue(lane_base + (uint32_t)(hh * 64), sr[0]);
+        tmem_ld32_issue(lane_base + (uint32_t)(hh * 64 + 32), sr[1]);
         tmem_wait_ld();
+        tmem_ld_pin32(sr[0]);
+        tmem_ld_pin32(sr[1]);
+        if (kmax < 64) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_pin32(sr[c]);
-        if (kmax < 128) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < 32; ++i) if (c * 32 + i >= kmax) sr[c][i] = 0xff800000u;    // -inf
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i])); mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i])); mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        *mine = fmaxf(mx0, mx1);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        const float mx = fmaxf(fmaxf(mx0, mx1), *theirs);        // finite: key 0 of every tile exists
         // Lazy rescale: the reference maximum moves only when some row of the warp would otherwise see P > 2^8 (bf16 / fp32
-        // have the headroom); then the O tile in TMEM is left alone — its load / scale / store round trip was a quarter of
-        // a tile's critical path, and after the first tiles of an utterance the running maximum rarely grows that much.
+        // have the headroom); then the O tile in TMEM is left alone.  (Both warps of a pair see the same 32 maxima: same vote.)
         const float m_cand = fmaxf(m, mx * p.sc2);
         const bool move = (j == 0) || __any_sync(0xffffffffu, m_cand - m > 8.0f);
         const float m_new = move ? m_cand : m;
         const float corr = move ? ex2_fast(m - m_new) : 1.0f;   // 0 on the first tile (m = -inf)
-        // The exponentials of the two warpgroups take turns (named barriers 2 + g): a warpgroup has one warp per scheduler
-        // and that warp alone saturates the scheduler's MUFU unit, so two exp sections side by side just run at half
-        // speed IN PHASE — and then both wait for their MMAs together.  Alternating, one warpgroup's TMEM loads, maximum,
+        // The exponentials of the two warpgroups take turns (named barriers 2 + g): side by side they just share the MUFU
+        // units IN PHASE and then both wait for their MMAs together.  Alternating, one warpgroup's TMEM loads, maximum,
         // P stores and MMAs run under the other's exponentials.
-        fa_trace(tr && q == 0, g, j, 0, 2, tri);
-        asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
-        fa_trace(tr && q == 0, g, j, 0, 3, tri);
-        // P = 2^(s sc2 - m_new) -> bf16 -> shared memory (K block = 64 keys; 16-byte chunks XOR row & 7); masked keys: 2^-inf = 0
+        fa_trace(tr && q == 0 && hh == 0, g, j, 0, 2, tri);
+        asm volatile("bar.sync %0, 512;" ::"r"(2 + g) : "memory");
+        fa_trace(tr && q == 0 && hh == 0, g, j, 0, 3, tri);
+        // P = 2^(s sc2 - m_new) -> bf16 -> K block hh of the warpgroup's P operand (16-byte chunks XOR row & 7); masked: 2^-inf = 0
         float l0 = 0.f, l1 = 0.f;
+        const uint32_t rowa = p_row + (uint32_t)hh * 16384u;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = ex2_fast(fmaf(__uint_as_float(sr[c][i]), p.sc2, -m_new));
 #pragma unroll
           for (int i = 0; i < 32; i += 2) { l0 += v[i]; l1 += v[i + 1]; }
-          const uint32_t rowa = p_row + (uint32_t)(c >> 1) * 16384u;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            sts128u(rowa + ((((uint32_t)((c & 1) * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
+            sts128u(rowa + ((((uint32_t)(c * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
                     ElemIO<E>::pack2(v[8 * k4 + 2], v[8 * k4 + 3]), ElemIO<E>::pack2(v[8 * k4 + 4], v[8 * k4 + 5]),
                     ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
         }
-        l = fmaf(l, corr, l0 + l1);
-        asm volatile("bar.arrive %0, 256;" ::"r"(3 - g) : "memory");      // the other warpgroup's turn
-        fa_trace(tr && q == 0, g, j, 0, 4, tri);
+        l = fmaf(l, corr, l0 + l1);                      // (this warp's half of the row sum; the halves meet at the end)
+        asm volatile("bar.arrive %0, 512;" ::"r"(3 - g) : "memory");      // the other warpgroup's turn
+        fa_trace(tr && q == 0 && hh == 0, g, j, 0, 4, tri);
         if (j > 0 && move) {
-          // the previous tile's P V has landed in O: rescale it to the new maximum (both halves in flight, one wait)
+          // the previous tile's P V has landed in O: rescale my 32 columns of it to the new maximum
           mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t orr[2][32];
-          tmem_ld32_issue(lane_base + 128u, orr[0]);
-          tmem_ld32_issue(lane_base + 160u, orr[1]);
-          tmem_wait_ld();
-          tmem_ld_pin32(orr[0]);
-          tmem_ld_pin32(orr[1]);
+          float v[32];
+          tmem_ld32(lane_base + 128u + (uint32_t)(hh * 32), v);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(orr[c][i]) * corr;
-            tmem_st32(lane_base + 128u + (uint32_t)(c * 32), v);
-          }
+          for (int i = 0; i < 32; ++i) v[i] *= corr;
+          tmem_st32(lane_base + 128u + (uint32_t)(hh * 32), v);
+          tmem_wait_st();
         }
         m = m_new;
-        if (j > 0 && move) tmem_wait_st();
         fence_async_smem();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (elect_one()) mbar_arrive(b_p_ready + 8u * g);
-        fa_trace(tr && q == 0, g, j, 0, 5, tri);
+        fa_trace(tr && q == 0 && hh == 0, g, j, 0, 5, tri);
       }
-      // ---- output: O / l -> bf16 -> this warp's 32 x 64 box (staged in the warpgroup's P buffer) -> TMA store ----
+      // ---- output: O / l -> bf16 -> my 32 of the 64 columns of the pair's 32 x 64 box (staged in the P buffer) -> TMA store ----
       mbar_wait(b_pv_done + 8u * g, (ns - 1u) & 1u, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float inv = (t_row < len && l > 0.f) ? 1.f / l : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      *mine = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float lt = l + *theirs;
+      const float inv = (t_row < len && lt > 0.f) ? 1.f / lt : 0.f;
+      {
         float v[32];
-        tmem_ld32(lane_base + 128u + (uint32_t)(c * 32), v);
+        tmem_ld32(lane_base + 128u + (uint32_t)(hh * 32), v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= inv;
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
-          sts128u(p_row + ((((uint32_t)(c * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
+          sts128u(p_row + ((((uint32_t)(hh * 4 + k4)) ^ ((uint32_t)erow & 7u)) << 4), ElemIO<E>::pack2(v[8 * k4], v[8 * k4 + 1]),
                   ElemIO<E>::pack2(v[8 * k4 + 2], v[8 * k4 + 3]), ElemIO<E>::pack2(v[8 * k4 + 4], v[8 * k4 + 5]),
                   ElemIO<E>::pack2(v[8 * k4 + 6], v[8 * k4 + 7]));
       }
       fence_async_smem();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (elect_one()) {
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both halves of the box are staged (and both have read the row sums)
+      if (hh == 0 && elect_one()) {
         tma_store_3d(&maps.O, sPg + (uint32_t)q * 4096u, h * 64, qp * 256 + g * 128 + q * 32, b);
         bulk_commit();
         bulk_wait_read<0>();                              // the box has left shared memory before the next item's P lands there
       }
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8)
+  if (warp == 16)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
