@@ -694,6 +694,25 @@ def main():
                 fe1.record(stream)
                 torch.cuda.synchronize(dev)
                 fms_b1 = fe0.elapsed_time(fe1) / 5
+                # other batch sizes: 8 utterances, and 37 (2 x 37 x 500 rows = 145 pair tiles of 256 rows on 74 CTA pairs: two full
+                # waves, where 32 utterances leave a third of the second wave empty)
+                sweep = []
+                for sb in (8, 37):
+                    sz = torch.randn(sb, 80, fT, generator=fg).to(dev)
+                    smu = (torch.randn(sb, 80, fT, generator=fg) * 0.5 - 1.0).to(dev)
+                    ssp = torch.nn.functional.normalize(torch.randn(sb, 80, generator=fg), dim=1).to(dev)
+                    scond = torch.zeros(sb, 80, fT, device=dev)
+                    for _ in range(2):
+                        flow.decode(sz, smu, ssp, scond)
+                    torch.cuda.synchronize(dev)
+                    fe0.record(stream)
+                    for _ in range(3):
+                        flow.decode(sz, smu, ssp, scond)
+                    fe1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    sms = fe0.elapsed_time(fe1) / 3
+                    sweep.append({"batch": sb, "ms_per_decode": sms, "value": sb * fT / 50.0 / (sms / 1e3), "unit": UNIT})
+                    del sz, smu, ssp, scond
                 # the two drop-ins chained, as S3Gen.inference chains them: flow decoder -> mel -> vocoder -> int16 PCM in
                 # pinned host memory (mu / spks / cond resident: the encoder in front stays the engine's)
                 chain = None
@@ -752,10 +771,11 @@ def main():
                                            "traffic": None,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
-                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain,
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "batch_sweep": sweep,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
-                                      "(classifier-free guidance); bf16: transformer blocks on flow_blk_kernel (fused q/k/v, "
-                                      "out-proj + residual + LayerNorm, whole feed-forward) and flow_attn_tc_kernel (tcgen05)"}
+                                      "(classifier-free guidance); bf16: between two attention launches (flow_attn_tc_kernel, tcgen05) a "
+                                      "transformer block is ONE flow_blk_kernel launch (out-proj + residual + LayerNorm + feed-forward + "
+                                      "residual + LayerNorm + the next block's q/k/v); ResNet blocks: conv + LayerNorm + Mish fused"}
                 del flow
                 torch.cuda.empty_cache()
             except Exception as e:
