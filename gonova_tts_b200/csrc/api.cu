@@ -284,8 +284,12 @@ struct gnv_decoder {
   bool use_tc = true;
   int tc_version = 2;
   bool fuse_pairs = true;   // conv1 + Snake + conv2 + residual of a ResBlock step in one kernel
-  int pair_cta2 = 0;        // CTA pairs in the fused kernel: -1 = choose, 0 = never, 1 = always.  Off: measured 0.15-0.2 ms
-                            // SLOWER per C=64 pair (the leader must wait for both CTAs' epilogue 1 before conv2)
+  int pair_cta2 = -1;       // CTA pairs in the fused kernel: -1 = choose (enough tiles for 74 pairs twice), 0 = never, 1 = always.
+                            // Round 1 measured pairs 0.15-0.2 ms SLOWER per C=64 pair and kept them off; the cost was the
+                            // `mbarrier.arrive.release.cluster` of every epilogue (MEMBAR.ALL.CTA + ERRBAR, 2.6 k cycles, found on
+                            // flow_blk_kernel's timeline).  With default-semantics arrives the step is 2.3 % faster in pairs
+                            // (three interleaved runs: 26.83 -> 26.20 ms), mostly as clock: half the weight traffic into shared
+                            // memory, and the step runs into the board's power cap.
   int fuse_max_c = 64;      // ... for stages with at most this many channels.  Measured (B=64, T=500, bf16): C=64
                             // pairs are 5-28 % faster fused; C=128 pairs must drop to 128-row tiles to fit TMEM
                             // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
