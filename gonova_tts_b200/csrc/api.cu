@@ -293,8 +293,9 @@ struct gnv_decoder {
   int fuse_max_c = 64;      // ... for stages with at most this many channels.  Measured (B=64, T=500, bf16): C=64
                             // pairs are 5-28 % faster fused; C=128 pairs must drop to 128-row tiles to fit TMEM
                             // (3*mh*C <= 512), which doubles the weight traffic and makes k=7/11 pairs 15-30 % slower.
-  int fuse_k3_max_c = 64;   // ... and for k = 3 ResBlocks up to this many channels (GONOVA_FUSE_K3_MAX_C).  Measured at C = 128:
-                            // the three fused k = 3 pairs take 1.51 ms against 1.59 ms in six launches, the step does not move
+  int fuse_k3_max_c = 128;  // ... and for k = 3 ResBlocks up to this many channels (GONOVA_FUSE_K3_MAX_C).  Measured at C = 128:
+                            // the three fused k = 3 pairs take 1.51 ms against 1.59 ms in six launches; with CTA pairs in the
+                            // fused kernel the step is 0.9 % shorter (three interleaved runs: 25.95 -> 25.72 ms)
   int chain_max_k = 3;      // whole-ResBlock kernel (conv_chain_kernel) for the blocks that open a stage's running sum (j = 0)
   int chain_max_c = 64;     // ... with at most this many taps / channels (GONOVA_CHAIN_MAX_K / _MAX_C; 0 = never)
   std::map<std::pair<int, int>, int> launch_counts;   // (B, T) -> conv launches of the last plan built
