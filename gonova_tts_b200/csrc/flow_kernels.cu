@@ -501,6 +501,143 @@ __global__ void __launch_bounds__(kAmWarps * 32, 2) flow_attn_mma_kernel(const _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The tf32 path: the same flash-attention on mma.sync m16n8k8 (tf32 operands, fp32 accumulate) over the fp32 q | k | v
+// buffer.  Block = 4 warps = 64 queries, K / V tiles of 64 keys by cp.async into a two-stage ring (rows padded to 68
+// floats: every fragment load is conflict-free).  S's accumulator layout has a thread's two columns at 2t, 2t + 1 while
+// the A fragment of the next MMA wants k-indices t, t + 4: the sum over keys does not care about their order, so the P V
+// step simply reads V's rows in that permuted order (b0 = row 2t, b1 = row 2t + 1) — no shuffles.
+// (The CUDA-core kernel above took 5.0 ms per call at 2B x T = 64 x 500: 93 % of a tf32 estimator evaluation.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAtQ = 64, kAtK = 64, kAtPitch = 68;
+constexpr int kAtSmem = 2 * 2 * kAtK * kAtPitch * 4;
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+__global__ void __launch_bounds__(128) flow_attn_tf32_kernel(const float* __restrict__ qkv, int T, const int* __restrict__ lengths,
+                                                             float scale, int round_tf32v, float* __restrict__ out) {
+  extern __shared__ __align__(16) float at_smem[];
+  float* Ks = at_smem;                                   // [2][64][68]
+  float* Vs = at_smem + 2 * kAtK * kAtPitch;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAtQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int len = lengths ? min(T, max(0, lengths[b])) : T;
+  const float* base = qkv + (size_t)b * T * 1536 + h * 64;
+  const int r0 = q0 + 16 * warp + g, r1 = r0 + 8;
+  const int n_tiles = (len + kAtK - 1) / kAtK;
+  const uint32_t ks_u = (uint32_t)__cvta_generic_to_shared(Ks), vs_u = (uint32_t)__cvta_generic_to_shared(Vs);
+  constexpr uint32_t kStage = kAtK * kAtPitch * 4;
+  auto load_tile = [&](int tile, int stage) {
+    const int k0 = tile * kAtK;
+    for (int i = threadIdx.x; i < kAtK * 16; i += 128) {   // 64 rows x 16 sixteen-byte words, K and V
+      const int kk = i >> 4, w = i & 15;
+      const int tk = k0 + kk;
+      const bool live = tk < len;
+      const float* kp = base + (size_t)(live ? tk : 0) * 1536 + 512 + 4 * w;
+      const uint32_t off = stage * kStage + (uint32_t)(kk * kAtPitch + 4 * w) * 4u;
+      cp_async16(ks_u + off, kp, live);
+      cp_async16(vs_u + off, kp + 512, live);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_tiles > 0) load_tile(0, 0);
+  uint32_t qa[8][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int c = 8 * ks + t;
+    qa[ks][0] = r0 < len ? __float_as_uint(base[(size_t)r0 * 1536 + c]) : 0u;
+    qa[ks][1] = r1 < len ? __float_as_uint(base[(size_t)r1 * 1536 + c]) : 0u;
+    qa[ks][2] = r0 < len ? __float_as_uint(base[(size_t)r0 * 1536 + c + 4]) : 0u;
+    qa[ks][3] = r1 < len ? __float_as_uint(base[(size_t)r1 * 1536 + c + 4]) : 0u;
+  }
+  const float sc2 = scale * 1.4426950408889634f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int stage = tile & 1, k0 = tile * kAtK;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (tile + 1 < n_tiles) load_tile(tile + 1, stage ^ 1);
+    const float* Kt = Ks + stage * kAtK * kAtPitch;
+    const float* Vt = Vs + stage * kAtK * kAtPitch;
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t b0 = __float_as_uint(Kt[(8 * j + g) * kAtPitch + 8 * ks + t]);
+        const uint32_t b1 = __float_as_uint(Kt[(8 * j + g) * kAtPitch + 8 * ks + t + 4]);
+        mma_tf32_1688(s[j], qa[ks], b0, b1);
+      }
+    }
+    if (k0 + kAtK > len) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = k0 + 8 * j + 2 * t;
+        if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0 * sc2), mn1 = fmaxf(m1, mx1 * sc2);
+    const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+      s[j][0] = ex2_approx(fmaf(s[j][0], sc2, -mn0)); s[j][1] = ex2_approx(fmaf(s[j][1], sc2, -mn0));
+      s[j][2] = ex2_approx(fmaf(s[j][2], sc2, -mn1)); s[j][3] = ex2_approx(fmaf(s[j][3], sc2, -mn1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                           // eight keys per k-step: S tile j, keys in the order 2t | 2t + 1
+      uint32_t pa[4];
+      pa[0] = tf32_bits(s[j][0]); pa[1] = tf32_bits(s[j][2]); pa[2] = tf32_bits(s[j][1]); pa[3] = tf32_bits(s[j][3]);
+#pragma unroll
+      for (int dj = 0; dj < 8; ++dj) {
+        const uint32_t b0 = __float_as_uint(Vt[(8 * j + 2 * t) * kAtPitch + 8 * dj + g]);
+        const uint32_t b1 = __float_as_uint(Vt[(8 * j + 2 * t + 1) * kAtPitch + 8 * dj + g]);
+        mma_tf32_1688(o[dj], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = (r0 < len && l0 > 0.f) ? 1.f / l0 : 0.f, i1 = (r1 < len && l1 > 0.f) ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int dj = 0; dj < 8; ++dj) {
+    const int c = h * 64 + 8 * dj + 2 * t;
+    float a0 = o[dj][0] * i0, a1 = o[dj][1] * i0, b0 = o[dj][2] * i1, b1 = o[dj][3] * i1;
+    if (round_tf32v) { a0 = round_tf32(a0); a1 = round_tf32(a1); b0 = round_tf32(b0); b1 = round_tf32(b1); }
+    if (r0 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + r0) * 512 + c) = make_float2(a0, a1);
+    if (r1 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + r1) * 512 + c) = make_float2(b0, b1);
+  }
+}
+
 cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths, float scale, int round_tf32v, void* out,
                              int elem_bytes, cudaStream_t st) {
   dim3 grid((T + kAttQ - 1) / kAttQ, 8, B2);
@@ -510,11 +647,19 @@ cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths,
     flow_attn_mma_kernel<<<gm, kAmWarps * 32, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, (__nv_bfloat16*)out);
     return cudaGetLastError();
   }
-  if (elem_bytes == 2)
+  if (elem_bytes == 2) {
     flow_attn_kernel<__nv_bfloat16><<<grid, kAttQ * 32, 0, st>>>((const __nv_bfloat16*)qkv, T, lengths, scale, 0,
                                                                  (__nv_bfloat16*)out);
-  else
-    flow_attn_kernel<float><<<grid, kAttQ * 32, 0, st>>>((const float*)qkv, T, lengths, scale, round_tf32v, (float*)out);
+    return cudaGetLastError();
+  }
+  if (use_mma) {
+    static const cudaError_t attr = cudaFuncSetAttribute(flow_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);
+    if (attr != cudaSuccess) return attr;
+    dim3 gt((T + kAtQ - 1) / kAtQ, 8, B2);
+    flow_attn_tf32_kernel<<<gt, 128, kAtSmem, st>>>((const float*)qkv, T, lengths, scale, round_tf32v, (float*)out);
+    return cudaGetLastError();
+  }
+  flow_attn_kernel<float><<<grid, kAttQ * 32, 0, st>>>((const float*)qkv, T, lengths, scale, round_tf32v, (float*)out);
   return cudaGetLastError();
 }
 
