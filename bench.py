@@ -713,6 +713,23 @@ def main():
                     sms = fe0.elapsed_time(fe1) / 3
                     sweep.append({"batch": sb, "ms_per_decode": sms, "value": sb * fT / 50.0 / (sms / 1e3), "unit": UNIT})
                     del sz, smu, ssp, scond
+                # the reference's arithmetic class (tf32 operands, one tensor-core launch per projection, mma.sync tf32 attention)
+                flow_tf32 = None
+                if flow.dtype == "bf16" and not args.no_tf32:
+                    try:
+                        f32 = B200Flow(random_flow_state_dict(0), device=dev, dtype="tf32")
+                        f32.decode(fz, fmu, fsp, fcond)
+                        torch.cuda.synchronize(dev)
+                        fe0.record(stream)
+                        f32.decode(fz, fmu, fsp, fcond)
+                        fe1.record(stream)
+                        torch.cuda.synchronize(dev)
+                        tms = fe0.elapsed_time(fe1)
+                        flow_tf32 = {"value": fB * fT / 50.0 / (tms / 1e3), "unit": UNIT, "ms_per_decode": tms, "batch": fB}
+                        del f32
+                        torch.cuda.empty_cache()
+                    except Exception as te:
+                        flow_tf32 = {"error": str(te)}
                 # the two drop-ins chained, as S3Gen.inference chains them: flow decoder -> mel -> vocoder -> int16 PCM in
                 # pinned host memory (mu / spks / cond resident: the encoder in front stays the engine's)
                 chain = None
@@ -771,7 +788,7 @@ def main():
                                            "traffic": None,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
-                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "batch_sweep": sweep,
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "batch_sweep": sweep, "tf32": flow_tf32,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
                                       "(classifier-free guidance); bf16: between two attention launches (flow_attn_tc_kernel, tcgen05) a "
                                       "transformer block is ONE flow_blk_kernel launch (out-proj + residual + LayerNorm + feed-forward + "
