@@ -159,3 +159,17 @@ def test_fused_blocks_equal_one_launch_per_projection(flows, cuda_device, tmp_pa
         snr = snr_db(got, ref)
         print(f"[parity] flow 3 steps bf16: default against '{name}': max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
         assert snr >= 38.0, name
+
+
+@pytest.mark.parametrize("B,T,lengths", [(1, 3, None), (3, 129, [129, 1, 128]), (2, 1031, [1031, 700])])
+def test_odd_and_long_shapes(flows, oracle, cuda_device, B, T, lengths):
+    """Three frames; lengths 1 / 128 / 129 around the 128-key attention tile; 20 s utterances (nine key tiles, five 256-row
+    tiles per utterance, T not a multiple of 8: the transposed-V pitch is padded)."""
+    z, mu, mask, spks, cond = FR.synthetic_inputs(B, T, seed=21, lengths=lengths)
+    want = FR.solve_euler(oracle, z * mask, mu, mask, spks, cond, n_timesteps=1).numpy()
+    dev = cuda_device
+    got = flows("bf16").decode(z.to(dev), mu.to(dev), spks.to(dev), cond.to(dev), lengths=lengths, n_timesteps=1).cpu().numpy()
+    zn = (z * mask).numpy()
+    snr = snr_db(got - zn, want - zn)
+    print(f"[parity] flow 1 step bf16 B={B} T={T} lengths={lengths}: max-abs {np.abs(got - want).max():.3e}  SNR of the velocity {snr:.1f} dB")
+    assert np.isfinite(got).all() and np.abs(got - want).max() <= TOL["bf16"][0] and snr >= TOL["bf16"][1]
