@@ -697,7 +697,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 o = lds128(sc + co_off[i]);
-              if (FULL || rok[i]) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + rdelta + odd * 16) = o;
+              if ((FULL || rok[i]) && !(p.dbg & 16)) *reinterpret_cast<float4*>(const_cast<float*>(rp[i]) + rdelta + odd * 16) = o;
             }
           }
           if (do_ln) {
@@ -715,7 +715,7 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const float4 o = lds128(sc + cbo[i]);
-              if (FULL || nok[i]) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
+              if ((FULL || nok[i]) && !(p.dbg & 32)) *reinterpret_cast<float4*>(np[i] + odd * 16) = o;
             }
           }
           __syncwarp();                                   // this scratch buffer is free again
