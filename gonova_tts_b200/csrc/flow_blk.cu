@@ -198,11 +198,19 @@ const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, c
 const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
                                    const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
                                    const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
-                                   int max_ctas, const void* w4, void* qkv_out, void* vt, int vt_tp) {
-  // the feed-forward's launch, then the out-projection's operands on top of it
-  const char* e = make_flow_blk_launch(out, FB_FF, o, 256, w1, b1, w2, b2, r, gamma, beta, ln, n_out, n_pitch, 256, M, T, max_ctas,
-                                       nullptr, 0, 0, nullptr);
+                                   int max_ctas, const void* w4, void* qkv_out, void* vt, int vt_tp, const float* r_in) {
+  // the feed-forward's launch, then the out-projection's operands on top of it.  w1 == NULL: no feed-forward (projection +
+  // residual + LayerNorm + the q/k/v tail): the maps of a dummy feed-forward over the projection's own weights are never used
+  const bool noff = w1 == nullptr;
+  if (noff && !w4) return "flow_outff: without a feed-forward the q/k/v tail is the launch's only output";
+  const char* e = make_flow_blk_launch(out, FB_FF, o, 256, noff ? w3 : w1, b1, noff ? w3 : w2, b2, r, gamma, beta, ln,
+                                       noff ? (void*)qkv_out : n_out, noff ? 1536 : n_pitch, 256, M, T, max_ctas, nullptr, 0, 0, nullptr);
   if (*e) return e;
+  out->p.noff = noff ? 1 : 0;
+  if (r_in) {
+    if ((uintptr_t)r_in & 15) return "flow_outff: residual input must be 16-byte aligned";
+    out->p.r_in = r_in;
+  }
   if (K <= 0 || K % 64 || !w3) return "flow_outff: bad out-projection";
   PFN_encodeTiled enc = get_encode_tiled();
   out->mode = FB_OUTFF;

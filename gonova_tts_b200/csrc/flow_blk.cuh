@@ -48,6 +48,8 @@ struct FlowBlkParams {
   const float *b1, *b2, *gamma, *beta;
   const float *b3, *g3, *be3;   // OUTFF: the out-projection's bias and the LayerNorm between it and the feed-forward
   int qkv;                      // OUTFF: 1 = the NEXT block's q/k/v projection runs on the tile's LayerNorm output before it leaves
+  int noff;                     // OUTFF: 1 = no feed-forward: projection + residual + LayerNorm, then the q/k/v tail (a ResNet
+                                // block's res_conv in front of a level's first transformer block)
   float* r;                 // FF / OUT: the residual stream [M, 256] fp32 (output); CONV with out_f32: the fp32 output
   const float* r_in;        // FF / OUT: the residual input (== r when updated in place)
   int conv_nch, conv_tpb;   // CONV: K blocks per tap (C_in / 64), pair tiles per utterance
@@ -308,12 +310,14 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         } else {
           for (int kb = 0; kb < 4; ++kb) load_a(kb, row0);
         }
-        load_w1(0);
-        load_w1(1);
-        for (int c = 0; c < 8; ++c) {
-          load_w2(c);
-          if (c + 2 < 8) load_w1(c + 2);
-          fb_trace(tr, 2, t, c, 3, tri);
+        if (!(MODE == FB_OUTFF && p.noff)) {
+          load_w1(0);
+          load_w1(1);
+          for (int c = 0; c < 8; ++c) {
+            load_w2(c);
+            if (c + 2 < 8) load_w1(c + 2);
+            fb_trace(tr, 2, t, c, 3, tri);
+          }
         }
         if constexpr (MODE == FB_OUTFF) {
           if (p.qkv) {
@@ -456,12 +460,13 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
             }
             if (elect_one()) umma_commit_2sm(b_acc2_full);                          // (phase 0 of the tile: the projection is done)
             __syncwarp();
-            mbar_wait(b_x_ready, p.qkv ? 0u : (uint32_t)(it & 1), 2);               // x is back in acc2, LayerNorm(x) in the x region
+            // x is back in acc2, LayerNorm(x) in the x region (two x_ready / acc2_full events per tile with feed-forward AND tail)
+            mbar_wait(b_x_ready, (p.qkv && !p.noff) ? 0u : (uint32_t)(it & 1), 2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
-          g1(0, MODE == FB_FF);
-          g1(1, false);
-          for (int c = 0; c < 8; ++c) {
+          const bool ff = !(MODE == FB_OUTFF && p.noff);
+          if (ff) { g1(0, MODE == FB_FF); g1(1, false); }
+          for (int c = 0; ff && c < 8; ++c) {
             const int nn = it * 8 + c;
             mbar_wait(b_e1_done + 8u * (nn & 1), (uint32_t)((nn >> 1) & 1), 2);     // H[nn & 1] valid, acc1[nn & 1] free
             if (MODE == FB_FF && c == 0) mbar_wait(b_acc2_free, (uint32_t)(it & 1) ^ 1u, 2);   // the previous tile's rows have left acc2
@@ -479,13 +484,17 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
               __syncwarp();
             }
           }
-          if (elect_one()) umma_commit_2sm(b_acc2_full);
-          __syncwarp();
+          if (ff) {
+            if (elect_one()) umma_commit_2sm(b_acc2_full);
+            __syncwarp();
+          }
           if constexpr (MODE == FB_OUTFF) {
             if (p.qkv) {
               // ---- the next block's q/k/v projection on the LayerNorm output the second epilogue left in the x region ----
-              mbar_wait(b_x_ready, 1u, 2);
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              if (ff) {
+                mbar_wait(b_x_ready, 1u, 2);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
               for (int n = 0; n < 6; ++n) {
                 const uint32_t buf = (uint32_t)(n & 1);
                 const uint32_t idx = (uint32_t)(3 * it + (n >> 1));
@@ -1006,10 +1015,13 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
         if constexpr (MODE == FB_OUTFF) {
           // the out-projection's epilogue: x = acc + b3 + R stays in TMEM (the feed-forward accumulates onto it),
           // LayerNorm(x) becomes the feed-forward's A operand in the x region; nothing goes to global memory
-          e2_tile(t, 256u, b_acc2_full, 0u, b_x_ready, true, false, true, true, true, tb1 + 1024, tb1 + 1280,
-                  tab + 1536 + 768 + 1024);
+          // (without a feed-forward the same epilogue also writes R': it is the block's only one)
+          // (acc2_full completes twice per tile — projection, feed-forward — unless there is no feed-forward)
+          e2_tile(t, 256u, b_acc2_full, p.noff ? (uint32_t)(it & 1) : 0u, b_x_ready, true, p.noff != 0, true, true, true,
+                  tb1 + 1024, tb1 + 1280, tab + 1536 + 768 + 1024);
         }
-        for (int c = 0; c < 8; ++c) {
+        const bool ff = !(MODE == FB_OUTFF && p.noff);
+        for (int c = 0; ff && c < 8; ++c) {
           const int nn = it * 8 + c;
           const uint32_t buf = (uint32_t)(nn & 1);
           mbar_wait(b_acc1_full + 8u * buf, (uint32_t)((nn >> 1) & 1), 4);
@@ -1040,9 +1052,10 @@ flow_blk_kernel(const FlowBlkMaps* __restrict__ maps_g, const __grid_constant__ 
           fb_trace(tre, 0, t, c, 3, tri);
         }
         // the tile's rows are complete once the last G2 has retired (which also frees the H region for the scratch)
-        if constexpr (MODE == FB_OUTFF)
-          e2_tile(t, 256u, b_acc2_full, 1u, p.qkv ? b_x_ready : b_acc2_free, false, true, p.qkv != 0, p.ln != 0, false, tb2, tg, tbt);
-        else
+        if constexpr (MODE == FB_OUTFF) {
+          if (ff)
+            e2_tile(t, 256u, b_acc2_full, 1u, p.qkv ? b_x_ready : b_acc2_free, false, true, p.qkv != 0, p.ln != 0, false, tb2, tg, tbt);
+        } else
           e2_tile(t, 256u, b_acc2_full, (uint32_t)(it & 1), b_acc2_free, true, true, false, p.ln != 0, false, tb2, tg, tbt);
         if constexpr (MODE == FB_OUTFF) {
           if (p.qkv) {
@@ -1132,12 +1145,13 @@ const char* make_flow_conv_launch(FlowBlkLaunch* out, const void* a, int C_in, c
                                   int max_ctas);
 // FB_OUTFF: o [M, K] bf16 (attention output), w3 [256, K] + b3 and LayerNorm (g3, be3), then the feed-forward as in FB_FF
 // w4 != NULL: the NEXT block's q/k/v projection [1536, 256] runs on the LayerNorm output (which then never leaves the SM):
-// qkv_out [M, 1536] bf16 (q | k), vt [M / T * 8, 64, vt_tp] (V transposed); n_out is not written in that case
+// qkv_out [M, 1536] bf16 (q | k), vt [M / T * 8, 64, vt_tp] (V transposed); n_out is not written in that case.
+// w1 == NULL: no feed-forward (projection + residual r_in -> r + LayerNorm(g3, be3) + the q/k/v tail)
 const char* make_flow_outff_launch(FlowBlkLaunch* out, const void* o, int K, const void* w3, const float* b3, const float* g3,
                                    const float* be3, const void* w1, const float* b1, const void* w2, const float* b2, float* r,
                                    const float* gamma, const float* beta, int ln, void* n_out, int n_pitch, int M, int T,
                                    int max_ctas, const void* w4 = nullptr, void* qkv_out = nullptr, void* vt = nullptr,
-                                   int vt_tp = 0);
+                                   int vt_tp = 0, const float* r_in = nullptr);
 cudaError_t launch_flow_blk(const FlowBlkLaunch& L, const int* lengths, cudaStream_t st, const float* tbias = nullptr);
 cudaError_t flow_blk_init();
 int flow_blk_read_trace(unsigned long long* out, int cap);   // tuning: CTA 0's timeline of the last traced launch
