@@ -24,6 +24,8 @@ SYMBOLS = [
     "gnv_debug_chain_trace",
     "gnv_flow_create", "gnv_flow_destroy", "gnv_flow_workspace_bytes", "gnv_flow_decode", "gnv_flow_launches",
     "gnv_flow_profile", "gnv_debug_flow_trace",
+    "gnv_flow_enc_create", "gnv_flow_enc_destroy", "gnv_flow_enc_workspace_bytes", "gnv_flow_encode",
+    "gnv_flow_encode_profile", "gnv_flow_enc_launches",
 ]
 
 
@@ -85,6 +87,15 @@ def load():
                                      C.c_size_t, vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_double), C.c_char_p, C.POINTER(C.c_int)]
     lib.gnv_flow_launches.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    lib.gnv_flow_enc_create.argtypes = [C.POINTER(GnvWeight), C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]
+    lib.gnv_flow_enc_destroy.argtypes = [vp]
+    lib.gnv_flow_enc_destroy.restype = None
+    lib.gnv_flow_enc_workspace_bytes.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+    lib.gnv_flow_encode.argtypes = [vp, i32p, i32p, f32p, C.c_int, C.c_int, f32p, f32p, vp, C.c_size_t, vp]
+    lib.gnv_flow_encode_profile.argtypes = [vp, i32p, i32p, f32p, C.c_int, C.c_int, f32p, f32p, vp, C.c_size_t, vp, C.c_int,
+                                            C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_char_p,
+                                            C.POINTER(C.c_int)]
+    lib.gnv_flow_enc_launches.argtypes = [vp, C.POINTER(C.c_int)]
     lib.gnv_debug_chain_trace.argtypes = [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]
     lib.gnv_debug_cluster_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.gnv_decode_launches.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
@@ -93,7 +104,7 @@ def load():
     lib.gnv_source_stream.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, vp, f32p, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_flow_destroy"):
+        if name not in ("gnv_destroy", "gnv_last_error", "gnv_abi_version", "gnv_flow_destroy", "gnv_flow_enc_destroy"):
             fn.restype = C.c_int
     _LIB = lib
     return lib

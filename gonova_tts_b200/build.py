@@ -19,7 +19,7 @@ INCLUDE = PKG.parent / "include"
 C_HOST_SRC = PKG.parent / "examples" / "c_host.c"
 C_HOST = LIBDIR / "hift_c_host"          # plain-C host over the C ABI (tests/test_gpu_c_host.py)
 
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "conv_chain.cu", "aux_kernels.cu", "flow_kernels.cu", "flow_blk.cu", "flow_attn.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair.cu", "conv_chain.cu", "aux_kernels.cu", "flow_kernels.cu", "flow_blk.cu", "flow_attn.cu", "flow_enc_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v",

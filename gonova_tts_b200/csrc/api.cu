@@ -41,6 +41,7 @@
 #include "flow_attn.cuh"
 #include "kernels.h"
 #include "flow_kernels.h"
+#include "flow_enc_kernels.h"
 
 using namespace gnv;
 
@@ -84,6 +85,7 @@ struct ConvLayer {
   bool strided_simt = false;   // source_downs on CUDA cores: strided rows, K = 18*k
   bool flat = false;           // source_downs as a GEMM over k consecutive STFT frames (tensor cores)
   bool causal = false;         // all of the conv's padding on the left (the flow decoder's CausalConv1d): L_out = L_in
+  bool ahead = false;          // all of the padding on the right (the flow encoder's pre-lookahead conv): L_out = L_in
   int conv_k = 0, conv_stride = 0, conv_pad = 0;   // the real conv geometry behind a flat layer
   double flops_per_row = 0.0;  // algorithmic flops per output row (0 = 2*C_out*C_in*k)
   int C_in_ld = 0;             // channel stride of the A operand (and of each tap in the packed W)
@@ -589,8 +591,8 @@ std::string make_op(const gnv_decoder* h, const ConvLayer& L, const void* A, int
     ep.dup_row = es.reflect_front ? 1 : -1;
     ep.L_out = ep.L_store + ep.shift;
   } else {
-    const int L_out = L.causal ? L_in : (L_in + 2 * L.pad - L.dil * (L.k - 1) - 1) / L.stride + 1;
-    g.off0 = L.causal ? -L.dil * (L.k - 1) : -L.pad; g.tap_step = L.dil; g.in_stride = L.stride;
+    const int L_out = (L.causal || L.ahead) ? L_in : (L_in + 2 * L.pad - L.dil * (L.k - 1) - 1) / L.stride + 1;
+    g.off0 = L.causal ? -L.dil * (L.k - 1) : (L.ahead ? 0 : -L.pad); g.tap_step = L.dil; g.in_stride = L.stride;
     g.M_rows = L_out;
     ep.up = 1; ep.pad_out = 0; ep.shift = 0; ep.dup_row = -1;
     ep.L_store = L_out; ep.L_out = L_out;
@@ -1535,3 +1537,4 @@ int gnv_inference_launches(gnv_handle h, int B, int T, int* out) {
 }  // extern "C"
 
 #include "flow_api.inc"
+#include "flow_enc_api.inc"

@@ -13,7 +13,7 @@
 
 namespace gnv {
 
-enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3, ACT_SNAKE_FAST = 4, ACT_ELU_FAST = 5, ACT_GELU = 6 };
+enum { ACT_NONE = 0, ACT_SNAKE = 1, ACT_LRELU = 2, ACT_ELU = 3, ACT_SNAKE_FAST = 4, ACT_ELU_FAST = 5, ACT_GELU = 6, ACT_SILU = 7 };
 
 constexpr int kMaxAct = 3;
 
@@ -103,6 +103,7 @@ __device__ __forceinline__ float act_apply(int kind, float x, float alpha, float
     // exp(x) - 1 through MUFU.EX2: absolute error ~6e-8 near 0, far below the bf16 / tf32 rounding of the stored operand
     case ACT_ELU_FAST: return x > 0.f ? x : __expf(x) - 1.0f;
     case ACT_GELU:  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));     // exact (erf) GELU, torch's default
+    case ACT_SILU:  return x / (1.0f + expf(-x));                                  // x sigmoid(x) (the Conformer's "swish")
     default:        return x;
   }
 }

@@ -362,6 +362,10 @@ __device__ __forceinline__ void epi_finish_item(const EpiCtx& c, float (&v)[32],
       } else if (kind == ACT_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) y[i] = gelu_erf_fast(v[i]);
+      } else if (kind == ACT_SILU) {
+        // x sigmoid(x) through MUFU.EX2 + MUFU.RCP (the Conformer feed-forward of the flow front)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __fdividef(v[i], 1.0f + __expf(-v[i]));
       } else if (kind == ACT_ELU_FAST) {
         // (the f0 predictor's five conv layers: with the out-of-line expm1f they were EPILOGUE-bound — ncu: tensor pipe
         // active 22 %, ~50 instructions per element — at 0.11 ms per layer against 0.04 ms of MMA time)

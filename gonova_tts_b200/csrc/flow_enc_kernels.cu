@@ -1,0 +1,381 @@
+// Small kernels of the flow front (oracle/flow_enc_ref.py): token embedding, LayerNorm(512), the relative
+// position table, relative-position self-attention, the mu transpose and the speaker projection.  Every Linear / Conv1d of
+// the Conformer encoder is a conv_tc2_kernel launch (tcgen05 / TMEM / TMA) with bias / residual / SiLU / LeakyReLU in its
+// epilogue; these kernels are what sits between them.
+// Activations are time-major [B, T, 512]; rows at or beyond an utterance's length are kept at zero (an utterance in a
+// ragged batch is encoded exactly as if it were alone: upstream's flow.inference asserts a batch of one).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "flow_enc_kernels.h"
+
+namespace gnv {
+
+namespace {
+
+__device__ __forceinline__ int enc_len(const int32_t* lengths, int b, int len_mul, int T) {
+  if (!lengths) return T;
+  const int n = lengths[b] * len_mul;
+  return n < 0 ? 0 : (n > T ? T : n);
+}
+
+template <typename E>
+__device__ __forceinline__ void enc_store4(E* dst, const float* v, int round_tf32v) {
+  float y[4] = {v[0], v[1], v[2], v[3]};
+  if constexpr (sizeof(E) == 4) {
+    if (round_tf32v) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = round_tf32(y[k]);
+    }
+  }
+  ElemIO<E>::template store_vec<4>(dst, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void enc_embed_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ token_len,
+                                 const float* __restrict__ table, int vocab, int B, int L, E* __restrict__ out, int round_tf32v) {
+  const size_t n = (size_t)B * L * (kEncC / 4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / (kEncC / 4);
+    const int c = (int)(i % (kEncC / 4)) * 4;
+    const int b = (int)(row / L), l = (int)(row - (size_t)b * L);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (l < enc_len(token_len, b, 1, L)) {
+      int tok = tokens[row];
+      tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+      const float4 a = *reinterpret_cast<const float4*>(table + (size_t)tok * kEncC + c);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    enc_store4<E>(out + row * kEncC + c, v, round_tf32v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm(512): one warp per row, a lane holds 4 x float4 (channels lane*4 + 128 j): coalesced 512-byte warp accesses.
+template <typename E>
+__global__ void __launch_bounds__(256) enc_ln_kernel(const float* __restrict__ in, int B, int T, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, const int32_t* __restrict__ lengths,
+                                                     int len_mul, E* __restrict__ out_e, float* __restrict__ out_f, int round_tf32v) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int rows = B * T;
+  float g[16], bt[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(gamma + 128 * j + lane * 4);
+    const float4 c = *reinterpret_cast<const float4*>(beta + 128 * j + lane * 4);
+    g[4 * j] = a.x; g[4 * j + 1] = a.y; g[4 * j + 2] = a.z; g[4 * j + 3] = a.w;
+    bt[4 * j] = c.x; bt[4 * j + 1] = c.y; bt[4 * j + 2] = c.z; bt[4 * j + 3] = c.w;
+  }
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const int b = row / T, t = row - b * T;
+    const bool live = t < enc_len(lengths, b, len_mul, T);
+    float v[16];
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(in + (size_t)row * kEncC + 128 * j + lane * 4);
+        v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += v[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / kEncC);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / kEncC) + eps);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf((v[i] - mean) * rstd, g[i], bt[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t o = (size_t)row * kEncC + 128 * j + lane * 4;
+      if (out_f) *reinterpret_cast<float4*>(out_f + o) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      if (out_e) enc_store4<E>(out_e + o, v + 4 * j, round_tf32v);
+    }
+  }
+}
+
+template <typename E>
+__global__ void enc_cast_kernel(const float* __restrict__ in, int B, int T, const int32_t* __restrict__ lengths, int len_mul,
+                                E* __restrict__ out, int round_tf32v) {
+  const size_t n = (size_t)B * T * (kEncC / 4);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / (kEncC / 4);
+    const int c = (int)(i % (kEncC / 4)) * 4;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t < enc_len(lengths, b, len_mul, T)) {
+      const float4 a = *reinterpret_cast<const float4*>(in + row * kEncC + c);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    enc_store4<E>(out + row * kEncC + c, v, round_tf32v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The relative-position table of one layer at one length (built once per plan): a block takes kPosRows rows r of pos_emb
+// (sinusoids of relative position (T-1) - r, the fp32 arithmetic of upstream's EspnetRelPositionalEncoding) and thread o
+// computes output channel o of linear_pos for each of them, reading its weight row once.
+constexpr int kPosRows = 8;
+
+__global__ void __launch_bounds__(kEncC) enc_pos_kernel(const float* __restrict__ w_pos, int T, float* __restrict__ P) {
+  __shared__ float pe[kPosRows][kEncC];
+  const int R = 2 * T - 1;
+  const int r0 = blockIdx.x * kPosRows;
+  const int c = threadIdx.x;
+  {
+    const float div = expf((float)(c & ~1) * (float)(-(9.210340371976184 / (double)kEncC)));   // ln(10000) / d
+    for (int k = 0; k < kPosRows; ++k) {
+      const int r = r0 + k;
+      float val = 0.f;
+      if (r < R) {
+        const int rel = (T - 1) - r;
+        const float arg = (float)(rel < 0 ? -rel : rel) * div;
+        val = (c & 1) ? cosf(arg) : (rel < 0 ? -sinf(arg) : sinf(arg));
+      }
+      pe[k][c] = val;
+    }
+  }
+  __syncthreads();
+  float acc[kPosRows];
+#pragma unroll
+  for (int k = 0; k < kPosRows; ++k) acc[k] = 0.f;
+  const float4* wrow = reinterpret_cast<const float4*>(w_pos + (size_t)c * kEncC);
+  for (int j = 0; j < kEncC / 4; ++j) {
+    const float4 w4 = wrow[j];
+#pragma unroll
+    for (int k = 0; k < kPosRows; ++k) {
+      acc[k] = fmaf(w4.x, pe[k][4 * j], acc[k]);
+      acc[k] = fmaf(w4.y, pe[k][4 * j + 1], acc[k]);
+      acc[k] = fmaf(w4.z, pe[k][4 * j + 2], acc[k]);
+      acc[k] = fmaf(w4.w, pe[k][4 * j + 3], acc[k]);
+    }
+  }
+  const int h = c >> 6, d = c & 63;
+  for (int k = 0; k < kPosRows; ++k) {
+    const int r = r0 + k;
+    if (r < R) P[((size_t)h * R + r) * 64 + d] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Relative-position attention, fp32 arithmetic on the CUDA cores (the encoder runs once per utterance against twenty
+// estimator evaluations: ~1 % of the flow's FLOPs).  A block = kAeQ consecutive query rows of one (utterance, head), one
+// warp per row; per tile of 32 keys lane j owns key j for the scores (K and the window of P rows the 16 x 32 (i, j) pairs
+// touch sit in shared memory with a 65-word pitch: conflict-free), then owns channels 2 lane, 2 lane + 1 for P V.
+constexpr int kAeQ = 16;
+constexpr int kAeK = 32;
+constexpr int kAeWin = kAeQ + kAeK - 1;
+
+template <typename E>
+__global__ void __launch_bounds__(kAeQ * 32) enc_attn_kernel(const E* __restrict__ qkv, const float* __restrict__ P, int T,
+                                                             const int32_t* __restrict__ lengths, int len_mul,
+                                                             E* __restrict__ out, int round_tf32v) {
+  __shared__ float s_qu[kAeQ][64], s_qv[kAeQ][64];
+  __shared__ float s_k[kAeK][65], s_v[kAeK][64], s_p[kAeWin][65];
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kAeQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = enc_len(lengths, b, len_mul, T);
+  const int i = i0 + warp;
+  E* orow = out + ((size_t)b * T + i) * kEncC + h * 64 + 2 * lane;
+  if (i0 >= len) {                                           // the whole block is padding
+    if (i < T) {
+      if constexpr (sizeof(E) == 2) *reinterpret_cast<uint32_t*>(orow) = 0u;
+      else *reinterpret_cast<float2*>(orow) = make_float2(0.f, 0.f);
+    }
+    return;
+  }
+  const int R = 2 * T - 1;
+  const E* base = qkv + (size_t)b * T * kEncQkv + h * 64;
+  {
+    const int ii = i < T ? i : T - 1;
+    const E* q = base + (size_t)ii * kEncQkv;
+    s_qu[warp][lane] = ElemIO<E>::load(q + lane);       s_qu[warp][lane + 32] = ElemIO<E>::load(q + lane + 32);
+    s_qv[warp][lane] = ElemIO<E>::load(q + 512 + lane); s_qv[warp][lane + 32] = ElemIO<E>::load(q + 512 + lane + 32);
+  }
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  const float sc = 0.125f * 1.4426950408889634f;             // 1 / sqrt(64), in the exp2 domain
+  for (int j0 = 0; j0 < len; j0 += kAeK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kAeK * 64; e += kAeQ * 32) {
+      const int j = e >> 6, d = e & 63;
+      const int jj = j0 + j;
+      float kv = 0.f, vv = 0.f;
+      if (jj < len) {
+        kv = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1024 + d);
+        vv = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1536 + d);
+      }
+      s_k[j][d] = kv;
+      s_v[j][d] = vv;
+    }
+    // window of P: local row w holds r = (T-1) - (i0 + kAeQ - 1) + j0 + w; pair (query i0 + q, key j0 + j) reads w = j + kAeQ-1 - q
+    const int rbase = (T - 1) - (i0 + kAeQ - 1) + j0;
+    for (int e = threadIdx.x; e < kAeWin * 64; e += kAeQ * 32) {
+      const int w = e >> 6, d = e & 63;
+      const int r = rbase + w;
+      s_p[w][d] = (r >= 0 && r < R) ? P[((size_t)h * R + r) * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    float ac = 0.f, bd = 0.f;
+    const float* kr = s_k[lane];
+    const float* pr = s_p[lane + kAeQ - 1 - warp];
+#pragma unroll 16
+    for (int d = 0; d < 64; ++d) {
+      ac = fmaf(s_qu[warp][d], kr[d], ac);
+      bd = fmaf(s_qv[warp][d], pr[d], bd);
+    }
+    const bool valid = j0 + lane < len;
+    const float s = valid ? (ac + bd) * sc : -INFINITY;
+    float mt = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+    const float mn = fmaxf(m, mt);                           // finite: key j0 is valid
+    const float corr = exp2f(m - mn);
+    const float p = valid ? exp2f(s - mn) : 0.f;
+    float ps = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    l = fmaf(l, corr, ps);
+    o0 *= corr; o1 *= corr;
+#pragma unroll 8
+    for (int j = 0; j < kAeK; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const float2 v2 = *reinterpret_cast<const float2*>(&s_v[j][2 * lane]);
+      o0 = fmaf(pj, v2.x, o0);
+      o1 = fmaf(pj, v2.y, o1);
+    }
+    m = mn;
+  }
+  if (i < T) {
+    const bool live = i < len;
+    const float inv = live ? 1.0f / l : 0.f;
+    float y0 = live ? o0 * inv : 0.f, y1 = live ? o1 * inv : 0.f;
+    if constexpr (sizeof(E) == 2) {
+      *reinterpret_cast<uint32_t*>(orow) = ElemIO<E>::pack2(y0, y1);
+    } else {
+      if (round_tf32v) { y0 = round_tf32(y0); y1 = round_tf32(y1); }
+      *reinterpret_cast<float2*>(orow) = make_float2(y0, y1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void enc_mu_kernel(const float* __restrict__ in, int B, int T, const int32_t* __restrict__ lengths, int len_mul,
+                              float* __restrict__ mu) {
+  __shared__ float tile[32][81];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const int len = enc_len(lengths, b, len_mul, T);
+  for (int e = threadIdx.x; e < 32 * 80; e += blockDim.x) {
+    const int t = e / 80, c = e - t * 80;
+    const int tt = t0 + t;
+    tile[t][c] = (tt < len) ? in[((size_t)b * T + tt) * 80 + c] : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 80; e += blockDim.x) {
+    const int c = e >> 5, t = e & 31;
+    const int tt = t0 + t;
+    if (tt < T) mu[((size_t)b * 80 + c) * T + tt] = tile[t][c];
+  }
+}
+
+__global__ void __launch_bounds__(192) enc_spk_kernel(const float* __restrict__ embedding, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ spks) {
+  __shared__ float xn[192];
+  __shared__ float part[6];
+  const int b = blockIdx.x, c = threadIdx.x;
+  const float x = embedding[(size_t)b * 192 + c];
+  float s = x * x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((c & 31) == 0) part[c >> 5] = s;
+  __syncthreads();
+  const float norm = sqrtf(part[0] + part[1] + part[2] + part[3] + part[4] + part[5]);
+  xn[c] = x / fmaxf(norm, 1e-12f);                           // F.normalize(dim=1), eps 1e-12
+  __syncthreads();
+  if (c < 80) {
+    float acc = bias[c];
+    for (int k = 0; k < 192; ++k) acc = fmaf(w[(size_t)c * 192 + k], xn[k], acc);
+    spks[(size_t)b * 80 + c] = acc;
+  }
+}
+
+inline int enc_blocks(size_t n, int per_block) {
+  const size_t need = (n + per_block - 1) / per_block;
+  return (int)(need < (size_t)148 * 8 ? (need ? need : 1) : (size_t)148 * 8);
+}
+
+}  // namespace
+
+cudaError_t launch_enc_embed(const int32_t* tokens, const int32_t* token_len, const float* table, int vocab, int B, int L,
+                             void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st) {
+  const int blocks = enc_blocks((size_t)B * L * (kEncC / 4), 256);
+  if (elem_bytes == 2)
+    enc_embed_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(tokens, token_len, table, vocab, B, L, (__nv_bfloat16*)out_e, 0);
+  else
+    enc_embed_kernel<float><<<blocks, 256, 0, st>>>(tokens, token_len, table, vocab, B, L, (float*)out_e, round_tf32v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_ln(const float* in, int B, int T, const float* gamma, const float* beta, float eps,
+                          const int32_t* lengths, int len_mul, void* out_e, int elem_bytes, int round_tf32v, float* out_f,
+                          cudaStream_t st) {
+  const int blocks = enc_blocks((size_t)B * T, 8);
+  if (elem_bytes == 2)
+    enc_ln_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, B, T, gamma, beta, eps, lengths, len_mul, (__nv_bfloat16*)out_e,
+                                                         out_f, 0);
+  else
+    enc_ln_kernel<float><<<blocks, 256, 0, st>>>(in, B, T, gamma, beta, eps, lengths, len_mul, (float*)out_e, out_f, round_tf32v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_cast(const float* in, int B, int T, const int32_t* lengths, int len_mul, void* out_e, int elem_bytes,
+                            int round_tf32v, cudaStream_t st) {
+  const int blocks = enc_blocks((size_t)B * T * (kEncC / 4), 256);
+  if (elem_bytes == 2)
+    enc_cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, B, T, lengths, len_mul, (__nv_bfloat16*)out_e, 0);
+  else
+    enc_cast_kernel<float><<<blocks, 256, 0, st>>>(in, B, T, lengths, len_mul, (float*)out_e, round_tf32v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, cudaStream_t st) {
+  const int R = 2 * T - 1;
+  enc_pos_kernel<<<(R + kPosRows - 1) / kPosRows, kEncC, 0, st>>>(w_pos, T, P);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_attn(const void* qkv, const float* P, int B, int T, const int32_t* lengths, int len_mul, void* out_e,
+                            int elem_bytes, int round_tf32v, cudaStream_t st) {
+  dim3 grid((T + kAeQ - 1) / kAeQ, kEncH, B);
+  if (elem_bytes == 2)
+    enc_attn_kernel<__nv_bfloat16><<<grid, kAeQ * 32, 0, st>>>((const __nv_bfloat16*)qkv, P, T, lengths, len_mul,
+                                                               (__nv_bfloat16*)out_e, 0);
+  else
+    enc_attn_kernel<float><<<grid, kAeQ * 32, 0, st>>>((const float*)qkv, P, T, lengths, len_mul, (float*)out_e, round_tf32v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_mu(const float* in, int B, int T, const int32_t* lengths, int len_mul, float* mu, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, B);
+  enc_mu_kernel<<<grid, 256, 0, st>>>(in, B, T, lengths, len_mul, mu);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_enc_spk(const float* embedding, const float* w, const float* bias, int B, float* spks, cudaStream_t st) {
+  enc_spk_kernel<<<B, 192, 0, st>>>(embedding, w, bias, spks);
+  return cudaGetLastError();
+}
+
+}  // namespace gnv

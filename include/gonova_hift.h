@@ -232,6 +232,30 @@ int gnv_debug_flow_trace(unsigned long long* out, int cap, int* n_out);
 /* kernel launches of one gnv_flow_decode with the plan last built (bench bookkeeping) */
 int gnv_flow_launches(gnv_flow_handle f, int n_timesteps, int* out);
 
+/* ---- the front of the flow step: speech tokens -> mu / spks ("tokens -> mel") -----------------------------
+ * replaces: the part of CausalMaskedDiffWithXvec.inference in front of `self.decoder(...)` in the engine's S3Gen flow
+ * (`flow.inference(token, token_len, prompt_token, ..., embedding, finalize)`): F.normalize + spk_embed_affine_layer,
+ * input_embedding, UpsampleConformerEncoder (pre-lookahead convs, 6 + 4 relative-position Conformer layers around a x2
+ * upsampling conv), encoder_proj; reached from services/tts/core/synthesizer.py:344-350 through S3Gen.inference.
+ * Weights: that module's state dict under upstream's names ("input_embedding.weight", "spk_embed_affine_layer.weight",
+ * "encoder.encoders.0.self_attn.linear_pos.weight", "encoder.up_layer.conv.weight", "encoder_proj.bias", ...), HOST fp32. */
+typedef struct gnv_flow_enc* gnv_flow_enc_handle;
+int gnv_flow_enc_create(const GnvWeight* weights, int n_weights, int device, int dtype, unsigned flags, gnv_flow_enc_handle* out);
+void gnv_flow_enc_destroy(gnv_flow_enc_handle f);
+int gnv_flow_enc_workspace_bytes(gnv_flow_enc_handle f, int B, int L, size_t* out_bytes);
+/* tokens [B, L] int32 device (the prompt's tokens followed by the utterance's; negative ids count as 0 like upstream's
+ * clamp), token_len [B] int32 device or NULL, embedding [B, 192] fp32 x-vectors (NULL with spks NULL: skip the speaker
+ * projection) -> mu [B, 80, 2L] fp32 (gnv_flow_decode's `mu`; frames at or past 2 * token_len[b] are zero) and
+ * spks [B, 80].  An utterance of a ragged batch is encoded exactly as if it were alone (upstream runs one at a time). */
+int gnv_flow_encode(gnv_flow_enc_handle f, const int32_t* tokens, const int32_t* token_len, const float* embedding, int B, int L,
+                    float* mu, float* spks, void* workspace, size_t workspace_bytes, void* stream);
+/* Measurement hook like gnv_flow_profile: one gnv_flow_encode with a CUDA event after every launch. */
+int gnv_flow_encode_profile(gnv_flow_enc_handle f, const int32_t* tokens, const int32_t* token_len, const float* embedding, int B,
+                            int L, float* mu, float* spks, void* workspace, size_t workspace_bytes, void* stream, int capacity,
+                            float* ms_out, int32_t* kind_out, double* flops_out, char* names_out, int* n_out);
+/* kernel launches of one gnv_flow_encode with the plan last built (bench bookkeeping) */
+int gnv_flow_enc_launches(gnv_flow_enc_handle f, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,119 @@
+"""The front of the flow step (token embedding, upsampling Conformer encoder, encoder_proj, speaker projection)
+on a B200 against its CPU oracle (oracle/flow_enc_ref.py; parity unpinned: the engine is not vendored).  Both sides hold the
+same seeded weights and get the same tokens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import snr_db
+from oracle import flow_enc_ref as ER
+from oracle import flow_ref as FR
+
+pytestmark = pytest.mark.gpu
+
+# (max-abs, SNR dB) of mu against the fp32 oracle, at about 2x what the kernels deliver (measured on B200: tf32 1.4e-3 /
+# 64.5 dB, bf16 1.2e-2 / 46.4 dB at |mu| up to 2.4).  Operands are rounded to 10 (tf32) / 7 (bf16) mantissa bits through
+# ~45 GEMMs; LayerNorm and the softmax run in fp32 on both paths.
+TOL = {"tf32": (3e-3, 58.0), "bf16": (2.5e-2, 40.0)}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return ER.random_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def oracle(sd):
+    return ER.load_front(sd)
+
+
+@pytest.fixture(scope="module")
+def fronts(lib, cuda_device, sd):
+    from gonova_tts_b200.flow_front import B200FlowFront
+
+    cache = {}
+
+    def get(dtype):
+        if dtype not in cache:
+            cache[dtype] = B200FlowFront(sd, device=cuda_device, dtype=dtype)
+        return cache[dtype]
+
+    return get
+
+
+def _check(got, want, dtype, what):
+    err, snr = np.abs(got - want).max(), snr_db(got, want)
+    print(f"[parity] flow front {what} {dtype}: max-abs {err:.3e}  SNR {snr:.1f} dB  (|mu| max {np.abs(want).max():.2f})")
+    assert err <= TOL[dtype][0] and snr >= TOL[dtype][1], (err, snr)
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_tokens_to_mu_and_spks(fronts, oracle, cuda_device, dtype):
+    B, L = 2, 50
+    tokens, token_len, emb = ER.synthetic_tokens(B, L, seed=5)
+    with torch.inference_mode():
+        want = oracle.encode(tokens, token_len).numpy()
+        want_s = oracle.speaker(emb).numpy()
+    mu, spks = fronts(dtype).encode(tokens.to(cuda_device), token_len.to(cuda_device), emb.to(cuda_device))
+    assert mu.shape == (B, 80, 2 * L) and spks.shape == (B, 80)
+    _check(mu.cpu().numpy(), want, dtype, f"B={B} L={L}")
+    assert np.abs(spks.cpu().numpy() - want_s).max() <= 1e-5          # fp32 on both sides
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_ragged_batch_rows_equal_the_utterance_alone(fronts, oracle, cuda_device, dtype):
+    """Lengths around the tile sizes (16-row attention blocks, 32-key tiles, the 3-token look-ahead), an empty utterance, and
+    a workspace poisoned with NaNs: every utterance must come out as if it were encoded alone, frames past its length zero."""
+    B, L = 5, 70
+    lengths = [70, 33, 1, 0, 48]
+    tokens, token_len, emb = ER.synthetic_tokens(B, L, seed=9, lengths=lengths)
+    with torch.inference_mode():
+        want = oracle.encode(tokens, token_len).numpy()
+    f = fronts(dtype)
+    f._workspace(B, L).view(torch.float32)[: f.workspace_bytes(B, L) // 4].fill_(float("nan"))
+    mu, _ = f.encode(tokens.to(cuda_device), token_len.to(cuda_device), emb.to(cuda_device))
+    got = mu.cpu().numpy()
+    assert np.isfinite(got).all()
+    for b, n in enumerate(lengths):
+        assert not got[b, :, 2 * n:].any(), f"utterance {b}: frames past its length are not zero"
+    _check(got, want, dtype, f"ragged {lengths}")
+    # and bit-identical to that utterance in a batch of its own
+    alone, _ = f.encode(tokens[1:2, :33].to(cuda_device).contiguous(), None, None)
+    assert torch.equal(alone[0], mu[1, :, :66])
+
+
+def test_long_utterance_bf16(fronts, oracle, cuda_device):
+    """20 s of speech tokens (25 Hz): positions far from the origin in the relative-position table."""
+    B, L = 1, 500
+    tokens, token_len, emb = ER.synthetic_tokens(B, L, seed=11)
+    with torch.inference_mode():
+        want = oracle.encode(tokens, token_len).numpy()
+    mu, _ = fronts("bf16").encode(tokens.to(cuda_device), None, None)
+    _check(mu.cpu().numpy(), want, "bf16", f"B={B} L={L}")
+
+
+def test_flow_inference_call_shape(lib, cuda_device, sd, oracle):
+    """Upstream's `flow.inference(token, token_len, prompt_token, prompt_token_len, prompt_feat, prompt_feat_len, embedding,
+    finalize)`: tokens -> mel through the encoder AND the ten-step CFM decoder, against the two oracles chained."""
+    from gonova_tts_b200.flow_front import B200FlowInference
+
+    est_sd = FR.random_state_dict(0)
+    full = dict(sd)
+    full.update({"decoder.estimator." + k: v for k, v in est_sd.items()})
+    cfm = FR.CausalConditionalCFM(FR.load_estimator(est_sd), noise_seed=0)
+    g = torch.Generator().manual_seed(21)
+    token = torch.randint(0, ER.VOCAB, (1, 30), generator=g, dtype=torch.int32)
+    prompt_token = torch.randint(0, ER.VOCAB, (1, 12), generator=g, dtype=torch.int32)
+    prompt_feat = torch.randn(1, 24, 80, generator=g) * 0.5
+    emb = torch.randn(1, 192, generator=g)
+    with torch.inference_mode():
+        want = ER.flow_inference(oracle, cfm, token, prompt_token, prompt_feat, emb).numpy()
+    flow = B200FlowInference(full, device=cuda_device, dtype="tf32", noise_seed=0)
+    got, _ = flow.inference(token=token.to(cuda_device), token_len=torch.tensor([30]), prompt_token=prompt_token.to(cuda_device),
+                            prompt_token_len=torch.tensor([12]), prompt_feat=prompt_feat.to(cuda_device),
+                            prompt_feat_len=torch.tensor([24]), embedding=emb.to(cuda_device), finalize=True)
+    got = got.cpu().numpy()
+    assert got.shape == want.shape == (1, 80, 2 * 42 - 24)
+    err, snr = np.abs(got - want).max(), snr_db(got, want)
+    print(f"[parity] flow.inference tf32, tokens -> mel: max-abs {err:.3e}  SNR {snr:.1f} dB")
+    assert err <= 5e-3 and snr >= 59.0, (err, snr)        # measured 1.9e-3 / 65.7 dB
