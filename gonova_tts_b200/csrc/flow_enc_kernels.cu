@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "flow_enc_kernels.h"
@@ -130,7 +131,8 @@ __global__ void enc_cast_kernel(const float* __restrict__ in, int B, int T, cons
 // computes output channel o of linear_pos for each of them, reading its weight row once.
 constexpr int kPosRows = 8;
 
-__global__ void __launch_bounds__(kEncC) enc_pos_kernel(const float* __restrict__ w_pos, int T, float* __restrict__ P) {
+__global__ void __launch_bounds__(kEncC) enc_pos_kernel(const float* __restrict__ w_pos, int T, float* __restrict__ P,
+                                                        __nv_bfloat16* __restrict__ Pb) {
   __shared__ float pe[kPosRows][kEncC];
   const int R = 2 * T - 1;
   const int r0 = blockIdx.x * kPosRows;
@@ -166,7 +168,10 @@ __global__ void __launch_bounds__(kEncC) enc_pos_kernel(const float* __restrict_
   const int h = c >> 6, d = c & 63;
   for (int k = 0; k < kPosRows; ++k) {
     const int r = r0 + k;
-    if (r < R) P[((size_t)h * R + r) * 64 + d] = acc[k];
+    if (r < R) {
+      P[((size_t)h * R + r) * 64 + d] = acc[k];
+      Pb[((size_t)h * R + r) * 64 + d] = __float2bfloat16_rn(acc[k]);
+    }
   }
 }
 
@@ -271,6 +276,210 @@ __global__ void __launch_bounds__(kAeQ * 32) enc_attn_kernel(const E* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The bf16 path: the same attention as a flash loop on mma.sync m16n8k16 (bf16 operands, fp32 accumulate / softmax).  Block
+// = 4 warps = 64 queries of one (utterance, head); per tile of 64 keys a two-stage cp.async ring brings K, V and the 127
+// rows of the position table the 64 x 64 (i, j) pairs touch (row (T-1) - i + j).  A warp (16 queries) computes
+//   AC = (q + u) K^T                                   16 x 64   (32 MMAs)
+//   BD' = (q + v) P_win^T over its 79-row sub-window   16 x 80   (40 MMAs), BD'[ii][c] with c = 15 - ii + jj
+// and "rel_shift" is the skewed read-back of BD' through 5.6 KB of per-warp shared memory: S[ii][jj] = AC + BD'[ii][15 - ii + jj].
+// Then the usual online softmax and P V (32 MMAs, V through ldmatrix.trans).  (The CUDA-core kernel above took 2.5 ms per
+// layer at B x T = 32 x 500: 87 % of an encode.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmQ = 64, kEmK = 64, kEmPitch = 72, kEmWin = 128, kEmBdPitch = 88;
+constexpr uint32_t kEmKvStage = kEmK * kEmPitch * 2, kEmPStage = kEmWin * kEmPitch * 2;
+constexpr int kEmSmem = 2 * (2 * kEmKvStage + kEmPStage) + 4 * 16 * kEmBdPitch * 4;
+
+__device__ __forceinline__ void enc_mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t enc_pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float enc_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void enc_cp16(uint32_t dst, const void* src, bool live) {
+  const int n = live ? 16 : 0;                               // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 2) enc_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                             const __nv_bfloat16* __restrict__ Pb, int T,
+                                                             const int32_t* __restrict__ lengths, int len_mul,
+                                                             __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char enc_smem[];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kEmQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int len = enc_len(lengths, b, len_mul, T);
+  const int R = 2 * T - 1;
+  const __nv_bfloat16* base = qkv + (size_t)b * T * kEncQkv + h * 64;
+  const __nv_bfloat16* pbase = Pb + (size_t)h * R * 64;
+  const int r0 = q0 + 16 * warp + g, r1 = r0 + 8;
+  const int n_tiles = q0 < len ? (len + kEmK - 1) / kEmK : 0;
+  const uint32_t ks_u = (uint32_t)__cvta_generic_to_shared(enc_smem);
+  const uint32_t vs_u = ks_u + 2 * kEmKvStage;
+  const uint32_t ps_u = vs_u + 2 * kEmKvStage;
+  float* bd_w = reinterpret_cast<float*>(enc_smem + 4 * kEmKvStage + 2 * kEmPStage) + warp * 16 * kEmBdPitch;
+  auto load_tile = [&](int tile, int stage) {
+    const int k0 = tile * kEmK;
+#pragma unroll
+    for (int i = threadIdx.x; i < kEmK * 8; i += 128) {     // 64 rows x 8 sixteen-byte words, K and V
+      const int kk = i >> 3, w = i & 7;
+      const int tk = k0 + kk;
+      const bool live = tk < len;
+      const __nv_bfloat16* kp = base + (size_t)(live ? tk : 0) * kEncQkv + 1024 + 8 * w;
+      const uint32_t off = stage * kEmKvStage + (uint32_t)(kk * kEmPitch + 8 * w) * 2u;
+      enc_cp16(ks_u + off, kp, live);
+      enc_cp16(vs_u + off, kp + 512, live);
+    }
+    const int rb = (T - 1) - (q0 + kEmQ - 1) + k0;           // window row wl holds table row rb + wl
+#pragma unroll
+    for (int i = threadIdx.x; i < kEmWin * 8; i += 128) {
+      const int wl = i >> 3, w = i & 7;
+      const int r = rb + wl;
+      const bool live = r >= 0 && r < R;
+      enc_cp16(ps_u + stage * kEmPStage + (uint32_t)(wl * kEmPitch + 8 * w) * 2u, pbase + (size_t)(live ? r : 0) * 64 + 8 * w, live);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_tiles > 0) load_tile(0, 0);
+  uint32_t qu[4][4], qv[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = 16 * ks + 2 * t;
+    const __nv_bfloat16* p0 = base + (size_t)r0 * kEncQkv + c;
+    const __nv_bfloat16* p1 = base + (size_t)r1 * kEncQkv + c;
+    qu[ks][0] = r0 < len ? *reinterpret_cast<const uint32_t*>(p0) : 0u;
+    qu[ks][1] = r1 < len ? *reinterpret_cast<const uint32_t*>(p1) : 0u;
+    qu[ks][2] = r0 < len ? *reinterpret_cast<const uint32_t*>(p0 + 8) : 0u;
+    qu[ks][3] = r1 < len ? *reinterpret_cast<const uint32_t*>(p1 + 8) : 0u;
+    qv[ks][0] = r0 < len ? *reinterpret_cast<const uint32_t*>(p0 + 512) : 0u;
+    qv[ks][1] = r1 < len ? *reinterpret_cast<const uint32_t*>(p1 + 512) : 0u;
+    qv[ks][2] = r0 < len ? *reinterpret_cast<const uint32_t*>(p0 + 520) : 0u;
+    qv[ks][3] = r1 < len ? *reinterpret_cast<const uint32_t*>(p1 + 520) : 0u;
+  }
+  const float sc2 = 0.125f * 1.4426950408889634f;            // 1 / sqrt(64), softmax in base 2
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t k_lane = (uint32_t)((lane & 7) * kEmPitch + 8 * (lane >> 3)) * 2u;
+  const uint32_t v_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * kEmPitch + 8 * (lane >> 4)) * 2u;
+  const int wb = 48 - 16 * warp;                             // first window row of this warp's 80-row sub-window
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int stage = tile & 1, k0 = tile * kEmK;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                         // tile `tile` has landed; every warp is done with tile - 1
+    if (tile + 1 < n_tiles) load_tile(tile + 1, stage ^ 1);
+    const uint32_t kb = ks_u + stage * kEmKvStage + k_lane, vb = vs_u + stage * kEmKvStage + v_lane;
+    const uint32_t pb = ps_u + stage * kEmPStage + (uint32_t)(wb * kEmPitch) * 2u + k_lane;
+    // BD' first: through shared memory while the AC MMAs run
+#pragma unroll
+    for (int n = 0; n < 10; ++n) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(pb + (uint32_t)(8 * n * kEmPitch + 32 * kp) * 2u));
+        enc_mma_bf16(d, qv[2 * kp], b0, b1);
+        enc_mma_bf16(d, qv[2 * kp + 1], b2, b3);
+      }
+      *reinterpret_cast<float2*>(bd_w + g * kEmBdPitch + 8 * n + 2 * t) = make_float2(d[0], d[1]);
+      *reinterpret_cast<float2*>(bd_w + (g + 8) * kEmBdPitch + 8 * n + 2 * t) = make_float2(d[2], d[3]);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(kb + (uint32_t)(8 * j * kEmPitch + 32 * kp) * 2u));
+        enc_mma_bf16(s[j], qu[2 * kp], b0, b1);
+        enc_mma_bf16(s[j], qu[2 * kp + 1], b2, b3);
+      }
+    }
+    __syncwarp();
+    {
+      const float* ra = bd_w + g * kEmBdPitch + (15 - g) + 2 * t;          // row g:     column 15 - g + jj
+      const float* rc = bd_w + (g + 8) * kEmBdPitch + (7 - g) + 2 * t;     // row g + 8: column 15 - (g + 8) + jj
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] += ra[8 * j]; s[j][1] += ra[8 * j + 1];
+        s[j][2] += rc[8 * j]; s[j][3] += rc[8 * j + 1];
+      }
+    }
+    if (k0 + kEmK > len) {                                   // the utterance's last tile: keys past its length
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = k0 + 8 * j + 2 * t;
+        if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0 * sc2), mn1 = fmaxf(m1, mx1 * sc2);      // finite: the tile holds at least one valid key
+    const float c0 = enc_ex2(m0 - mn0), c1 = enc_ex2(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+      s[j][0] = enc_ex2(fmaf(s[j][0], sc2, -mn0)); s[j][1] = enc_ex2(fmaf(s[j][1], sc2, -mn0));
+      s[j][2] = enc_ex2(fmaf(s[j][2], sc2, -mn1)); s[j][3] = enc_ex2(fmaf(s[j][3], sc2, -mn1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {                        // 16 keys per k-step: S tiles 2 kk and 2 kk + 1
+      uint32_t pa[4];
+      pa[0] = enc_pack2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = enc_pack2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = enc_pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = enc_pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {                      // d tiles 2 dp, 2 dp + 1
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vb + (uint32_t)(16 * kk * kEmPitch + 16 * dp) * 2u));
+        enc_mma_bf16(o[2 * dp], pa, b0, b1);
+        enc_mma_bf16(o[2 * dp + 1], pa, b2, b3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = (r0 < len && l0 > 0.f) ? 1.f / l0 : 0.f, i1 = (r1 < len && l1 > 0.f) ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int dj = 0; dj < 8; ++dj) {
+    const int c = h * 64 + 8 * dj + 2 * t;
+    if (r0 < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + r0) * kEncC + c) = enc_pack2(o[dj][0] * i0, o[dj][1] * i0);
+    if (r1 < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + r1) * kEncC + c) = enc_pack2(o[dj][2] * i1, o[dj][3] * i1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void enc_mu_kernel(const float* __restrict__ in, int B, int T, const int32_t* __restrict__ lengths, int len_mul,
                               float* __restrict__ mu) {
@@ -350,14 +559,24 @@ cudaError_t launch_enc_cast(const float* in, int B, int T, const int32_t* length
   return cudaGetLastError();
 }
 
-cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, cudaStream_t st) {
+cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, void* P_bf16, cudaStream_t st) {
   const int R = 2 * T - 1;
-  enc_pos_kernel<<<(R + kPosRows - 1) / kPosRows, kEncC, 0, st>>>(w_pos, T, P);
+  enc_pos_kernel<<<(R + kPosRows - 1) / kPosRows, kEncC, 0, st>>>(w_pos, T, P, (__nv_bfloat16*)P_bf16);
   return cudaGetLastError();
 }
 
-cudaError_t launch_enc_attn(const void* qkv, const float* P, int B, int T, const int32_t* lengths, int len_mul, void* out_e,
-                            int elem_bytes, int round_tf32v, cudaStream_t st) {
+cudaError_t launch_enc_attn(const void* qkv, const float* P, const void* P_bf16, int B, int T, const int32_t* lengths,
+                            int len_mul, void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st) {
+  // bf16: tensor cores (mma.sync); GONOVA_ENC_ATTN_MMA=0 keeps the fp32 CUDA-core kernel (tests run both)
+  static const bool mma_env = [] { const char* v = getenv("GONOVA_ENC_ATTN_MMA"); return !(v && atoi(v) == 0); }();
+  if (elem_bytes == 2 && mma_env && P_bf16) {
+    static const cudaError_t attr = cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
+    if (attr != cudaSuccess) return attr;
+    dim3 grid((T + kEmQ - 1) / kEmQ, kEncH, B);
+    enc_attn_mma_kernel<<<grid, 128, kEmSmem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)P_bf16, T, lengths, len_mul,
+                                                    (__nv_bfloat16*)out_e);
+    return cudaGetLastError();
+  }
   dim3 grid((T + kAeQ - 1) / kAeQ, kEncH, B);
   if (elem_bytes == 2)
     enc_attn_kernel<__nv_bfloat16><<<grid, kAeQ * 32, 0, st>>>((const __nv_bfloat16*)qkv, P, T, lengths, len_mul,

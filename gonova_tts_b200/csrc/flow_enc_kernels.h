@@ -20,12 +20,14 @@ cudaError_t launch_enc_ln(const float* in, int B, int T, const float* gamma, con
 // fp32 [B*T, 512] -> E, rows past the length zero
 cudaError_t launch_enc_cast(const float* in, int B, int T, const int32_t* lengths, int len_mul, void* out_e, int elem_bytes,
                             int round_tf32v, cudaStream_t st);
-// P[h][r][64] = linear_pos(pos_emb)[r, h*64 ...], r in [0, 2T-1): row r is relative position (T-1) - r (ESPnet layout)
-cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, cudaStream_t st);
+// P[h][r][64] = linear_pos(pos_emb)[r, h*64 ...], r in [0, 2T-1): row r is relative position (T-1) - r (ESPnet layout);
+// fp32 and a bf16 copy
+cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, void* P_bf16, cudaStream_t st);
 // relative-position self-attention of one Conformer layer: QKV [B*T, 2048] (E) -> O [B*T, 512] (E)
 //   score(i, j) = ((q_i + u) k_j + (q_i + v) p_{(T-1) - i + j}) / 8, softmax over the keys j < len, rows i >= len are zero
-cudaError_t launch_enc_attn(const void* qkv, const float* P, int B, int T, const int32_t* lengths, int len_mul, void* out_e,
-                            int elem_bytes, int round_tf32v, cudaStream_t st);
+//   (bf16 with P_bf16: mma.sync tensor-core kernel; otherwise fp32 on the CUDA cores)
+cudaError_t launch_enc_attn(const void* qkv, const float* P, const void* P_bf16, int B, int T, const int32_t* lengths,
+                            int len_mul, void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st);
 // [B*T, 80] fp32 -> mu [B, 80, T], frames past the length zero
 cudaError_t launch_enc_mu(const float* in, int B, int T, const int32_t* lengths, int len_mul, float* mu, cudaStream_t st);
 // spks[b] = W normalize(embedding[b]) + bias   (192 -> 80)

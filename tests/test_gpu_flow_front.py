@@ -117,3 +117,36 @@ def test_flow_inference_call_shape(lib, cuda_device, sd, oracle):
     err, snr = np.abs(got - want).max(), snr_db(got, want)
     print(f"[parity] flow.inference tf32, tokens -> mel: max-abs {err:.3e}  SNR {snr:.1f} dB")
     assert err <= 5e-3 and snr >= 59.0, (err, snr)        # measured 1.9e-3 / 65.7 dB
+
+
+def test_tensor_core_attention_equals_the_cuda_core_kernel(fronts, cuda_device, tmp_path):
+    """bf16 runs the relative-position attention on mma.sync (scores from two MMAs, rel_shift as a skewed read-back);
+    GONOVA_ENC_ATTN_MMA=0 (read once per process, hence a child process) keeps the fp32 CUDA-core kernel.  Lengths around the
+    64-query / 64-key tiles."""
+    import os
+    import subprocess
+    import sys
+
+    B, L = 4, 130
+    lengths = [130, 64, 65, 7]
+    tokens, token_len, emb = ER.synthetic_tokens(B, L, seed=13, lengths=lengths)
+    mu, _ = fronts("bf16").encode(tokens.to(cuda_device), token_len.to(cuda_device), None)
+    got = mu.cpu().numpy()
+    out = tmp_path / "simt.npy"
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n"
+        "from oracle import flow_enc_ref as ER\n"
+        "from gonova_tts_b200.flow_front import B200FlowFront\n"
+        f"tokens, token_len, emb = ER.synthetic_tokens({B}, {L}, seed=13, lengths={lengths})\n"
+        "f = B200FlowFront(ER.random_state_dict(0), device='cuda:0', dtype='bf16')\n"
+        "mu, _ = f.encode(tokens.to('cuda:0'), token_len.to('cuda:0'), None)\n"
+        f"np.save({str(out)!r}, mu.cpu().numpy())\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GONOVA_ENC_ATTN_MMA="0"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(out)
+    snr = snr_db(got, ref)
+    print(f"[parity] flow front bf16: mma.sync attention against the CUDA-core kernel: max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
+    assert snr >= 40.0
