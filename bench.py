@@ -757,6 +757,90 @@ def main():
                                      "pinned host memory, both on this repo's kernels"}
                 except Exception as ce:
                     chain = {"error": str(ce)}
+                # the front of the flow step (speech tokens -> mu / spks: embedding + upsampling Conformer encoder), and the whole
+                # tokens -> PCM chain on this repo's kernels: pinned int32 tokens + x-vectors H2D, encode, ten Euler steps, vocoder,
+                # int16 PCM back to pinned host memory
+                front_block = None
+                try:
+                    from gonova_tts_b200.flow_front import B200FlowFront, random_front_state_dict
+
+                    front = B200FlowFront(random_front_state_dict(0), device=dev, dtype=flow.dtype)
+                    tL = fT // 2
+                    htok = torch.randint(0, 6561, (fB, tL), generator=fg, dtype=torch.int32).pin_memory()
+                    hemb = torch.randn(fB, 192, generator=fg).pin_memory()
+                    dtok, demb = htok.to(dev), hemb.to(dev)
+                    for _ in range(2):
+                        front.encode(dtok, None, demb)
+                    torch.cuda.synchronize(dev)
+                    fe0.record(stream)
+                    for _ in range(5):
+                        front.encode(dtok, None, demb)
+                    fe1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    enc_ms = fe0.elapsed_time(fe1) / 5
+                    prof_rows = front.profile(dtok, None, demb)
+                    prof_rows = front.profile(dtok, None, demb)
+                    t_ms = sum(r[2] for r in prof_rows if r[3] > 0 and r[0] != "self_attn")
+                    t_fl = sum(r[3] for r in prof_rows if r[3] > 0 and r[0] != "self_attn")
+                    a_ms = sum(r[2] for r in prof_rows if r[0] == "self_attn")
+                    a_fl = sum(r[3] for r in prof_rows if r[0] == "self_attn")
+                    pcm_host2 = torch.empty(fB, fT * 480, dtype=torch.int16).pin_memory()
+                    pcm_dev2 = torch.empty(fB, fT * 480, dtype=torch.int16, device=dev)
+                    no_cache2 = torch.zeros(fB, 1, 0, device=dev)
+
+                    def tokens_to_pcm():
+                        dtok.copy_(htok, non_blocking=True); demb.copy_(hemb, non_blocking=True)
+                        mu_t, sp_t = front.encode(dtok, None, demb)
+                        mel_t = flow.decode(fz, mu_t, sp_t, fcond)
+                        wav_t, _ = dec.inference(mel_t, cache_source=no_cache2)
+                        pcm_tail(wav_t, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm_dev2)
+                        pcm_host2.copy_(pcm_dev2, non_blocking=True)
+
+                    tokens_to_pcm()
+                    torch.cuda.synchronize(dev)
+                    fe0.record(stream)
+                    for _ in range(3):
+                        tokens_to_pcm()
+                    fe1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    t2p_ms = fe0.elapsed_time(fe1) / 3
+                    front_cpu = None
+                    if not args.no_cpu_baseline:
+                        from oracle import flow_enc_ref as ER
+                        torch.set_num_threads(os.cpu_count() or 1)
+                        ofront = ER.load_front(ER.random_state_dict(0))
+                        ctok, clen, _ = ER.synthetic_tokens(1, 250, seed=1)
+                        with torch.inference_mode():
+                            ofront.encode(ctok[:, :50])
+                            t0c = time.perf_counter()
+                            ofront.encode(ctok, clen)
+                            dtc = time.perf_counter() - t0c
+                        front_cpu = {"value": 10.0 / dtc, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                     "sample": f"1 utterance x 250 tokens (10 audio-s) in {dtc:.2f} s, fp32 torch CPU oracle "
+                                               "(oracle/flow_enc_ref.py)"}
+                    front_block = {"value": fB * fT / 50.0 / (enc_ms / 1e3), "unit": UNIT, "ms_per_encode": enc_ms, "batch": fB,
+                                   "tokens": tL, "frames": fT, "dtype": front.dtype, "gpu_launches": front.launches(),
+                                   "roofline_kernels": [
+                                       {"kernel": "conv_tc2_kernel (the encoder's 45 Linear / Conv1d launches)", "bound": "tensor",
+                                        "ms": t_ms, "achieved": t_fl / (t_ms / 1e3) / 1e12 if t_ms else 0.0, "unit": "TFLOP/s",
+                                        "peak": f_peak, "frac": (t_fl / (t_ms / 1e3) / 1e12 / f_peak) if (f_peak and t_ms) else None},
+                                       {"kernel": "enc_attn_mma_kernel (relative-position attention, mma.sync; 6 B H T^2 d flops)"
+                                                  if front.dtype == "bf16" else "enc_attn_kernel (relative-position attention, fp32 CUDA cores)",
+                                        "bound": "tensor", "ms": a_ms, "achieved": a_fl / (a_ms / 1e3) / 1e12 if a_ms else 0.0,
+                                        "unit": "TFLOP/s", "peak": f_peak,
+                                        "frac": (a_fl / (a_ms / 1e3) / 1e12 / f_peak) if (f_peak and a_ms) else None}],
+                                   "cpu_baseline": front_cpu,
+                                   "tokens_to_pcm": {"value": fB * fT / 50.0 / (t2p_ms / 1e3), "unit": UNIT, "ms_per_batch": t2p_ms,
+                                                     "batch": fB, "h2d_bytes_per_step": int(htok.numel() * 4 + hemb.numel() * 4),
+                                                     "d2h_bytes_per_step": int(pcm_host2.numel() * 2),
+                                                     "what": "pinned speech tokens + x-vectors -> embedding + Conformer encoder -> ten "
+                                                             "Euler steps of the CFM decoder -> f0 / source / HiFT decode -> int16 PCM in "
+                                                             "pinned host memory: S3Gen.inference without its prompt bookkeeping, every "
+                                                             "kernel this repo's"},
+                                   "what": "gnv_flow_encode: tokens [B, L] + x-vectors -> mu [B, 80, 2L], spks [B, 80]"}
+                    del front
+                except Exception as fe:
+                    front_block = {"error": str(fe)}
                 flow_cpu = None
                 if not args.no_cpu_baseline:
                     # the oracle (fp32 torch CPU restatement) on all host cores, bounded sample: 1 utterance x 100 frames, 2 Euler steps
@@ -788,7 +872,7 @@ def main():
                                            "traffic": None,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
-                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "batch_sweep": sweep, "tf32": flow_tf32,
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "front": front_block, "batch_sweep": sweep, "tf32": flow_tf32,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
                                       "(classifier-free guidance); bf16: between two attention launches (flow_attn_tc_kernel, tcgen05) a "
                                       "transformer block is ONE flow_blk_kernel launch (out-proj + residual + LayerNorm + feed-forward + "

@@ -1,5 +1,5 @@
 // Host-callable launchers of the flow front's small kernels (flow_enc_kernels.cu): everything of the token embedding +
-// upsampling Conformer encoder (oracle/flow_enc_ref.py) that is not a GEMM.
+// upsampling Conformer encoder that is not a GEMM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -216,12 +216,18 @@ class B200FlowInference(torch.nn.Module):
     prompt_feat, prompt_feat_len, embedding, finalize)` -> (mel [1, 80, frames of the new tokens], None); tokens -> mel
     entirely on this library (B200FlowFront, then B200Flow's ten Euler steps from the engine's fixed noise buffer)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", dtype: str = "bf16", prefix: str = "",
-                 noise_seed: int = 0):
+    def __init__(self, state_dict: Optional[Dict[str, torch.Tensor]] = None, device="cuda:0", dtype: str = "bf16",
+                 prefix: str = "", noise_seed: int = 0, front: Optional[B200FlowFront] = None,
+                 decoder: Optional[B200Flow] = None):
         super().__init__()
-        sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)} if prefix else dict(state_dict)
-        self.front = B200FlowFront(sd, device=device, dtype=dtype)
-        self.decoder = B200Flow(sd, device=device, dtype=dtype, prefix="decoder.estimator.", noise_seed=noise_seed)
+        if front is None or decoder is None:
+            if state_dict is None:
+                raise ValueError("give the flow module's state dict, or both parts")
+            sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)} if prefix else dict(state_dict)
+            front = front or B200FlowFront(sd, device=device, dtype=dtype)
+            decoder = decoder or B200Flow(sd, device=device, dtype=dtype, prefix="decoder.estimator.", noise_seed=noise_seed)
+        self.front = front
+        self.decoder = decoder
         self.device = self.front.device
         self.pre_lookahead_len = PRE_LOOKAHEAD_LEN
         self.token_mel_ratio = TOKEN_MEL_RATIO

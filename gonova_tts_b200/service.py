@@ -49,10 +49,13 @@ def install(model, dtype: Optional[str] = None, device=None, bucket_frames: int 
     return new
 
 
-def install_flow(model, dtype: Optional[str] = None, device=None):
+def install_flow(model, dtype: Optional[str] = None, device=None, front: bool = True):
     """Swap `model.s3gen.flow.decoder` (upstream CausalConditionalCFM: the estimator + the Euler loop that turn the encoder's
     `mu` into mel frames) for a B200Flow built from its estimator's weights and its fixed noise buffer.  The
     engine keeps calling `self.decoder(mu=..., mask=..., spks=..., cond=..., n_timesteps=10)` and gets `(mel, None)` back.
+    With `front` (and a flow module that holds `input_embedding` / `encoder` / `encoder_proj` / `spk_embed_affine_layer`),
+    `model.s3gen.flow.inference(token=..., prompt_token=..., prompt_feat=..., embedding=..., finalize=...)` is rebound too:
+    token embedding, Conformer encoder and projections run on B200FlowFront, so tokens -> mel never leaves this library.
     Same placement as install(): right after ChatterboxTTS.from_pretrained (synthesizer.py:185)."""
     from .flow import B200Flow
 
@@ -70,6 +73,14 @@ def install_flow(model, dtype: Optional[str] = None, device=None):
     if isinstance(noise, torch.Tensor):                 # the same noise the engine would have used: same mel
         new.rand_noise = noise.detach().to(new.device, torch.float32).contiguous()
     model.s3gen.flow.decoder = new
+    flow = model.s3gen.flow
+    if front and all(hasattr(flow, n) for n in ("input_embedding", "encoder", "encoder_proj", "spk_embed_affine_layer")):
+        from .flow_front import B200FlowFront, B200FlowInference
+
+        sd = {k: v for k, v in flow.state_dict().items() if not k.startswith("decoder.")}
+        whole = B200FlowInference(front=B200FlowFront(sd, device=new.device, dtype=dtype), decoder=new)
+        flow.inference = whole.inference                 # an instance attribute: shadows the class's method
+        new.flow_inference = whole
     return new
 
 

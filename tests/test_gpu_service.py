@@ -222,3 +222,46 @@ def test_install_flow_swaps_the_cfm_decoder(lib, cuda_device):
     err, snr = float((got.cpu() - want).abs().max()), snr_db(got.cpu().numpy(), want.numpy())
     print(f"[parity] installed flow decoder vs oracle CFM module: max-abs {err:.3e} SNR {snr:.1f} dB")
     assert err <= 1e-2 and snr >= 55.0
+
+
+def test_install_flow_rebinds_flow_inference(lib, cuda_device):
+    """An engine whose flow module holds the whole front (input_embedding / encoder / encoder_proj / spk_embed_affine_layer,
+    upstream's CausalMaskedDiffWithXvec): install_flow also rebinds `flow.inference`, so the engine's own keyword call runs
+    tokens -> mel on this library and returns what the oracle modules return."""
+    from types import SimpleNamespace
+
+    from gonova_tts_b200.service import install_flow
+    from oracle import flow_enc_ref as ER
+    from oracle import flow_ref as FR
+
+    class FakeFlow(ER.FlowFront):
+        def __init__(self, cfm):
+            super().__init__()
+            self.decoder = cfm
+
+        def inference(self, token, token_len, prompt_token, prompt_token_len, prompt_feat, prompt_feat_len, embedding, finalize):
+            return ER.flow_inference(self, self.decoder, token, prompt_token, prompt_feat, embedding), None
+
+    flow = FakeFlow(FR.CausalConditionalCFM(FR.make_estimator(3), noise_seed=5))
+    flow.load_state_dict(ER.random_state_dict(4), strict=False)
+    flow.eval()
+    s3gen = torch.nn.Module()
+    s3gen.flow = flow
+    eng = SimpleNamespace(s3gen=s3gen)
+    g = torch.Generator().manual_seed(8)
+    token = torch.randint(0, ER.VOCAB, (1, 40), generator=g, dtype=torch.int32)
+    prompt_token = torch.randint(0, ER.VOCAB, (1, 10), generator=g, dtype=torch.int32)
+    prompt_feat = torch.randn(1, 20, 80, generator=g) * 0.5
+    emb = torch.randn(1, 192, generator=g)
+    kw = dict(token=token, token_len=torch.tensor([40]), prompt_token=prompt_token, prompt_token_len=torch.tensor([10]),
+              prompt_feat=prompt_feat, prompt_feat_len=torch.tensor([20]), embedding=emb, finalize=True)
+    with torch.inference_mode():
+        want, _ = eng.s3gen.flow.inference(**kw)
+    new = install_flow(eng, dtype="tf32", device=cuda_device)
+    assert eng.s3gen.flow.decoder is new and new.flow_inference.front is not None
+    got, none = eng.s3gen.flow.inference(**{k: (v.to(cuda_device) if k in ("token", "prompt_token", "prompt_feat", "embedding") else v)
+                                            for k, v in kw.items()})
+    assert none is None and got.shape == want.shape == (1, 80, 80)
+    err, snr = float((got.cpu() - want).abs().max()), snr_db(got.cpu().numpy(), want.numpy())
+    print(f"[parity] installed flow.inference (tokens -> mel) vs the oracle modules: max-abs {err:.3e} SNR {snr:.1f} dB")
+    assert err <= 5e-3 and snr >= 59.0

@@ -103,3 +103,25 @@ def test_flow_oracle_equals_upstream_estimator():
         got = mine(z, mask, mu, t, spks, cond)
     np.testing.assert_allclose(got.numpy(), want.numpy(), atol=2e-5, rtol=1e-4)
     assert CausalConditionalCFM is not None
+
+
+def test_flow_front_oracle_equals_upstream_encoder():
+    """oracle/flow_enc_ref.py (tokens -> mu) against upstream's UpsampleConformerEncoder as S3Token2Mel builds it."""
+    from chatterbox.models.s3gen.transformer.upsample_encoder import UpsampleConformerEncoder
+    from oracle import flow_enc_ref as ER
+
+    sd = ER.random_state_dict(0)
+    enc = UpsampleConformerEncoder(output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+                                   positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True,
+                                   input_layer="linear", pos_enc_layer_type="rel_pos_espnet", selfattention_layer_type="rel_selfattn",
+                                   input_size=512, use_cnn_module=False, macaron_style=False).eval()
+    esd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    missing, unexpected = enc.load_state_dict(esd, strict=False)
+    assert not unexpected, unexpected                    # the oracle's key names ARE upstream's
+    assert not [k for k in missing if "pe" not in k], missing
+    mine = ER.load_front(sd)
+    x = torch.randn(1, 37, 512, generator=torch.Generator().manual_seed(3))
+    with torch.inference_mode():
+        want, _ = enc(x, torch.tensor([37]))
+        got = mine.encoder(x)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), atol=5e-5, rtol=1e-4)
