@@ -9,4 +9,7 @@ python tools/flow_profile.py bf16 32 500 > gpurun_out/r02_flow_launch_table_bf16
 python tools/flow_profile.py tf32 32 500 > gpurun_out/r02_flow_launch_table_tf32_B32_T500.csv 2>&1
 python tools/flow_profile.py bf16 1 500 > gpurun_out/r02_flow_launch_table_bf16_B1_T500.csv 2>&1
 python tools/flow_timing.py bf16 > gpurun_out/r02_flow_timing_bf16.txt 2>&1
+python tools/flow_front_profile.py bf16 32 250 > gpurun_out/r02_flow_front_launch_table_bf16_B32_L250.csv 2>&1
+python tools/flow_front_profile.py bf16 1 250 > gpurun_out/r02_flow_front_launch_table_bf16_B1_L250.csv 2>&1
+python tools/flow_front_profile.py tf32 32 250 > gpurun_out/r02_flow_front_launch_table_tf32_B32_L250.csv 2>&1
 tail -5 gpurun_out/r02_flow_timing_bf16.txt
