@@ -821,7 +821,7 @@ def main():
                     front_block = {"value": fB * fT / 50.0 / (enc_ms / 1e3), "unit": UNIT, "ms_per_encode": enc_ms, "batch": fB,
                                    "tokens": tL, "frames": fT, "dtype": front.dtype, "gpu_launches": front.launches(),
                                    "roofline_kernels": [
-                                       {"kernel": "conv_tc2_kernel (the encoder's 45 Linear / Conv1d launches)", "bound": "tensor",
+                                       {"kernel": "conv_tc2_kernel (the encoder's 46 Linear / Conv1d launches)", "bound": "tensor",
                                         "ms": t_ms, "achieved": t_fl / (t_ms / 1e3) / 1e12 if t_ms else 0.0, "unit": "TFLOP/s",
                                         "peak": f_peak, "frac": (t_fl / (t_ms / 1e3) / 1e12 / f_peak) if (f_peak and t_ms) else None},
                                        {"kernel": "enc_attn_mma_kernel (relative-position attention, mma.sync; 6 B H T^2 d flops)"
