@@ -150,3 +150,53 @@ def test_tensor_core_attention_equals_the_cuda_core_kernel(fronts, cuda_device, 
     snr = snr_db(got, ref)
     print(f"[parity] flow front bf16: mma.sync attention against the CUDA-core kernel: max-abs {np.abs(got - ref).max():.3e}  SNR {snr:.1f} dB")
     assert snr >= 40.0
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 251])
+def test_tiny_and_odd_token_counts(fronts, oracle, cuda_device, dtype, L):
+    """Fewer tokens than the look-ahead (3) and than the conv kernels' taps; one token = a 1 x 1 attention with a one-row
+    position table; 251 tokens = 502 frames, not a multiple of any tile."""
+    tokens, token_len, emb = ER.synthetic_tokens(2, L, seed=30 + L, lengths=[L, max(1, L - 1)])
+    with torch.inference_mode():
+        want = oracle.encode(tokens, token_len).numpy()
+    mu, _ = fronts(dtype).encode(tokens.to(cuda_device), token_len.to(cuda_device), None)
+    _check(mu.cpu().numpy(), want, dtype, f"L={L}")
+
+
+def test_argument_and_weight_errors(lib, cuda_device, sd, fronts):
+    """The C ABI's error behaviour: a missing or mis-shaped weight names the tensor; a too-small or unaligned workspace, a
+    spks / embedding mismatch and non-positive sizes are refused before anything is launched."""
+    import ctypes as C
+
+    from gonova_tts_b200 import _cabi
+    from gonova_tts_b200.flow_front import B200FlowFront
+
+    bad = dict(sd)
+    del bad["encoder.up_layer.conv.weight"]
+    with pytest.raises(RuntimeError, match="encoder.up_layer.conv.weight"):
+        B200FlowFront(bad, device=cuda_device, dtype="bf16")
+    bad = dict(sd)
+    bad["encoder.encoders.2.self_attn.pos_bias_u"] = torch.zeros(8, 32)
+    with pytest.raises(RuntimeError, match="encoder.encoders.2.self_attn"):
+        B200FlowFront(bad, device=cuda_device, dtype="bf16")
+    f = fronts("bf16")
+    B, L = 2, 16
+    tok = torch.zeros(B, L, dtype=torch.int32, device=cuda_device)
+    mu = torch.empty(B, 80, 2 * L, device=cuda_device)
+    spks = torch.empty(B, 80, device=cuda_device)
+    ws = torch.empty(f.workspace_bytes(B, L) + 2048, dtype=torch.uint8, device=cuda_device)
+    base = ws.data_ptr() + (-ws.data_ptr()) % 1024
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def call(tokens=tok, emb=None, spk=None, b=B, l=L, wptr=base, wbytes=f.workspace_bytes(B, L)):
+        return lib.gnv_flow_encode(f._h, C.c_void_p(tokens.data_ptr()) if tokens is not None else None, None,
+                                   C.c_void_p(emb.data_ptr()) if emb is not None else None, b, l, C.c_void_p(mu.data_ptr()),
+                                   C.c_void_p(spk.data_ptr()) if spk is not None else None, C.c_void_p(wptr), wbytes, st)
+
+    assert call() == 0
+    for kw, msg in ((dict(tokens=None), "NULL"), (dict(spk=spks), "go together"), (dict(b=0), "positive"), (dict(l=0), "positive"),
+                    (dict(wptr=base + 8), "aligned"), (dict(wbytes=1024), "too small")):
+        assert call(**kw) != 0, kw
+        assert msg in _cabi.last_error(None), (kw, _cabi.last_error(None))
+    torch.cuda.synchronize()
