@@ -200,3 +200,40 @@ def test_argument_and_weight_errors(lib, cuda_device, sd, fronts):
         assert call(**kw) != 0, kw
         assert msg in _cabi.last_error(None), (kw, _cabi.last_error(None))
     torch.cuda.synchronize()
+
+
+def test_tokens_to_waveform_like_s3gen_inference(lib, cuda_device, sd):
+    """B200Token2Wav.inference(speech_tokens, ref_dict=...) = upstream S3Token2Wav.inference: the mel against the two flow
+    oracles chained, and the waveform against the vocoder oracle's decode of THAT mel with the source the call returned
+    (the NSF source is stochastic), times trim_fade."""
+    from gonova_tts_b200 import B200Token2Wav, random_state_dict
+    from oracle import hift_ref as R
+
+    est_sd = FR.random_state_dict(0)
+    hift_sd = random_state_dict(0, False)
+    full = {"flow." + k: v for k, v in sd.items()}
+    full.update({"flow.decoder.estimator." + k: v for k, v in est_sd.items()})
+    full.update({"mel2wav." + k: v for k, v in hift_sd.items()})
+    t2w = B200Token2Wav.from_state_dict(full, device=cuda_device, dtype="tf32", noise_seed=0)
+    g = torch.Generator().manual_seed(33)
+    tokens = torch.randint(0, ER.VOCAB, (25,), generator=g, dtype=torch.int32)          # 1-D like the engine's call
+    ref = {"prompt_token": torch.randint(0, ER.VOCAB, (1, 10), generator=g, dtype=torch.int32), "prompt_token_len": torch.tensor([10]),
+           "prompt_feat": torch.randn(1, 20, 80, generator=g) * 0.5, "prompt_feat_len": None, "embedding": torch.randn(1, 192, generator=g)}
+    dev_ref = {k: (v.to(cuda_device) if isinstance(v, torch.Tensor) and k != "prompt_token_len" else v) for k, v in ref.items()}
+    wav, src = t2w.inference(tokens.to(cuda_device), ref_dict=dev_ref)
+    assert wav.shape == (1, 480 * 50) and src.shape == (1, 1, 480 * 50)
+    front = ER.load_front(sd)
+    cfm = FR.CausalConditionalCFM(FR.load_estimator(est_sd), noise_seed=0)
+    with torch.inference_mode():
+        mel_want = ER.flow_inference(front, cfm, tokens.unsqueeze(0), ref["prompt_token"], ref["prompt_feat"], ref["embedding"])
+        mel_got = t2w.flow_inference(tokens.to(cuda_device), dev_ref).cpu()
+        err_m = float((mel_got - mel_want).abs().max())
+        hift = R.load_model(hift_sd)
+        want = hift.decode(mel_got, src.cpu()).clone()
+        want[:, :960] *= R.trim_fade_window()
+    err = float((wav.cpu() - want).abs().max())
+    print(f"[parity] tokens -> waveform tf32: mel max-abs {err_m:.3e}; wav vs oracle decode of that mel + source {err:.3e}")
+    assert err_m <= 5e-3 and err <= 1e-3
+    assert not wav[:, :480].any()                                                     # trim_fade silences the first 20 ms
+    with pytest.raises(ValueError, match="ref_dict"):
+        t2w.inference(tokens.to(cuda_device))
