@@ -804,6 +804,27 @@ def main():
                     fe1.record(stream)
                     torch.cuda.synchronize(dev)
                     t2p_ms = fe0.elapsed_time(fe1) / 3
+                    # one sentence alone (the service's case): tokens -> int16 PCM in pinned host memory
+                    tok1, emb1, nc1 = dtok[:1].contiguous(), demb[:1].contiguous(), torch.zeros(1, 1, 0, device=dev)
+                    pcm1_host = torch.empty(1, fT * 480, dtype=torch.int16).pin_memory()
+                    pcm1_dev = torch.empty(1, fT * 480, dtype=torch.int16, device=dev)
+
+                    def one_sentence():
+                        mu_1, sp_1 = front.encode(tok1, None, emb1)
+                        mel_1 = flow.decode(z1, mu_1, sp_1, c1)
+                        wav_1, _ = dec.inference(mel_1, cache_source=nc1)
+                        pcm_tail(wav_1, None, None, 0.99, want_i16=True, want_f32=False, out_i16=pcm1_dev)
+                        pcm1_host.copy_(pcm1_dev, non_blocking=True)
+
+                    for _ in range(2):
+                        one_sentence()
+                    torch.cuda.synchronize(dev)
+                    fe0.record(stream)
+                    for _ in range(5):
+                        one_sentence()
+                    fe1.record(stream)
+                    torch.cuda.synchronize(dev)
+                    t2p1_ms = fe0.elapsed_time(fe1) / 5
                     front_cpu = None
                     if not args.no_cpu_baseline:
                         from oracle import flow_enc_ref as ER
@@ -837,6 +858,9 @@ def main():
                                                              "Euler steps of the CFM decoder -> f0 / source / HiFT decode -> int16 PCM in "
                                                              "pinned host memory: S3Gen.inference without its prompt bookkeeping, every "
                                                              "kernel this repo's"},
+                                   "tokens_to_pcm_one_sentence": {"ms": t2p1_ms, "value": fT / 50.0 / (t2p1_ms / 1e3), "unit": UNIT,
+                                                                  "what": "the same chain for ONE 10 s sentence (250 tokens): the latency "
+                                                                          "a single request sees between its last token and its PCM"},
                                    "what": "gnv_flow_encode: tokens [B, L] + x-vectors -> mu [B, 80, 2L], spks [B, 80]"}
                     del front
                 except Exception as fe:
