@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kEncC) enc_pos_kernel(const float* __restrict_
 // Relative-position attention, fp32 arithmetic on the CUDA cores (the encoder runs once per utterance against twenty
 // estimator evaluations: ~1 % of the flow's FLOPs).  A block = kAeQ consecutive query rows of one (utterance, head), one
 // warp per row; per tile of 32 keys lane j owns key j for the scores (K and the window of P rows the 16 x 32 (i, j) pairs
-// touch sit in shared memory with a 65-word pitch: conflict-free), then owns channels 2 lane, 2 lane + 1 for P V.
+// touch sit in shared memory, read as float4), then owns channels 2 lane, 2 lane + 1 for P V.
 constexpr int kAeQ = 16;
 constexpr int kAeK = 32;
 constexpr int kAeWin = kAeQ + kAeK - 1;
@@ -188,8 +188,10 @@ template <typename E>
 __global__ void __launch_bounds__(kAeQ * 32) enc_attn_kernel(const E* __restrict__ qkv, const float* __restrict__ P, int T,
                                                              const int32_t* __restrict__ lengths, int len_mul,
                                                              E* __restrict__ out, int round_tf32v) {
-  __shared__ float s_qu[kAeQ][64], s_qv[kAeQ][64];
-  __shared__ float s_k[kAeK][65], s_v[kAeK][64], s_p[kAeWin][65];
+  // K and the P window with a 68-word pitch: rows are 16-byte aligned and a quarter-warp's float4 loads (lanes 68 words apart)
+  // cover all 32 banks
+  __shared__ __align__(16) float s_qu[kAeQ][64], s_qv[kAeQ][64];
+  __shared__ __align__(16) float s_k[kAeK][68], s_v[kAeK][64], s_p[kAeWin][68];
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * kAeQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int len = enc_len(lengths, b, len_mul, T);
@@ -212,34 +214,58 @@ __global__ void __launch_bounds__(kAeQ * 32) enc_attn_kernel(const E* __restrict
   }
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
   const float sc = 0.125f * 1.4426950408889634f;             // 1 / sqrt(64), in the exp2 domain
-  for (int j0 = 0; j0 < len; j0 += kAeK) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < kAeK * 64; e += kAeQ * 32) {
+  // the next tile's K / V / P-window elements travel in registers while this tile is computed (one global round trip per
+  // tile would otherwise sit between the two barriers)
+  constexpr int kKvPer = kAeK * 64 / (kAeQ * 32), kPPer = (kAeWin * 64 + kAeQ * 32 - 1) / (kAeQ * 32);
+  float rk[kKvPer], rv[kKvPer], rp[kPPer];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < kKvPer; ++u) {
+      const int e = threadIdx.x + u * kAeQ * 32;
       const int j = e >> 6, d = e & 63;
       const int jj = j0 + j;
-      float kv = 0.f, vv = 0.f;
+      rk[u] = rv[u] = 0.f;
       if (jj < len) {
-        kv = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1024 + d);
-        vv = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1536 + d);
+        rk[u] = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1024 + d);
+        rv[u] = ElemIO<E>::load(base + (size_t)jj * kEncQkv + 1536 + d);
       }
-      s_k[j][d] = kv;
-      s_v[j][d] = vv;
     }
     // window of P: local row w holds r = (T-1) - (i0 + kAeQ - 1) + j0 + w; pair (query i0 + q, key j0 + j) reads w = j + kAeQ-1 - q
     const int rbase = (T - 1) - (i0 + kAeQ - 1) + j0;
-    for (int e = threadIdx.x; e < kAeWin * 64; e += kAeQ * 32) {
+#pragma unroll
+    for (int u = 0; u < kPPer; ++u) {
+      const int e = threadIdx.x + u * kAeQ * 32;
       const int w = e >> 6, d = e & 63;
       const int r = rbase + w;
-      s_p[w][d] = (r >= 0 && r < R) ? P[((size_t)h * R + r) * 64 + d] : 0.f;
+      rp[u] = (e < kAeWin * 64 && r >= 0 && r < R) ? P[((size_t)h * R + r) * 64 + d] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int j0 = 0; j0 < len; j0 += kAeK) {
+    __syncthreads();                                         // every warp is done with the previous tile
+#pragma unroll
+    for (int u = 0; u < kKvPer; ++u) {
+      const int e = threadIdx.x + u * kAeQ * 32;
+      s_k[e >> 6][e & 63] = rk[u];
+      s_v[e >> 6][e & 63] = rv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kPPer; ++u) {
+      const int e = threadIdx.x + u * kAeQ * 32;
+      if (e < kAeWin * 64) s_p[e >> 6][e & 63] = rp[u];
     }
     __syncthreads();
+    if (j0 + kAeK < len) fetch(j0 + kAeK);
     float ac = 0.f, bd = 0.f;
-    const float* kr = s_k[lane];
-    const float* pr = s_p[lane + kAeQ - 1 - warp];
-#pragma unroll 16
-    for (int d = 0; d < 64; ++d) {
-      ac = fmaf(s_qu[warp][d], kr[d], ac);
-      bd = fmaf(s_qv[warp][d], pr[d], bd);
+    const float4* kr = reinterpret_cast<const float4*>(s_k[lane]);
+    const float4* pr = reinterpret_cast<const float4*>(s_p[lane + kAeQ - 1 - warp]);
+    const float4* qu4 = reinterpret_cast<const float4*>(s_qu[warp]);
+    const float4* qv4 = reinterpret_cast<const float4*>(s_qv[warp]);
+#pragma unroll 8
+    for (int d = 0; d < 16; ++d) {
+      const float4 k4 = kr[d], p4 = pr[d], u4 = qu4[d], v4 = qv4[d];
+      ac = fmaf(u4.x, k4.x, ac); ac = fmaf(u4.y, k4.y, ac); ac = fmaf(u4.z, k4.z, ac); ac = fmaf(u4.w, k4.w, ac);
+      bd = fmaf(v4.x, p4.x, bd); bd = fmaf(v4.y, p4.y, bd); bd = fmaf(v4.z, p4.z, bd); bd = fmaf(v4.w, p4.w, bd);
     }
     const bool valid = j0 + lane < len;
     const float s = valid ? (ac + bd) * sc : -INFINITY;
