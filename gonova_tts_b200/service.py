@@ -80,7 +80,9 @@ def install_flow(model, dtype: Optional[str] = None, device=None, front: bool = 
         sd = {k: v for k, v in flow.state_dict().items() if not k.startswith("decoder.")}
         whole = B200FlowInference(front=B200FlowFront(sd, device=new.device, dtype=dtype), decoder=new)
         flow.inference = whole.inference                 # an instance attribute: shadows the class's method
-        new.flow_inference = whole
+        # (a plain attribute, not a registered child: `whole.decoder` is `new`, and a module cycle would make
+        # s3gen.eval() / .to() / .state_dict() recurse forever)
+        object.__setattr__(new, "flow_inference", whole)
     return new
 
 

@@ -259,6 +259,8 @@ def test_install_flow_rebinds_flow_inference(lib, cuda_device):
         want, _ = eng.s3gen.flow.inference(**kw)
     new = install_flow(eng, dtype="tf32", device=cuda_device)
     assert eng.s3gen.flow.decoder is new and new.flow_inference.front is not None
+    eng.s3gen.eval()                                     # the module tree stays a tree (no cycle through flow_inference)
+    assert sum(1 for _ in eng.s3gen.modules()) < 400 and "decoder.flow_inference" not in dict(eng.s3gen.flow.named_modules())
     got, none = eng.s3gen.flow.inference(**{k: (v.to(cuda_device) if k in ("token", "prompt_token", "prompt_feat", "embedding") else v)
                                             for k, v in kw.items()})
     assert none is None and got.shape == want.shape == (1, 80, 80)
