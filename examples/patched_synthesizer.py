@@ -19,7 +19,7 @@ from typing import AsyncGenerator, Optional
 
 import numpy as np
 
-from gonova_tts_b200.service import chunk_tap, install, patch_get_stats
+from gonova_tts_b200.service import chunk_tap, install, install_flow, patch_get_stats
 
 
 class StreamingSynthesizerPatch:
@@ -27,10 +27,14 @@ class StreamingSynthesizerPatch:
 
     decoder = None
 
-    def install_b200_decoder(self, dtype: str = "bf16"):
+    def install_b200_decoder(self, dtype: str = "bf16", flow: bool = False):
         """Call in load(), after `self.model = ChatterboxTTS.from_pretrained(device=self.device)` (synthesizer.py:185)
-        and before the warm-up loop (:199-207)."""
+        and before the warm-up loop (:199-207).  `flow=True` also moves the step in front of the vocoder onto the B200
+        kernels: `s3gen.flow.decoder` (ten Euler steps of the CFM estimator) and, when the flow module holds them, the token
+        embedding + Conformer encoder behind `s3gen.flow.inference` — tokens -> PCM without a stock-PyTorch op."""
         self.decoder = install(self.model, dtype=dtype)
+        if flow:
+            self.flow_decoder = install_flow(self.model, dtype=dtype)
         patch_get_stats(self, self.decoder)          # get_stats()["decoder"] (synthesizer.py:411-420)
         return self.decoder
 
