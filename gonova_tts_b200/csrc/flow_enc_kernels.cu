@@ -553,6 +553,11 @@ inline int enc_blocks(size_t n, int per_block) {
 
 }  // namespace
 
+// Per device (function attributes are per device): called by gnv_flow_enc_create under its device guard.
+cudaError_t flow_enc_init() {
+  return cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
+}
+
 cudaError_t launch_enc_embed(const int32_t* tokens, const int32_t* token_len, const float* table, int vocab, int B, int L,
                              void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st) {
   const int blocks = enc_blocks((size_t)B * L * (kEncC / 4), 256);
@@ -596,8 +601,6 @@ cudaError_t launch_enc_attn(const void* qkv, const float* P, const void* P_bf16,
   // bf16: tensor cores (mma.sync); GONOVA_ENC_ATTN_MMA=0 keeps the fp32 CUDA-core kernel (tests run both)
   static const bool mma_env = [] { const char* v = getenv("GONOVA_ENC_ATTN_MMA"); return !(v && atoi(v) == 0); }();
   if (elem_bytes == 2 && mma_env && P_bf16) {
-    static const cudaError_t attr = cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
-    if (attr != cudaSuccess) return attr;
     dim3 grid((T + kEmQ - 1) / kEmQ, kEncH, B);
     enc_attn_mma_kernel<<<grid, 128, kEmSmem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)P_bf16, T, lengths, len_mul,
                                                     (__nv_bfloat16*)out_e);

@@ -10,6 +10,8 @@ constexpr int kEncC = 512;       // model width
 constexpr int kEncH = 8;         // heads (x 64)
 constexpr int kEncQkv = 2048;    // [q + pos_bias_u | q + pos_bias_v | k | v] per row
 
+// opt-in to > 48 KB of dynamic shared memory for the tensor-core attention kernel, on the CURRENT device
+cudaError_t flow_enc_init();
 // E[b, l, :] = table[clamp(tokens[b, l], 0, vocab - 1)] for l < token_len[b], else 0
 cudaError_t launch_enc_embed(const int32_t* tokens, const int32_t* token_len, const float* table, int vocab, int B, int L,
                              void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st);

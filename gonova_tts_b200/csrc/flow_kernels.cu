@@ -638,6 +638,11 @@ __global__ void __launch_bounds__(128) flow_attn_tf32_kernel(const float* __rest
   }
 }
 
+// Per device (function attributes are per device): called by gnv_flow_create under its device guard.
+cudaError_t flow_kernels_init() {
+  return cudaFuncSetAttribute(flow_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);
+}
+
 cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths, float scale, int round_tf32v, void* out,
                              int elem_bytes, cudaStream_t st) {
   dim3 grid((T + kAttQ - 1) / kAttQ, 8, B2);
@@ -653,8 +658,6 @@ cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths,
     return cudaGetLastError();
   }
   if (use_mma) {
-    static const cudaError_t attr = cudaFuncSetAttribute(flow_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);
-    if (attr != cudaSuccess) return attr;
     dim3 gt((T + kAtQ - 1) / kAtQ, 8, B2);
     flow_attn_tf32_kernel<<<gt, 128, kAtSmem, st>>>((const float*)qkv, T, lengths, scale, round_tf32v, (float*)out);
     return cudaGetLastError();

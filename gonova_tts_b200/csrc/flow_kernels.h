@@ -21,6 +21,8 @@ cudaError_t launch_flow_ln(const float* in, int rows, int T, const float* gamma,
 // fp32 [rows, 256] -> E [rows, dst_pitch] at channel offset dst_off, masked
 cudaError_t launch_flow_cast(const float* in, int rows, int T, const int* lengths, void* dst, int dst_pitch, int dst_off,
                              int elem_bytes, int round_tf32v, cudaStream_t st);
+// opt-in to > 48 KB of dynamic shared memory for the tf32 attention kernel, on the CURRENT device
+cudaError_t flow_kernels_init();
 // QKV [B2,T,1536] -> O [B2,T,512]: 8 heads x 64, softmax over the valid keys
 cudaError_t launch_flow_attn(const void* qkv, int B2, int T, const int* lengths, float scale, int round_tf32v, void* out,
                              int elem_bytes, cudaStream_t st);
