@@ -53,6 +53,20 @@ def test_b200hift_refuses_to_run_without_cuda():
         B200HiFT(random_state_dict(0, False), device="cpu")
 
 
+def test_flow_classes_refuse_to_run_without_cuda():
+    """No CPU fallback anywhere on the tokens -> mel path either: the constructors raise before touching the weights."""
+    from gonova_tts_b200 import B200Flow, B200FlowFront, B200FlowInference, B200Token2Wav
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU box: covered by the gpu tests")
+    for cls in (B200Flow, B200FlowFront, B200FlowInference):
+        for dev in ("cuda:0", "cpu"):
+            with pytest.raises(RuntimeError, match="CUDA"):
+                cls({}, device=dev)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        B200Token2Wav.from_state_dict({}, device="cuda:0")
+
+
 class FakeQueueManager:
     """The three calls of services/tts/core/queue_manager.py the worker uses, same names and argument order."""
 
