@@ -260,13 +260,17 @@ def synthetic_tokens(B: int, L: int, seed: int = 0, lengths=None):
     return tokens, token_len, emb
 
 
-def flow_inference(front: FlowFront, cfm, token, prompt_token, prompt_feat, embedding, n_timesteps: int = 10):
+def flow_inference(front: FlowFront, cfm, token, prompt_token, prompt_feat, embedding, n_timesteps: int = 10,
+                   finalize: bool = True):
     """Upstream's `flow.inference` for one utterance with `finalize=True`: token [1, n], prompt_token [1, m], prompt_feat
     [1, mel_len1, 80], embedding [1, 192] -> mel [1, 80, 2 (m + n) - mel_len1].  `cfm` is oracle/flow_ref's
-    CausalConditionalCFM (the estimator and the engine's fixed noise buffer)."""
+    CausalConditionalCFM (the estimator and the engine's fixed noise buffer).  `finalize=False` (more tokens will follow):
+    upstream drops the last pre_lookahead_len * token_mel_ratio = 6 encoder frames before the decoder."""
     spks = front.speaker(embedding)
     tok = torch.cat([prompt_token, token], dim=1)
     mu = front.encode(tok)
+    if not finalize:
+        mu = mu[:, :, : mu.shape[2] - PRE_LOOKAHEAD * UP_STRIDE]
     T = mu.shape[2]
     mel_len1 = prompt_feat.shape[1]
     cond = torch.zeros(1, MEL, T)

@@ -117,6 +117,17 @@ def test_flow_inference_call_shape(lib, cuda_device, sd, oracle):
     err, snr = np.abs(got - want).max(), snr_db(got, want)
     print(f"[parity] flow.inference tf32, tokens -> mel: max-abs {err:.3e}  SNR {snr:.1f} dB")
     assert err <= 5e-3 and snr >= 59.0, (err, snr)        # measured 1.9e-3 / 65.7 dB
+    # finalize=False (a chunk in the middle of a token stream): the last 3 tokens' 6 frames are held back before the decoder
+    with torch.inference_mode():
+        want_open = ER.flow_inference(oracle, cfm, token, prompt_token, prompt_feat, emb, finalize=False).numpy()
+    got_open, _ = flow.inference(token=token.to(cuda_device), token_len=torch.tensor([30]), prompt_token=prompt_token.to(cuda_device),
+                                 prompt_token_len=torch.tensor([12]), prompt_feat=prompt_feat.to(cuda_device),
+                                 prompt_feat_len=torch.tensor([24]), embedding=emb.to(cuda_device), finalize=False)
+    got_open = got_open.cpu().numpy()
+    assert got_open.shape == want_open.shape == (1, 80, 2 * 42 - 24 - 6)
+    err, snr = np.abs(got_open - want_open).max(), snr_db(got_open, want_open)
+    print(f"[parity] flow.inference tf32, finalize=False: max-abs {err:.3e}  SNR {snr:.1f} dB")
+    assert err <= 5e-3 and snr >= 59.0, (err, snr)
 
 
 def test_tensor_core_attention_equals_the_cuda_core_kernel(fronts, cuda_device, tmp_path):
