@@ -507,6 +507,171 @@ __global__ void __launch_bounds__(128, 2) enc_attn_mma_kernel(const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------
+// The tf32 path: the same attention on mma.sync m16n8k8 (tf32 operands, fp32 accumulate / softmax) over the fp32 buffer.
+// Block = 4 warps = 64 queries; per tile of 64 keys K, V and the 127-row window of the position table are staged by
+// cp.async (rows padded to 68 floats: every fragment load below is conflict-free); two blocks per SM overlap each other's
+// loads.  AC and BD' as in the bf16 kernel (64 + 80 MMAs per warp), the same skewed read-back; for P V the accumulator
+// layout of S (a thread's columns 2t, 2t + 1) serves as the A fragment (k indices t, t + 4) by reading V's rows in that
+// permuted key order.  (The CUDA-core kernel took 2.5 ms per layer at B x T = 32 x 500.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kEtQ = 64, kEtK = 64, kEtPitch = 68, kEtWin = 128, kEtBdPitch = 88;
+constexpr int kEtSmem = ((2 * kEtK + kEtWin) * kEtPitch + 4 * 16 * kEtBdPitch) * 4;
+
+__device__ __forceinline__ void enc_mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t enc_tf32_bits(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+__global__ void __launch_bounds__(128, 2) enc_attn_tf32_kernel(const float* __restrict__ qkv, const float* __restrict__ P, int T,
+                                                              const int32_t* __restrict__ lengths, int len_mul,
+                                                              float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char enc_smem[];
+  float* Ks = reinterpret_cast<float*>(enc_smem);
+  float* Vs = Ks + kEtK * kEtPitch;
+  float* Ps = Vs + kEtK * kEtPitch;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kEtQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float* bd_w = Ps + kEtWin * kEtPitch + warp * 16 * kEtBdPitch;
+  const int len = enc_len(lengths, b, len_mul, T);
+  const int R = 2 * T - 1;
+  const float* base = qkv + (size_t)b * T * kEncQkv + h * 64;
+  const float* pbase = P + (size_t)h * R * 64;
+  const int r0 = q0 + 16 * warp + g, r1 = r0 + 8;
+  const int n_tiles = q0 < len ? (len + kEtK - 1) / kEtK : 0;
+  const uint32_t ks_u = (uint32_t)__cvta_generic_to_shared(Ks), vs_u = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t ps_u = (uint32_t)__cvta_generic_to_shared(Ps);
+  // A fragments of (q + u) and (q + v): a0 = (g, t), a1 = (g + 8, t), a2 = (g, t + 4), a3 = (g + 8, t + 4) per k-step of 8
+  uint32_t qu[8][4], qv[8][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float* p0 = base + (size_t)r0 * kEncQkv + 8 * ks + t;
+    const float* p1 = base + (size_t)r1 * kEncQkv + 8 * ks + t;
+    qu[ks][0] = r0 < len ? __float_as_uint(p0[0]) : 0u;   qu[ks][1] = r1 < len ? __float_as_uint(p1[0]) : 0u;
+    qu[ks][2] = r0 < len ? __float_as_uint(p0[4]) : 0u;   qu[ks][3] = r1 < len ? __float_as_uint(p1[4]) : 0u;
+    qv[ks][0] = r0 < len ? __float_as_uint(p0[512]) : 0u; qv[ks][1] = r1 < len ? __float_as_uint(p1[512]) : 0u;
+    qv[ks][2] = r0 < len ? __float_as_uint(p0[516]) : 0u; qv[ks][3] = r1 < len ? __float_as_uint(p1[516]) : 0u;
+  }
+  const float sc2 = 0.125f * 1.4426950408889634f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int wb = 48 - 16 * warp;                             // first window row of this warp's 80-row sub-window
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int k0 = tile * kEtK;
+    __syncthreads();                                         // every warp is done with the previous tile
+    for (int i = threadIdx.x; i < kEtK * 16; i += 128) {     // 64 rows x 16 sixteen-byte words, K and V
+      const int kk = i >> 4, w = i & 15;
+      const int tk = k0 + kk;
+      const bool live = tk < len;
+      const float* kp = base + (size_t)(live ? tk : 0) * kEncQkv + 1024 + 4 * w;
+      const uint32_t off = (uint32_t)(kk * kEtPitch + 4 * w) * 4u;
+      enc_cp16(ks_u + off, kp, live);
+      enc_cp16(vs_u + off, kp + 512, live);
+    }
+    const int rb = (T - 1) - (q0 + kEtQ - 1) + k0;           // window row wl holds table row rb + wl
+    for (int i = threadIdx.x; i < kEtWin * 16; i += 128) {
+      const int wl = i >> 4, w = i & 15;
+      const int r = rb + wl;
+      const bool live = r >= 0 && r < R;
+      enc_cp16(ps_u + (uint32_t)(wl * kEtPitch + 4 * w) * 4u, pbase + (size_t)(live ? r : 0) * 64 + 4 * w, live);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // BD' = (q + v) P_win^T over this warp's 80 window rows, through shared memory
+    {
+      const float* pw = Ps + (wb + g) * kEtPitch + t;        // B fragment: b0 = (k = t, n = g), b1 = (k = t + 4, n = g)
+#pragma unroll
+      for (int n = 0; n < 10; ++n) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          enc_mma_tf32(d, qv[ks], __float_as_uint(pw[(8 * n) * kEtPitch + 8 * ks]), __float_as_uint(pw[(8 * n) * kEtPitch + 8 * ks + 4]));
+        *reinterpret_cast<float2*>(bd_w + g * kEtBdPitch + 8 * n + 2 * t) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2*>(bd_w + (g + 8) * kEtBdPitch + 8 * n + 2 * t) = make_float2(d[2], d[3]);
+      }
+    }
+    float s[8][4];
+    {
+      const float* kw = Ks + g * kEtPitch + t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          enc_mma_tf32(s[j], qu[ks], __float_as_uint(kw[(8 * j) * kEtPitch + 8 * ks]), __float_as_uint(kw[(8 * j) * kEtPitch + 8 * ks + 4]));
+      }
+    }
+    __syncwarp();
+    {
+      const float* ra = bd_w + g * kEtBdPitch + (15 - g) + 2 * t;          // row g:     column 15 - g + jj
+      const float* rc = bd_w + (g + 8) * kEtBdPitch + (7 - g) + 2 * t;     // row g + 8: column 15 - (g + 8) + jj
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j][0] += ra[8 * j]; s[j][1] += ra[8 * j + 1];
+        s[j][2] += rc[8 * j]; s[j][3] += rc[8 * j + 1];
+      }
+    }
+    if (k0 + kEtK > len) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = k0 + 8 * j + 2 * t;
+        if (key >= len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0 * sc2), mn1 = fmaxf(m1, mx1 * sc2);      // finite: the tile holds at least one valid key
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
+      s[j][0] = exp2f(fmaf(s[j][0], sc2, -mn0)); s[j][1] = exp2f(fmaf(s[j][1], sc2, -mn0));
+      s[j][2] = exp2f(fmaf(s[j][2], sc2, -mn1)); s[j][3] = exp2f(fmaf(s[j][3], sc2, -mn1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    {
+      const float* vw = Vs + (2 * t) * kEtPitch + g;         // B fragment in the permuted key order: b0 = row 2t, b1 = row 2t + 1
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {                       // 8 keys per k-step: S tile kk
+        uint32_t pa[4] = {enc_tf32_bits(s[kk][0]), enc_tf32_bits(s[kk][2]), enc_tf32_bits(s[kk][1]), enc_tf32_bits(s[kk][3])};
+#pragma unroll
+        for (int dj = 0; dj < 8; ++dj)
+          enc_mma_tf32(o[dj], pa, __float_as_uint(vw[(8 * kk) * kEtPitch + 8 * dj]), __float_as_uint(vw[(8 * kk + 1) * kEtPitch + 8 * dj]));
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = (r0 < len && l0 > 0.f) ? 1.f / l0 : 0.f, i1 = (r1 < len && l1 > 0.f) ? 1.f / l1 : 0.f;
+#pragma unroll
+  for (int dj = 0; dj < 8; ++dj) {
+    const int c = h * 64 + 8 * dj + 2 * t;
+    if (r0 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + r0) * kEncC + c) = make_float2(round_tf32(o[dj][0] * i0), round_tf32(o[dj][1] * i0));
+    if (r1 < T) *reinterpret_cast<float2*>(out + ((size_t)b * T + r1) * kEncC + c) = make_float2(round_tf32(o[dj][2] * i1), round_tf32(o[dj][3] * i1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void enc_mu_kernel(const float* __restrict__ in, int B, int T, const int32_t* __restrict__ lengths, int len_mul,
                               float* __restrict__ mu) {
   __shared__ float tile[32][81];
@@ -555,7 +720,9 @@ inline int enc_blocks(size_t n, int per_block) {
 
 // Per device (function attributes are per device): called by gnv_flow_enc_create under its device guard.
 cudaError_t flow_enc_init() {
-  return cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
+  cudaError_t e = cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(enc_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEtSmem);
 }
 
 cudaError_t launch_enc_embed(const int32_t* tokens, const int32_t* token_len, const float* table, int vocab, int B, int L,
@@ -598,12 +765,17 @@ cudaError_t launch_enc_pos(const float* w_pos, int T, float* P, void* P_bf16, cu
 
 cudaError_t launch_enc_attn(const void* qkv, const float* P, const void* P_bf16, int B, int T, const int32_t* lengths,
                             int len_mul, void* out_e, int elem_bytes, int round_tf32v, cudaStream_t st) {
-  // bf16: tensor cores (mma.sync); GONOVA_ENC_ATTN_MMA=0 keeps the fp32 CUDA-core kernel (tests run both)
+  // tensor cores (mma.sync bf16 / tf32); GONOVA_ENC_ATTN_MMA=0 keeps the fp32 CUDA-core kernel (tests run both)
   static const bool mma_env = [] { const char* v = getenv("GONOVA_ENC_ATTN_MMA"); return !(v && atoi(v) == 0); }();
   if (elem_bytes == 2 && mma_env && P_bf16) {
     dim3 grid((T + kEmQ - 1) / kEmQ, kEncH, B);
     enc_attn_mma_kernel<<<grid, 128, kEmSmem, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)P_bf16, T, lengths, len_mul,
                                                     (__nv_bfloat16*)out_e);
+    return cudaGetLastError();
+  }
+  if (elem_bytes == 4 && mma_env && round_tf32v) {
+    dim3 grid((T + kEtQ - 1) / kEtQ, kEncH, B);
+    enc_attn_tf32_kernel<<<grid, 128, kEtSmem, st>>>((const float*)qkv, P, T, lengths, len_mul, (float*)out_e);
     return cudaGetLastError();
   }
   dim3 grid((T + kAeQ - 1) / kAeQ, kEncH, B);
