@@ -730,6 +730,35 @@ def main():
                         torch.cuda.empty_cache()
                     except Exception as te:
                         flow_tf32 = {"error": str(te)}
+                # the only pre-existing Blackwell path for this step: stock PyTorch (the engine's nn.Modules, here their oracle
+                # restatement) on the same GPU with cudnn.benchmark + TF32, as synthesizer.py:175-179 configures it
+                flow_stock = None
+                if not args.no_stock_torch:
+                    try:
+                        from oracle import flow_ref as FRs
+                        old_flags = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+                        torch.backends.cudnn.benchmark = True
+                        torch.backends.cuda.matmul.allow_tf32 = True
+                        torch.backends.cudnn.allow_tf32 = True
+                        est_t = FRs.load_estimator(random_flow_state_dict(0)).to(dev).eval()
+                        ones = torch.ones(fB, 1, fT, device=dev)
+                        with torch.inference_mode():
+                            FRs.solve_euler(est_t, fz, fmu, ones, fsp, fcond, n_timesteps=2)
+                            torch.cuda.synchronize(dev)
+                            fe0.record(stream)
+                            FRs.solve_euler(est_t, fz, fmu, ones, fsp, fcond, n_timesteps=10)
+                            fe1.record(stream)
+                            torch.cuda.synchronize(dev)
+                        sms = fe0.elapsed_time(fe1)
+                        flow_stock = {"value": fB * fT / 50.0 / (sms / 1e3), "unit": UNIT, "ms_per_decode": sms, "batch": fB,
+                                      "speedup": sms / fms, "ours_dtype": flow.dtype,
+                                      "what": "solve_euler of the same batch (ten steps, CFG) on the estimator's nn.Modules (oracle "
+                                              "restatement) on cuda:0, eager, cudnn.benchmark + TF32, inputs resident"}
+                        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_flags
+                        del est_t
+                        torch.cuda.empty_cache()
+                    except Exception as se:
+                        flow_stock = {"error": str(se)}
                 # the two drop-ins chained, as S3Gen.inference chains them: flow decoder -> mel -> vocoder -> int16 PCM in
                 # pinned host memory (mu / spks / cond resident: the encoder in front stays the engine's)
                 chain = None
@@ -896,7 +925,7 @@ def main():
                                            "traffic": None,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
-                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "flow_then_vocoder": chain, "front": front_block, "batch_sweep": sweep, "tf32": flow_tf32,
+                              "roofline_kernels": fk, "cpu_baseline": flow_cpu, "stock_torch_gpu": flow_stock, "flow_then_vocoder": chain, "front": front_block, "batch_sweep": sweep, "tf32": flow_tf32,
                               "what": "gnv_flow_decode: mu / spks / cond resident -> mel, ten Euler steps x doubled batch "
                                       "(classifier-free guidance); bf16: between two attention launches (flow_attn_tc_kernel, tcgen05) a "
                                       "transformer block is ONE flow_blk_kernel launch (out-proj + residual + LayerNorm + feed-forward + "

@@ -67,7 +67,7 @@ class EspnetRelPositionalEncoding(nn.Module):
         return torch.cat([pos, neg], dim=1)
 
     def forward(self, x: torch.Tensor):
-        return x * self.xscale, self.position_encoding(x.size(1)).to(x.dtype)
+        return x * self.xscale, self.position_encoding(x.size(1)).to(x.dtype).to(x.device)
 
 
 class LinearNoSubsampling(nn.Module):
@@ -127,7 +127,7 @@ class RelPositionMultiHeadedAttention(nn.Module):
     def rel_shift(x: torch.Tensor) -> torch.Tensor:
         """[B, H, T, 2T-1] indexed by row r of pos_emb -> [B, H, T, T] indexed by key: out[i, j] = x[i, (T-1) - i + j]."""
         b, h, t, n = x.shape
-        zero_pad = torch.zeros((b, h, t, 1), dtype=x.dtype)
+        zero_pad = torch.zeros((b, h, t, 1), dtype=x.dtype, device=x.device)
         x_padded = torch.cat([zero_pad, x], dim=-1).view(b, h, n + 1, t)
         return x_padded[:, :, 1:].view_as(x)[:, :, :, : n // 2 + 1]
 
@@ -216,7 +216,7 @@ class FlowFront(nn.Module):
         """tokens [B, L] (prompt tokens followed by the utterance's) -> mu [B, 80, 2L]; utterance b is encoded alone at
         token_len[b], frames past 2 * token_len[b] are zero."""
         B, L = tokens.shape
-        mu = torch.zeros(B, MEL, UP_STRIDE * L)
+        mu = torch.zeros(B, MEL, UP_STRIDE * L, device=tokens.device)
         for b in range(B):
             n = L if token_len is None else int(token_len[b])
             if n > 0:

@@ -47,7 +47,7 @@ class SinusoidalPosEmb(nn.Module):
     def forward(self, t: torch.Tensor, scale: float = 1000.0) -> torch.Tensor:
         half = self.dim // 2
         emb = math.log(10000) / (half - 1)
-        emb = torch.exp(torch.arange(half, dtype=t.dtype) * -emb)
+        emb = torch.exp(torch.arange(half, dtype=t.dtype, device=t.device) * -emb)
         emb = scale * t[:, None] * emb[None, :]
         return torch.cat([emb.sin(), emb.cos()], dim=-1)
 
@@ -213,7 +213,7 @@ def solve_euler(est: ConditionalDecoder, z: torch.Tensor, mu: torch.Tensor, mask
     """CausalConditionalCFM.solve_euler: the conditioned and the unconditioned estimate come from ONE estimator call on a
     doubled batch (second half: mu, spks, cond zeroed)."""
     B = z.shape[0]
-    t_span = cosine_t_span(n_timesteps).to(z.dtype)
+    t_span = cosine_t_span(n_timesteps).to(z.dtype).to(z.device)       # (device-agnostic: the bench's stock-PyTorch row runs this on cuda)
     x = z.clone()
     t, dt = t_span[0], t_span[1] - t_span[0]
     zeros = torch.zeros_like
