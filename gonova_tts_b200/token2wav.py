@@ -9,12 +9,13 @@ the speaker encoder and the mel extractor that produce `ref_dict`) stays the eng
 sentence (the service caches it per voice, synthesizer.py:238-262)."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from .decoder import B200HiFT, trim_fade_window
-from .flow_front import B200FlowInference
+from .flow import CFG_RATE, N_TIMESTEPS
+from .flow_front import MEL, TOKEN_MEL_RATIO, B200FlowInference
 
 REF_KEYS = ("prompt_token", "prompt_token_len", "prompt_feat", "prompt_feat_len", "embedding")
 
@@ -69,3 +70,61 @@ class B200Token2Wav(torch.nn.Module):
         return wavs, sources
 
     forward = inference
+
+    # ---- many requests at once (SURVEY 8f-4 for the whole tokens -> PCM path; upstream runs one utterance per call) ----
+    @torch.no_grad()
+    def flow_inference_batch(self, requests: Sequence[Tuple[torch.Tensor, Dict[str, torch.Tensor]]],
+                             n_timesteps: int = N_TIMESTEPS) -> List[torch.Tensor]:
+        """[(speech_tokens [n_i] or [1, n_i], ref_dict_i), ...] -> [mel_i [1, 80, frames of request i's new tokens], ...].
+        ONE ragged batch through the encoder and the ten Euler steps: every utterance is encoded and decoded exactly as if it
+        were alone (lengths mask the rest: tests hold the rows against `flow_inference` of each request)."""
+        dev = self.device
+        B = len(requests)
+        if B == 0:
+            return []
+        toks, embs, feats = [], [], []
+        for tokens, ref in requests:
+            t = tokens.reshape(-1).to(dev, torch.int32)
+            toks.append(torch.cat([ref["prompt_token"].reshape(-1).to(dev, torch.int32), t]))
+            embs.append(ref["embedding"].reshape(1, -1).to(dev, torch.float32))
+            feats.append(ref["prompt_feat"].to(dev, torch.float32).reshape(-1, MEL))
+        lens = [int(t.numel()) for t in toks]
+        L = max(lens)
+        tokens = torch.zeros(B, L, dtype=torch.int32, device=dev)
+        for b, t in enumerate(toks):
+            tokens[b, : lens[b]] = t
+        token_len = torch.tensor(lens, dtype=torch.int32, device=dev)
+        mu, spks = self.flow.front.encode(tokens, token_len, torch.cat(embs, dim=0))
+        T = TOKEN_MEL_RATIO * L
+        cond = torch.zeros(B, MEL, T, dtype=torch.float32, device=dev)
+        for b, f in enumerate(feats):
+            cond[b, :, : f.shape[0]] = f.transpose(0, 1)
+        dec = self.flow.decoder
+        if T > dec.rand_noise.shape[2]:
+            raise ValueError("utterance longer than the noise buffer")
+        z = dec.rand_noise[:, :, :T].expand(B, -1, -1).contiguous()     # every utterance starts from the buffer's first frames
+        mel = dec.decode(z, mu, spks, cond, lengths=[TOKEN_MEL_RATIO * n for n in lens], n_timesteps=n_timesteps,
+                         cfg_rate=CFG_RATE)
+        return [mel[b : b + 1, :, feats[b].shape[0] : TOKEN_MEL_RATIO * lens[b]] for b in range(B)]
+
+    @torch.no_grad()
+    def inference_batch(self, requests: Sequence[Tuple[torch.Tensor, Dict[str, torch.Tensor]]],
+                        n_timesteps: int = N_TIMESTEPS) -> List[torch.Tensor]:
+        """The same requests -> [wav_i [1, 480 * frames_i], ...]: one ragged flow batch, then one ragged vocoder batch, then each
+        utterance's own trim_fade."""
+        mels = self.flow_inference_batch(requests, n_timesteps=n_timesteps)
+        if not mels:
+            return []
+        frames = [int(m.shape[2]) for m in mels]
+        Tm = max(frames)
+        batch = torch.zeros(len(mels), MEL, Tm, dtype=torch.float32, device=self.device)
+        for b, m in enumerate(mels):
+            batch[b, :, : frames[b]] = m[0]
+        wavs, _ = self.mel2wav.inference(speech_feat=batch, lengths=frames)
+        out = []
+        for b, n in enumerate(frames):
+            w = wavs[b : b + 1, : 480 * n].clone()
+            k = min(self.trim_fade.shape[0], w.shape[1])
+            w[:, :k] *= self.trim_fade[:k]
+            out.append(w)
+        return out

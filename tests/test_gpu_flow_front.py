@@ -249,3 +249,35 @@ def test_tokens_to_waveform_like_s3gen_inference(lib, cuda_device, sd):
     assert not wav[:, :480].any()                                                     # trim_fade silences the first 20 ms
     with pytest.raises(ValueError, match="ref_dict"):
         t2w.inference(tokens.to(cuda_device))
+
+
+def test_batched_requests_equal_single_requests(lib, cuda_device, sd):
+    """B200Token2Wav.flow_inference_batch / inference_batch: three requests with different token counts, prompts and voices as
+    ONE ragged batch; every mel equals that request's own flow_inference (masking, not approximation), and the waveforms have
+    each request's own length and trim_fade."""
+    from gonova_tts_b200 import B200Token2Wav, random_state_dict
+
+    est_sd = FR.random_state_dict(0)
+    full = {"flow." + k: v for k, v in sd.items()}
+    full.update({"flow.decoder.estimator." + k: v for k, v in est_sd.items()})
+    full.update({"mel2wav." + k: v for k, v in random_state_dict(0, False).items()})
+    t2w = B200Token2Wav.from_state_dict(full, device=cuda_device, dtype="tf32", noise_seed=0)
+    g = torch.Generator().manual_seed(44)
+    reqs = []
+    for n_tok, n_prompt in ((31, 10), (12, 20), (50, 5)):
+        ref = {"prompt_token": torch.randint(0, ER.VOCAB, (1, n_prompt), generator=g, dtype=torch.int32).to(cuda_device),
+               "prompt_token_len": torch.tensor([n_prompt]), "prompt_feat": (torch.randn(1, 2 * n_prompt, 80, generator=g) * 0.5).to(cuda_device),
+               "prompt_feat_len": None, "embedding": torch.randn(1, 192, generator=g).to(cuda_device)}
+        reqs.append((torch.randint(0, ER.VOCAB, (n_tok,), generator=g, dtype=torch.int32).to(cuda_device), ref))
+    mels = t2w.flow_inference_batch(reqs)
+    for (tokens, ref), mel in zip(reqs, mels):
+        alone = t2w.flow_inference(tokens, ref)
+        assert mel.shape == alone.shape == (1, 80, 2 * tokens.numel())
+        snr = snr_db(mel.cpu().numpy(), alone.cpu().numpy())
+        print(f"[parity] batched request ({tokens.numel()} tokens) against the same request alone: SNR {snr:.1f} dB")
+        assert snr >= 50.0
+    wavs = t2w.inference_batch(reqs)
+    for (tokens, _), w in zip(reqs, wavs):
+        assert w.shape == (1, 480 * 2 * tokens.numel()) and torch.isfinite(w).all()
+        assert not w[:, :480].any() and w[:, 960:].abs().max() > 0
+    assert t2w.inference_batch([]) == []
