@@ -195,3 +195,81 @@ def for_decoder(hift, max_batch: int = 64, max_wait_ms: float = 2.0, max_queue: 
 
     return MicroBatcher(decode, max_batch, max_wait_ms, max_queue, pad_frames, workers, pad_batch,
                         per_request_seeds=True)
+
+
+class RequestBatcher:
+    """The same gathering policy for arbitrary requests: `submit(item) -> Future`; ONE worker takes whatever is queued (what
+    arrived while its previous batch was running; it never waits for company, so a lone request starts at once) and calls
+    `batch_fn([item, ...]) -> [result, ...]` (same order, same count).  `for_token2wav` puts the whole tokens -> PCM path behind it (SURVEY 8f-4 one step further up: the
+    reference handles one `generate` at a time, services/tts/server.py:110-186)."""
+
+    def __init__(self, batch_fn: Callable[[list], list], max_batch: int = 32, max_queue: int = 500):
+        if max_batch < 1 or max_queue < 1:
+            raise ValueError("max_batch and max_queue must be positive")
+        self._fn = batch_fn
+        self.max_batch = max_batch
+        self._q: "queue.Queue" = queue.Queue(maxsize=max_queue)
+        self.metrics = {"requests": 0, "dropped": 0, "batches": 0, "largest_batch": 0}
+        self._closed = False
+        self._worker = threading.Thread(target=self._run, name="gonova-request-batcher", daemon=True)
+        self._worker.start()
+
+    def submit(self, item) -> Future:
+        """Like the reference queue, a full queue drops the request: queue.Full is raised and counted."""
+        if self._closed:
+            raise RuntimeError("RequestBatcher is closed")
+        fut: Future = Future()
+        try:
+            self._q.put_nowait((item, fut))
+        except queue.Full:
+            self.metrics["dropped"] += 1
+            raise
+        self.metrics["requests"] += 1
+        return fut
+
+    def close(self, timeout: Optional[float] = 30.0) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        self._q.put(None)
+        self._worker.join(timeout)
+
+    def _run(self) -> None:
+        while True:
+            first = self._q.get()
+            if first is None:
+                return
+            batch = [first]
+            stop = False
+            while len(batch) < self.max_batch:
+                try:
+                    item = self._q.get_nowait()
+                except queue.Empty:
+                    break
+                if item is None:
+                    stop = True
+                    break
+                batch.append(item)
+            live = [(x, f) for x, f in batch if f.set_running_or_notify_cancel()]
+            if live:
+                self.metrics["batches"] += 1
+                self.metrics["largest_batch"] = max(self.metrics["largest_batch"], len(live))
+                try:
+                    results = self._fn([x for x, _ in live])
+                    if len(results) != len(live):
+                        raise RuntimeError(f"batch_fn returned {len(results)} results for {len(live)} requests")
+                    for (_, f), r in zip(live, results):
+                        f.set_result(r)
+                except BaseException as e:      # every caller of the batch sees the failure, the worker survives
+                    for _, f in live:
+                        if not f.done():
+                            f.set_exception(e)
+            if stop:
+                return
+
+
+def for_token2wav(t2w, max_batch: int = 32, max_queue: int = 500) -> RequestBatcher:
+    """Requests `(speech_tokens, ref_dict)` from many connections -> futures of each request's waveform [1, n]; whatever is
+    queued when the GPU becomes free rides in ONE ragged batch (B200Token2Wav.inference_batch): a lone request pays no
+    batching delay, a loaded service gets the batched throughput (2.6 k against 0.24 k audio-s/s one sentence at a time)."""
+    return RequestBatcher(t2w.inference_batch, max_batch=max_batch, max_queue=max_queue)

@@ -141,3 +141,54 @@ def test_pad_batch_adds_silent_rows_only():
     mb.close()
     assert [s[0] for s, _ in dec.batches] == [1, 8]                          # a lone request stays alone, 5 -> 8 rows
     assert dec.batches[0][1] == [2] and dec.batches[1][1] == [3] * 5 + [0] * 3
+
+
+def test_request_batcher_batches_what_queues_up_and_keeps_order():
+    """RequestBatcher (the gathering policy for whole tokens -> PCM requests): while one batch runs, arrivals pile up and ride
+    together in the next one; results go back to the right caller; a failure reaches every caller of that batch; a full queue
+    drops the request like the reference's."""
+    import queue as _q
+    import threading
+    import time
+
+    from gonova_tts_b200.batching import RequestBatcher
+
+    seen = []
+    gate = threading.Event()
+
+    def fn(items):
+        seen.append(list(items))
+        if len(seen) == 1:
+            gate.wait(5)                                # the first batch holds the "GPU" while the others arrive
+        if any(i < 0 for i in items):
+            raise ValueError("bad request")
+        return [i * 10 for i in items]
+
+    rb = RequestBatcher(fn, max_batch=4, max_queue=6)
+    first = rb.submit(1)
+    time.sleep(0.05)
+    rest = [rb.submit(i) for i in (2, 3, 4, 5, 6, 7)]    # 6 queued behind the running batch: the queue is now full
+    try:
+        rb.submit(8)
+        raise AssertionError("a full queue must drop")
+    except _q.Full:
+        pass
+    gate.set()
+    assert first.result(5) == 10
+    assert [f.result(5) for f in rest] == [20, 30, 40, 50, 60, 70]
+    assert seen[0] == [1] and seen[1] == [2, 3, 4, 5] and seen[2] == [6, 7]
+    bad = [rb.submit(-1), rb.submit(9)]
+    for f in bad:
+        try:
+            f.result(5)
+        except ValueError:
+            continue
+        # (the two may have landed in different batches: then the second one succeeds)
+        assert f.result(5) == 90
+    rb.close()
+    assert rb.metrics["dropped"] == 1 and rb.metrics["largest_batch"] == 4 and rb.metrics["requests"] == 9
+    try:
+        rb.submit(1)
+        raise AssertionError("closed")
+    except RuntimeError:
+        pass

@@ -281,3 +281,26 @@ def test_batched_requests_equal_single_requests(lib, cuda_device, sd):
         assert w.shape == (1, 480 * 2 * tokens.numel()) and torch.isfinite(w).all()
         assert not w[:, :480].any() and w[:, 960:].abs().max() > 0
     assert t2w.inference_batch([]) == []
+
+
+def test_request_batcher_over_tokens_to_pcm(lib, cuda_device, sd):
+    """batching.for_token2wav: concurrent (tokens, ref_dict) requests come back as each caller's own waveform."""
+    from gonova_tts_b200 import B200Token2Wav, random_state_dict
+    from gonova_tts_b200.batching import for_token2wav
+
+    full = {"flow." + k: v for k, v in sd.items()}
+    full.update({"flow.decoder.estimator." + k: v for k, v in FR.random_state_dict(0).items()})
+    full.update({"mel2wav." + k: v for k, v in random_state_dict(0, False).items()})
+    t2w = B200Token2Wav.from_state_dict(full, device=cuda_device, dtype="bf16", noise_seed=0)
+    g = torch.Generator().manual_seed(45)
+    ref = {"prompt_token": torch.randint(0, ER.VOCAB, (1, 8), generator=g, dtype=torch.int32).to(cuda_device), "prompt_token_len": None,
+           "prompt_feat": (torch.randn(1, 16, 80, generator=g) * 0.5).to(cuda_device), "prompt_feat_len": None,
+           "embedding": torch.randn(1, 192, generator=g).to(cuda_device)}
+    rb = for_token2wav(t2w, max_batch=8)
+    counts = [20, 7, 33, 12, 25]
+    futs = [rb.submit((torch.randint(0, ER.VOCAB, (n,), generator=g, dtype=torch.int32).to(cuda_device), ref)) for n in counts]
+    for n, f in zip(counts, futs):
+        w = f.result(120)
+        assert w.shape == (1, 480 * 2 * n) and torch.isfinite(w).all() and not w[:, :480].any()
+    rb.close()
+    assert rb.metrics["requests"] == 5 and rb.metrics["batches"] <= 5
