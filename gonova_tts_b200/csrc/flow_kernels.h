@@ -8,9 +8,10 @@ namespace gnv {
 struct FlowTimes { float t[32]; };      // the Euler grid, passed by value (no copy, no synchronisation)
 
 // tb[s][r][256] = Linear_r(Mish(time_mlp(sinusoidal(t_steps[s]))))  for every Euler step s and ResNet block r
+// (scratch: 2 * n_steps * 1024 floats)
 cudaError_t launch_flow_time(const FlowTimes& t_steps, int n_steps, const float* w1, const float* b1, const float* w2,
-                             const float* b2, const float* const* wr, const float* const* br, int n_res, float* tb,
-                             cudaStream_t st);
+                             const float* b2, const float* const* wr, const float* const* br, int n_res, float* scratch,
+                             float* tb, cudaStream_t st);
 // z / mu / cond [B,80,T], spks [B,80] -> x_state [B,T,80] fp32 and X0 [2B,T,320] (E)
 cudaError_t launch_flow_pack(const float* z, const float* mu, const float* spks, const float* cond, const int* lengths,
                              int B, int T, float* x_state, void* X0, int elem_bytes, cudaStream_t st);
