@@ -909,6 +909,15 @@ def main():
                     flow_cpu = {"value": 100 / 50.0 / (dtc * 5.0), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"1 utterance x 100 frames, 2 of the 10 Euler steps in {dtc:.2f} s (x5 for the full "
                                           "solve), fp32 torch CPU oracle (oracle/flow_ref.py)"}
+                # DRAM bytes of one estimator evaluation from the committed ncu launch list (valid for this default shape)
+                flow_traffic, flow_traffic_src = None, None
+                try:
+                    with open(os.path.join(ROOT, "profiles", "r02_flow_traffic.json")) as tf_:
+                        tjf = json.load(tf_)
+                    if (fB, fT, flow.dtype) == (32, 500, "bf16"):
+                        flow_traffic, flow_traffic_src = tjf["traffic_bytes_per_evaluation"], tjf["source"]
+                except Exception:
+                    pass
                 flow_block = {"value": fB * fT / 50.0 / (fms / 1e3), "unit": UNIT, "ms_per_decode": fms, "batch": fB, "frames": fT,
                               "dtype": flow.dtype, "n_timesteps": 10, "cfg_rate": 0.7, "gpu_launches": flow.launches(10),
                               "algorithmic_tflops": gemm_flops / (fms / 1e3) / 1e12,
@@ -922,7 +931,7 @@ def main():
                                            "achieved": tens_fl / (tens_ms / 1e3) / 1e12 if tens_ms else 0.0, "peak": f_peak,
                                            "unit": "TFLOP/s",
                                            "frac": (tens_fl / (tens_ms / 1e3) / 1e12 / f_peak) if (f_peak and tens_ms) else None,
-                                           "traffic": None,
+                                           "traffic": flow_traffic, "traffic_source": flow_traffic_src,
                                            "how": "algorithmic FLOPs of the projections, convs and attention (4 B2 H T^2 d) / summed "
                                                   "per-launch CUDA-event time of those launches in one evaluation"},
                               "roofline_kernels": fk, "cpu_baseline": flow_cpu, "stock_torch_gpu": flow_stock, "flow_then_vocoder": chain, "front": front_block, "batch_sweep": sweep, "tf32": flow_tf32,
