@@ -588,27 +588,42 @@ __global__ void __launch_bounds__(128, 2) enc_attn_tf32_kernel(const float* __re
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // BD' = (q + v) P_win^T over this warp's 80 window rows, through shared memory
+    // (B fragments of two k-steps per ldmatrix.x4: an 8 x 8 b16 matrix is 8 rows x 4 floats and thread i receives the 32-bit
+    //  word (row i / 4, word i % 4) — b0 = (k = t, n = g), b1 = (k = t + 4, n = g) of m16n8k8)
+    const uint32_t ld_lane = (uint32_t)(((lane & 7) * kEtPitch + 4 * (lane >> 3)) * 4);
     {
-      const float* pw = Ps + (wb + g) * kEtPitch + t;        // B fragment: b0 = (k = t, n = g), b1 = (k = t + 4, n = g)
+      const uint32_t pw = ps_u + (uint32_t)(wb * kEtPitch * 4) + ld_lane;
 #pragma unroll
       for (int n = 0; n < 10; ++n) {
         float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          enc_mma_tf32(d, qv[ks], __float_as_uint(pw[(8 * n) * kEtPitch + 8 * ks]), __float_as_uint(pw[(8 * n) * kEtPitch + 8 * ks + 4]));
+        for (int kp = 0; kp < 4; ++kp) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(pw + (uint32_t)((8 * n * kEtPitch + 16 * kp) * 4)));
+          enc_mma_tf32(d, qv[2 * kp], b0, b1);
+          enc_mma_tf32(d, qv[2 * kp + 1], b2, b3);
+        }
         *reinterpret_cast<float2*>(bd_w + g * kEtBdPitch + 8 * n + 2 * t) = make_float2(d[0], d[1]);
         *reinterpret_cast<float2*>(bd_w + (g + 8) * kEtBdPitch + 8 * n + 2 * t) = make_float2(d[2], d[3]);
       }
     }
     float s[8][4];
     {
-      const float* kw = Ks + g * kEtPitch + t;
+      const uint32_t kw = ks_u + ld_lane;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          enc_mma_tf32(s[j], qu[ks], __float_as_uint(kw[(8 * j) * kEtPitch + 8 * ks]), __float_as_uint(kw[(8 * j) * kEtPitch + 8 * ks + 4]));
+        for (int kp = 0; kp < 4; ++kp) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(kw + (uint32_t)((8 * j * kEtPitch + 16 * kp) * 4)));
+          enc_mma_tf32(s[j], qu[2 * kp], b0, b1);
+          enc_mma_tf32(s[j], qu[2 * kp + 1], b2, b3);
+        }
       }
     }
     __syncwarp();

@@ -593,13 +593,20 @@ __global__ void __launch_bounds__(128) flow_attn_tf32_kernel(const float* __rest
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+    // B fragments of two k-steps per ldmatrix.x4: an 8 x 8 b16 matrix is 8 keys x 16 bytes = 4 floats, and thread i receives
+    // the 32-bit word (row i / 4, word i % 4) = K[key g][4 floats' column t]: exactly b0 / b1 of m16n8k8 (four scalar loads
+    // per MMA pair otherwise: the kernel was bound by shared-memory instructions)
+    const uint32_t k_lane = (uint32_t)__cvta_generic_to_shared(Kt) + (uint32_t)(((lane & 7) * kAtPitch + 4 * (lane >> 3)) * 4);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t b0 = __float_as_uint(Kt[(8 * j + g) * kAtPitch + 8 * ks + t]);
-        const uint32_t b1 = __float_as_uint(Kt[(8 * j + g) * kAtPitch + 8 * ks + t + 4]);
-        mma_tf32_1688(s[j], qa[ks], b0, b1);
+      for (int kp = 0; kp < 4; ++kp) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(k_lane + (uint32_t)((8 * j * kAtPitch + 16 * kp) * 4)));
+        mma_tf32_1688(s[j], qa[2 * kp], b0, b1);
+        mma_tf32_1688(s[j], qa[2 * kp + 1], b2, b3);
       }
     }
     if (k0 + kAtK > len) {
