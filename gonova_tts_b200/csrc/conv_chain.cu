@@ -17,6 +17,7 @@ cudaError_t conv_chain_init() {
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
   const auto set = [](auto kernel) {
+    preload_kernel((const void*)kernel);
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmemChain);
   };
   if ((e = set(conv_chain_kernel<__nv_bfloat16, 64, false>)) != cudaSuccess) return e;

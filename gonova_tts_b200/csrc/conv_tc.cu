@@ -22,6 +22,21 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+void preload_kernel(const void* kernel) {
+  typedef CUresult (*PFN_funcLoad)(CUfunction);
+  static PFN_funcLoad fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuFuncLoad", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<PFN_funcLoad>(p);
+    return static_cast<PFN_funcLoad>(nullptr);
+  }();
+  if (!fn) return;
+  cudaFunction_t f = nullptr;
+  if (cudaGetFuncBySymbol(&f, kernel) == cudaSuccess && f) fn(reinterpret_cast<CUfunction>(f));
+  cudaGetLastError();                                        // (best effort: never leaves an error behind)
+}
+
 static constexpr size_t kMaxDynSmem = 227 * 1024;
 
 static uint32_t* g_dbg_host = nullptr;
@@ -52,6 +67,8 @@ cudaError_t conv_tc_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
+  preload_kernel((const void*)conv_tc_kernel<__nv_bfloat16>);
+  preload_kernel((const void*)conv_tc_kernel<float>);
   e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kMaxDynSmem);
   if (e != cudaSuccess) return e;

@@ -240,6 +240,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();   // resolved through cudaGetDriverEntryPoint (no libcuda link)
+// Lazy module loading (the CUDA 12 default) defers a kernel's load to its FIRST LAUNCH: 0.1-0.5 s for the large persistent
+// kernels, in the middle of whichever request first needs that variant (measured: tools/t2w_plan_cost.py).  The *_init()
+// functions call this for every kernel they configure, so a handle's kernels are resident when its create call returns.
+// cuFuncLoad through cudaGetDriverEntryPoint; a no-op on drivers without it.
+void preload_kernel(const void* kernel);
 
 struct ConvTcLaunch {
   CUtensorMap tmA, tmW;

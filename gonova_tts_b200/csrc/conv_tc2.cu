@@ -34,6 +34,7 @@ cudaError_t conv_tc2_init() {
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
   const auto set = [](auto kernel) {
+    preload_kernel((const void*)kernel);
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem2);
   };
   if ((e = set(conv_tc2_kernel<__nv_bfloat16, false, false>)) != cudaSuccess) return e;

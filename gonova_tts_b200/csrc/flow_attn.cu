@@ -15,6 +15,7 @@ cudaError_t flow_attn_init() {
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
+  preload_kernel((const void*)flow_attn_tc_kernel<0>);
   return cudaFuncSetAttribute(flow_attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFaMaxDynSmem);
 }
 

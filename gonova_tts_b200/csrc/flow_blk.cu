@@ -16,6 +16,7 @@ cudaError_t flow_blk_init() {
   e = cudaMemcpyToSymbol(tc::g_tc_debug, &dptr, sizeof(dptr));
   if (e != cudaSuccess) return e;
   const auto set = [](auto kernel) {
+    preload_kernel((const void*)kernel);
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFbMaxDynSmem);
   };
   if ((e = set(flow_blk_kernel<FB_FF>)) != cudaSuccess) return e;

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "flow_enc_kernels.h"
 
+namespace gnv { void preload_kernel(const void* kernel); }   // conv_tc.cu
+
 namespace gnv {
 
 namespace {
@@ -735,6 +737,8 @@ inline int enc_blocks(size_t n, int per_block) {
 
 // Per device (function attributes are per device): called by gnv_flow_enc_create under its device guard.
 cudaError_t flow_enc_init() {
+  preload_kernel((const void*)enc_attn_mma_kernel);
+  preload_kernel((const void*)enc_attn_tf32_kernel);
   cudaError_t e = cudaFuncSetAttribute(enc_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmSmem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(enc_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEtSmem);

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "flow_kernels.h"
 
+namespace gnv { void preload_kernel(const void* kernel); }   // conv_tc.cu
+
 namespace gnv {
 
 __device__ __forceinline__ float mish_f(float x) {
@@ -664,6 +666,8 @@ __global__ void __launch_bounds__(128) flow_attn_tf32_kernel(const float* __rest
 
 // Per device (function attributes are per device): called by gnv_flow_create under its device guard.
 cudaError_t flow_kernels_init() {
+  preload_kernel((const void*)flow_attn_tf32_kernel);
+  preload_kernel((const void*)flow_attn_mma_kernel);
   return cudaFuncSetAttribute(flow_attn_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem);
 }
 

@@ -72,12 +72,19 @@ class B200Token2Wav(torch.nn.Module):
     forward = inference
 
     # ---- many requests at once (SURVEY 8f-4 for the whole tokens -> PCM path; upstream runs one utterance per call) ----
+    @staticmethod
+    def _rows(n: int, pad_pow2: bool) -> int:
+        return 1 << (n - 1).bit_length() if pad_pow2 and n > 1 else n
+
     @torch.no_grad()
     def flow_inference_batch(self, requests: Sequence[Tuple[torch.Tensor, Dict[str, torch.Tensor]]],
-                             n_timesteps: int = N_TIMESTEPS) -> List[torch.Tensor]:
+                             n_timesteps: int = N_TIMESTEPS, pad_tokens: int = 16, pad_batch_pow2: bool = True) -> List[torch.Tensor]:
         """[(speech_tokens [n_i] or [1, n_i], ref_dict_i), ...] -> [mel_i [1, 80, frames of request i's new tokens], ...].
         ONE ragged batch through the encoder and the ten Euler steps: every utterance is encoded and decoded exactly as if it
-        were alone (lengths mask the rest: tests hold the rows against `flow_inference` of each request)."""
+        were alone (lengths mask the rest: tests hold the rows against `flow_inference` of each request).
+        pad_tokens / pad_batch_pow2: the batch is padded to a multiple of `pad_tokens` tokens and to a power-of-two number of
+        rows (zero-length rows, skipped by every kernel), so that a service's batches fall on few distinct (rows, length)
+        shapes and find their launch plans built."""
         dev = self.device
         B = len(requests)
         if B == 0:
@@ -89,38 +96,44 @@ class B200Token2Wav(torch.nn.Module):
             embs.append(ref["embedding"].reshape(1, -1).to(dev, torch.float32))
             feats.append(ref["prompt_feat"].to(dev, torch.float32).reshape(-1, MEL))
         lens = [int(t.numel()) for t in toks]
-        L = max(lens)
-        tokens = torch.zeros(B, L, dtype=torch.int32, device=dev)
+        L = -(-max(lens) // max(1, pad_tokens)) * max(1, pad_tokens)
+        rows = self._rows(B, pad_batch_pow2)
+        tokens = torch.zeros(rows, L, dtype=torch.int32, device=dev)
         for b, t in enumerate(toks):
             tokens[b, : lens[b]] = t
-        token_len = torch.tensor(lens, dtype=torch.int32, device=dev)
-        mu, spks = self.flow.front.encode(tokens, token_len, torch.cat(embs, dim=0))
+        lens_all = lens + [0] * (rows - B)
+        token_len = torch.tensor(lens_all, dtype=torch.int32, device=dev)
+        emb = torch.zeros(rows, embs[0].shape[1], dtype=torch.float32, device=dev)
+        emb[:B] = torch.cat(embs, dim=0)
+        mu, spks = self.flow.front.encode(tokens, token_len, emb)
         T = TOKEN_MEL_RATIO * L
-        cond = torch.zeros(B, MEL, T, dtype=torch.float32, device=dev)
+        cond = torch.zeros(rows, MEL, T, dtype=torch.float32, device=dev)
         for b, f in enumerate(feats):
             cond[b, :, : f.shape[0]] = f.transpose(0, 1)
         dec = self.flow.decoder
         if T > dec.rand_noise.shape[2]:
             raise ValueError("utterance longer than the noise buffer")
-        z = dec.rand_noise[:, :, :T].expand(B, -1, -1).contiguous()     # every utterance starts from the buffer's first frames
-        mel = dec.decode(z, mu, spks, cond, lengths=[TOKEN_MEL_RATIO * n for n in lens], n_timesteps=n_timesteps,
+        z = dec.rand_noise[:, :, :T].expand(rows, -1, -1).contiguous()  # every utterance starts from the buffer's first frames
+        mel = dec.decode(z, mu, spks, cond, lengths=[TOKEN_MEL_RATIO * n for n in lens_all], n_timesteps=n_timesteps,
                          cfg_rate=CFG_RATE)
         return [mel[b : b + 1, :, feats[b].shape[0] : TOKEN_MEL_RATIO * lens[b]] for b in range(B)]
 
     @torch.no_grad()
     def inference_batch(self, requests: Sequence[Tuple[torch.Tensor, Dict[str, torch.Tensor]]],
-                        n_timesteps: int = N_TIMESTEPS) -> List[torch.Tensor]:
+                        n_timesteps: int = N_TIMESTEPS, pad_tokens: int = 16, pad_frames: int = 32,
+                        pad_batch_pow2: bool = True) -> List[torch.Tensor]:
         """The same requests -> [wav_i [1, 480 * frames_i], ...]: one ragged flow batch, then one ragged vocoder batch, then each
         utterance's own trim_fade."""
-        mels = self.flow_inference_batch(requests, n_timesteps=n_timesteps)
+        mels = self.flow_inference_batch(requests, n_timesteps=n_timesteps, pad_tokens=pad_tokens, pad_batch_pow2=pad_batch_pow2)
         if not mels:
             return []
         frames = [int(m.shape[2]) for m in mels]
-        Tm = max(frames)
-        batch = torch.zeros(len(mels), MEL, Tm, dtype=torch.float32, device=self.device)
+        Tm = -(-max(frames) // max(1, pad_frames)) * max(1, pad_frames)
+        rows = self._rows(len(mels), pad_batch_pow2)
+        batch = torch.zeros(rows, MEL, Tm, dtype=torch.float32, device=self.device)
         for b, m in enumerate(mels):
             batch[b, :, : frames[b]] = m[0]
-        wavs, _ = self.mel2wav.inference(speech_feat=batch, lengths=frames)
+        wavs, _ = self.mel2wav.inference(speech_feat=batch, lengths=frames + [0] * (rows - len(mels)))
         out = []
         for b, n in enumerate(frames):
             w = wavs[b : b + 1, : 480 * n].clone()
